@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py - DQN gradient-steps/s of the batch_train! hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          our engine (one process per GPU under torchrun)
+    python bench.py --impl reference ...                   the reference's CPU path (torch-CPU restatement, oracle/)
+
+Workload (N=1): BASELINE.json configs[2] - synthetic Atari-shaped uint8 observations 84x84x4, Nature-DQN conv trunk
++ dueling heads (|A|=6), batch 256, 1M-transition prioritized replay shard resident in HBM, double-Q + PER.
+A "step" is one full batch_train!: sum-tree sample, gather, 3 forwards, fused head, reverse pass, Adam, priority
+write-back.  Under N>1 every rank owns a private 1M shard and the gradient bucket is all-reduced (weak scaling).
+One JSON line is printed by rank 0."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "dqn_gradient_steps_per_sec"
+UNIT = "steps/s"
+TRAIN_FREQ = 4          # env steps per gradient step (src/solver.jl:6) => transitions ingested per e2e step
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.rows, self.proc, self.dev = [], None, dev
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.dev)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    """Control plane only (id broadcast, barrier, max over ranks); the gradient all-reduce is NCCL inside the engine."""
+    if n <= 1 or "RANK" not in os.environ:
+        return None, 0, 1, 0
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo")
+    return dist, dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def c3_layers(lib):
+    import util
+    return util.layer_descs(util.SPECS["c3_conv"]), util.SPECS["c3_conv"]
+
+
+def run_reference(args):
+    """The reference's CPU path on this box's host cores (Flux-equivalent restatement, torch-CPU, all threads)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import util
+    from oracle.cpu_baseline import CpuBaseline
+    spec = util.SPECS["c3_conv"]
+    cb = CpuBaseline(spec["layers"], spec["obs"], spec["nA"], 256, args.buffer, True, store_rows=4096)
+    ts = cb.time_steps(args.steps, args.warmup)
+    total = float(np.sum(ts))
+    v = args.steps / total
+    sample = f"{args.steps} full steps (B=256, O(N) sampling over N={args.buffer} priorities; observation store bounded to 4096 rows, index mod 4096)"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": workload_config(args, 1),
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cb.threads, "kind": "port", "sample": sample,
+                                       "label": "Flux-equivalent CPU restatement (torch-CPU); Julia is not installed in this image"},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE.json configs[2]: synthetic Atari-shaped obs 84x84x4 (u8), Nature-DQN conv + dueling, |A|=6, batch 256/GPU, "
+                        f"{args.buffer}-transition PER shard/GPU, double-Q, Adam lr 1e-4",
+            "batch_per_gpu": 256, "buffer_per_gpu": args.buffer, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2: every step gathers 14.5 MB of fresh rows from a 56 GB store and streams 92 MB of optimizer state",
+            "math": args.math}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--buffer", type=int, default=1_000_000)
+    ap.add_argument("--math", default=os.environ.get("DQN_MATH", "auto"), choices=["auto", "fp32", "3xtf32"])
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import dqn_b200 as lib
+    import util
+    dist, rank, world, local = dist_setup(args.gpus)
+    peaks = load_peaks()
+    spec = util.SPECS["c3_conv"]
+    nccl_id = None
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(lib.nccl_unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.tolist())
+    math_mode = {"auto": lib.MATH_3XTF32 if os.environ.get("DQN_DEFAULT_TC", "0") == "1" else lib.MATH_FP32, "fp32": lib.MATH_FP32, "3xtf32": lib.MATH_3XTF32}[args.math]
+    args.math = "3xtf32 (tcgen05 kind::tf32, 3-pass split)" if math_mode == lib.MATH_3XTF32 else "fp32 (CUDA-core FMA)"
+    cfg = lib.make_config(util.layer_descs(spec), (84, 84, 4), 6, obs_dtype="u8", batch_size=256, buffer_size=args.buffer, learning_rate=1e-4,
+                          discount=0.99, seed=2 + rank, device=local, math_mode=math_mode, use_graph=not args.no_graph, rank=rank, world=world, nccl_id=nccl_id)
+    eng = lib.Engine(cfg)
+    net = util.make_oracle_net(spec, True, seed=1)                 # glorot-uniform weights from seed 1 (same on every rank)
+    import oracle as O
+    theta = O.flat_params(net)
+    eng.set_params(theta, 0)
+    eng.sync_target()
+    eng.replay_fill_synthetic(args.buffer, seed=1000 + rank)       # per-GPU shard
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    # ---- device-resident throughput (value) ------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.train_step_async()
+    eng.sync()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.train_step_async()
+    ms = eng.timer_stop()
+    loss, gn = eng.sync()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    if dist:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    launches = eng.launches_per_step() * args.steps
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public call with host buffers (e2e) -------------------------------
+    #   per gradient step: add_exp! of train_freq=4 fresh transitions from pinned host memory (H2D), batch_train!, read (loss, grad_norm) (D2H)
+    s_h = lib._capi.pinned_empty((TRAIN_FREQ, 4, 84, 84), np.uint8)
+    sp_h = lib._capi.pinned_empty((TRAIN_FREQ, 4, 84, 84), np.uint8)
+    rng = np.random.default_rng(5 + rank)
+    s_h[...] = rng.integers(0, 256, s_h.shape, dtype=np.uint8)
+    sp_h[...] = rng.integers(0, 256, sp_h.shape, dtype=np.uint8)
+    a_h = rng.integers(1, 7, TRAIN_FREQ).astype(np.int32)
+    r_h = rng.uniform(-1, 1, TRAIN_FREQ).astype(np.float32)
+    d_h = np.zeros(TRAIN_FREQ, np.uint8)
+    td_h = np.abs(r_h)
+    h2d = int(s_h.nbytes + sp_h.nbytes + a_h.nbytes + r_h.nbytes + d_h.nbytes + td_h.nbytes)
+    for _ in range(args.warmup):
+        eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
+        eng.train_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
+        loss, gn = eng.train_step()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e = world * args.steps / e2e_s
+
+    # ---- per-kernel timing (eager launches bracketed by CUDA events on the engine's stream) -> roofline ---
+    roof, kernels = None, None
+    if rank == 0:
+        eng.set_profiling(1)
+        for _ in range(10):
+            eng.train_step_async()
+        eng.sync()
+        prof = eng.get_profile()
+        eng.set_profiling(0)
+        tot = sum(k["ms"] * 1 for k in prof)
+        kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"])][:12]
+        top = max(prof, key=lambda k: k["ms"])
+        if top["flops"] > 0:
+            tf32_peak = 0.5 * peaks["bf16_sus"]
+            ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                    "peak_note": f"dense TF32 = 1/2 of the {peaks['src']} sustained bf16 cuBLAS peak ({peaks['bf16_sus']} TFLOP/s); algorithmic FLOPs of the launch"}
+        else:
+            ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                    "peak_note": f"{peaks['src']} HBM copy bandwidth"}
+        step_flops = 26.36e9
+        roof["step_tflops_algorithmic"] = step_flops * (args.steps / (ms * 1e-3)) / 1e12
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) --------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.cpu_baseline import CpuBaseline
+        cb = CpuBaseline(spec["layers"], spec["obs"], spec["nA"], 256, args.buffer, True, store_rows=4096)
+        ts = cb.time_steps(args.cpu_steps, 3)
+        cpu = {"value": 1.0 / float(np.median(ts)), "unit": UNIT, "cores": cb.threads, "kind": "port",
+               "sample": f"median of {args.cpu_steps} full steps after 3 warm-ups (B=256, O(N) sampling over N={args.buffer}; obs store bounded to 4096 rows)",
+               "label": "Flux-equivalent CPU restatement (torch-CPU); Julia is not installed in this image"}
+
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": workload_config(args, world),
+                          "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                                  "what": f"per step: add_exp! x{TRAIN_FREQ} from pinned host memory + batch_train! + (loss, grad_norm) read back; wall clock"},
+                          "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+                          "last_loss": loss, "last_grad_norm": gn}))
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

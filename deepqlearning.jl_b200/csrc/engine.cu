@@ -1,0 +1,1005 @@
+// engine.cu - host side of libdqn_b200.so: handle lifecycle, HBM layout, the step schedule (eager or one
+// CUDA graph), parameter import/export in Flux order, and the C-ABI of include/dqn_b200.h.
+//
+// The step (dqn_train_step) is the reference's batch_train! (src/solver.jl:191-236):
+//   sample -> gather -> online forward on [s ; s'] -> target forward on s' -> fused head (dueling, Double-Q,
+//   Bellman target, IS-Huber, dQ, td, new priorities) -> reverse pass -> [NCCL all-reduce] -> fused Adam +
+//   max|g| -> sum-tree refresh -> publish (loss, grad_norm).
+// There is no CPU fallback anywhere in this file: every numerical result is produced by a kernel launch.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dqn_b200.h"
+#include "igemm.cuh"
+#include "kernels.cuh"
+#include "tc_gemm.cuh"
+
+using namespace dqn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Err {
+  int code; std::string msg;
+};
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess) throw Err{DQN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)}; \
+  } while (0)
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  throw Err{code, buf};
+}
+
+// ---- NCCL through dlopen: the library resolves the NCCL already loaded in the process (torch's), else the system one.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& why) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { why = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+struct Mat { long long off; int K, N, act; };        // augmented matrix [(K+1)][N] at theta + off
+struct ConvL { ConvGeom g; Mat w; };
+
+struct ProfRec { cudaEvent_t a, b; std::string name; double flops, bytes; };
+
+constexpr int MAXD = DQN_MAX_LAYERS;
+
+struct ActBufs {
+  std::vector<float*> conv_out;
+  float* tow_out[2][MAXD] = {};
+};
+
+}  // namespace
+
+struct dqn_engine {
+  dqn_config_t cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  int nsm = 148;
+  // topology
+  std::vector<ConvL> convs;
+  int hwc = 0;                     // 1: observations stored H,W,C (conv trunk), 0: flat in Flux order
+  long long obs_elems = 0, obs_row_bytes = 0; int elem_bytes = 4;
+  int feat = 0;                    // trunk output features (== obs_elems when there is no trunk)
+  int ntow = 1, depth = 0;
+  Mat tow[2][MAXD];
+  long long nflux = 0, nint = 0;   // Flux parameter count, internal (padded) float count
+  std::vector<long long> perm;     // Flux flat index -> internal index
+  // parameters / optimiser state
+  float *theta = nullptr, *theta_t = nullptr, *adam_m = nullptr, *adam_v = nullptr, *grad = nullptr;
+  // replay
+  long long cap = 0, cursor = 0, curr_size = 0; int P = 0;
+  uint8_t *store_s = nullptr, *store_sp = nullptr, *done = nullptr;
+  int* act = nullptr; float* rew = nullptr; float* tree = nullptr;
+  DevState* st = nullptr;
+  // batch
+  int B = 0, rows_on = 0;
+  long long* idx_d = nullptr; uint8_t* xb = nullptr;
+  int* a_b = nullptr; float *r_b = nullptr, *d_b = nullptr, *w_b = nullptr;
+  ActBufs on, tg;
+  std::vector<float*> conv_delta; float* tow_delta[2][MAXD] = {};
+  float *q_s = nullptr, *q_sp_on = nullptr, *q_sp_tg = nullptr, *y = nullptr, *td = nullptr, *newp = nullptr; int* best_a = nullptr;
+  float* ws = nullptr; long long ws_floats = 0;
+  // staging for host I/O
+  uint8_t* stage = nullptr; long long stage_bytes = 0;
+  float* host_out = nullptr; float* host_out_dev = nullptr;   // mapped pinned: loss, grad_norm, error
+  long long* idx_h = nullptr;                                  // pinned
+  // graph
+  cudaGraphExec_t graph_sample = nullptr, graph_idx = nullptr;
+  // nccl
+  ncclComm_t comm = nullptr;
+  // measurement
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  int counting = 0, launches = 0, launches_per_step = 0;
+  int profiling = 0; std::vector<ProfRec> prof; std::vector<cudaEvent_t> ev_pool;
+  uint32_t* flush_buf = nullptr; long long flush_n = 0;
+  bool capturing = false;
+};
+
+namespace {
+
+using E = dqn_engine;
+
+template <class T> T* dalloc(long long n) {
+  T* p = nullptr;
+  CK(cudaMalloc(&p, std::max<long long>(n, 1) * sizeof(T)));
+  CK(cudaMemset(p, 0, std::max<long long>(n, 1) * sizeof(T)));
+  return p;
+}
+
+// ---- launch bookkeeping -------------------------------------------------------------------------
+struct Scope {
+  E* e; bool on;
+  Scope(E* e_, const char* name, double flops, double bytes) : e(e_), on(e_->profiling && !e_->capturing) {
+    if (e->counting) e->launches++;
+    if (on) {
+      ProfRec r; r.name = name; r.flops = flops; r.bytes = bytes;
+      CK(cudaEventCreate(&r.a)); CK(cudaEventCreate(&r.b));
+      CK(cudaEventRecord(r.a, e->stream));
+      e->prof.push_back(r);
+    }
+  }
+  ~Scope() { if (on) cudaEventRecord(e->prof.back().b, e->stream); }
+};
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- fp32 implicit-GEMM launch ------------------------------------------------------------------
+template <class Op>
+void launch_igemm(E* e, const char* name, Op a, Op b, int nz, bool allow_split, double flops, double bytes) {
+  Op a0 = a;
+  if (Op::Z_IS_CLASS) a0.set_class(0);
+  int M = a0.M, N = a0.N, K = a0.K;
+  if (!Op::Z_IS_CLASS && nz == 2) { M = std::max(M, b.M); N = std::max(N, b.N); K = std::max(K, b.K); }
+  if (M <= 0 || N <= 0) return;
+  int cfgid;   // 0: 128x64, 1: 64x64, 2: 128x32
+  auto ctas = [&](int bm, int bn) { return (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * nz; };
+  if (N <= 32) cfgid = 2;
+  else if (ctas(128, 64) >= e->nsm) cfgid = 0;
+  else cfgid = 1;
+  const int bm = cfgid == 1 ? 64 : 128, bn = cfgid == 2 ? 32 : 64;
+  int nsplit = 1;
+  if (allow_split) {
+    const int ktiles = (K + IGEMM_BK - 1) / IGEMM_BK;
+    long long c = ctas(bm, bn);
+    nsplit = (int)std::max<long long>(1, std::min<long long>({(2LL * e->nsm + c - 1) / c, (long long)ktiles / 4, 64LL}));
+    const long long stride = (long long)M * N;
+    if (nsplit > 1 && (long long)nz * nsplit * stride > e->ws_floats) nsplit = (int)std::max<long long>(1, e->ws_floats / (nz * stride));
+  }
+  dim3 grid((M + bm - 1) / bm, (N + bn - 1) / bn, nz * nsplit);
+  const long long ws_stride = (long long)M * N;
+  {
+    Scope sc(e, name, flops, bytes);
+    if (cfgid == 0) igemm_kernel<128, 64, 8, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    else if (cfgid == 1) igemm_kernel<64, 64, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    else igemm_kernel<128, 32, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    CK(cudaGetLastError());
+  }
+  if (nsplit > 1) {
+    Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
+    dim3 g2((unsigned)std::min<long long>((ws_stride + 255) / 256, 4 * e->nsm), nz);
+    splitk_reduce_kernel<Op><<<g2, 256, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    CK(cudaGetLastError());
+  }
+}
+
+// ---- network schedule ---------------------------------------------------------------------------
+void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag) {
+  const void* cur = X; int cur_u8 = x_u8;
+  char nm[64];
+  for (size_t l = 0; l < e->convs.size(); ++l) {
+    const ConvL& c = e->convs[l];
+    ConvFwdOp op{};
+    op.X = cur; op.x_u8 = cur_u8; op.W = P + c.w.off; op.Y = bufs.conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
+    op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
+    op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
+    snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, tag);
+    const double fl = 2.0 * op.M * op.N * op.K;
+    const double by = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8 ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
+    if (!tc_conv_fwd(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
+    cur = bufs.conv_out[l]; cur_u8 = 0;
+  }
+  for (int l = 0; l < e->depth; ++l) {
+    DenseFwdOp ops[2];
+    for (int t = 0; t < e->ntow; ++t) {
+      const Mat& w = e->tow[t][l];
+      DenseFwdOp& op = ops[t]; op = DenseFwdOp{};
+      op.X = l == 0 ? cur : (const void*)bufs.tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8 : 0;
+      op.W = P + w.off; op.C = bufs.tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
+      op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
+    }
+    if (e->ntow == 1) ops[1] = ops[0];
+    snprintf(nm, sizeof nm, "dense%d_fwd_%s", l + 1, tag);
+    double fl = 0, by = 0;
+    for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * rows * ops[t].N * ops[t].K; by += 4.0 * ((double)rows * ops[t].K / (l == 0 ? e->ntow : 1) + (double)(ops[t].K + 1) * ops[t].N + (double)rows * ops[t].N); }
+    if (!tc_dense_fwd(e, nm, ops, e->ntow, fl, by)) launch_igemm(e, nm, ops[0], ops[1], e->ntow, false, fl, by);
+  }
+}
+
+void backward(E* e) {
+  const int B = e->B;
+  char nm[64];
+  const bool trunk = !e->convs.empty();
+  float* dfeat = trunk ? e->conv_delta.back() : nullptr;
+  for (int l = e->depth - 1; l >= 0; --l) {
+    // weight + bias gradients of both towers in one launch
+    DenseWgradOp wg[2];
+    for (int t = 0; t < e->ntow; ++t) {
+      const Mat& w = e->tow[t][l];
+      DenseWgradOp& op = wg[t]; op = DenseWgradOp{};
+      if (l == 0) { op.X = trunk ? (const void*)e->on.conv_out.back() : (const void*)e->xb; op.x_u8 = trunk ? 0 : (e->elem_bytes == 1); }
+      else { op.X = e->on.tow_out[t][l - 1]; op.x_u8 = 0; }
+      op.ldx = w.K; op.D = e->tow_delta[t][l]; op.ldd = w.N; op.dW = e->grad + w.off; op.M = w.K + 1; op.N = w.N; op.K = B;
+      op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
+    }
+    if (e->ntow == 1) wg[1] = wg[0];
+    snprintf(nm, sizeof nm, "dense%d_wgrad", l + 1);
+    double fl = 0, by = 0;
+    for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * wg[t].M * wg[t].N * B; by += 4.0 * ((double)B * wg[t].M + (double)B * wg[t].N + (double)wg[t].M * wg[t].N); }
+    if (!tc_dense_wgrad(e, nm, wg, e->ntow, fl, by)) launch_igemm(e, nm, wg[0], wg[1], e->ntow, true, fl, by);
+    // input gradients
+    if (l > 0) {
+      DenseDgradOp dg[2];
+      for (int t = 0; t < e->ntow; ++t) {
+        const Mat& w = e->tow[t][l]; const Mat& wp = e->tow[t][l - 1];
+        DenseDgradOp& op = dg[t]; op = DenseDgradOp{};
+        op.D = e->tow_delta[t][l]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = e->tow_delta[t][l - 1]; op.ldx = w.K;
+        op.Y = e->on.tow_out[t][l - 1]; op.ldy = w.K; op.act = wp.act; op.accumulate = 0; op.apply_act = 1;
+        op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
+      }
+      if (e->ntow == 1) dg[1] = dg[0];
+      snprintf(nm, sizeof nm, "dense%d_dgrad", l + 1);
+      double fl = 0, by = 0;
+      for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * B * dg[t].N * dg[t].K; by += 4.0 * ((double)B * dg[t].K + (double)dg[t].N * dg[t].K + 2.0 * B * dg[t].N); }
+      launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
+    } else if (trunk) {
+      for (int t = 0; t < e->ntow; ++t) {       // towers accumulate into the trunk gradient in a fixed order
+        const Mat& w = e->tow[t][0];
+        DenseDgradOp op{};
+        op.D = e->tow_delta[t][0]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = dfeat; op.ldx = w.K;
+        op.Y = e->on.conv_out.back(); op.ldy = w.K; op.act = e->convs.back().w.act; op.accumulate = t > 0; op.apply_act = (t == e->ntow - 1);
+        op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
+        snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
+        const double fl = 2.0 * B * op.N * op.K, by = 4.0 * ((double)B * op.K + (double)op.N * op.K + 2.0 * B * op.N);
+        if (!tc_dense_dgrad(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
+      }
+    }
+  }
+  for (int l = (int)e->convs.size() - 1; l >= 0; --l) {
+    const ConvL& c = e->convs[l];
+    ConvWgradOp wg{};
+    wg.X = l == 0 ? (const void*)e->xb : (const void*)e->on.conv_out[l - 1]; wg.x_u8 = l == 0 ? (e->elem_bytes == 1) : 0;
+    wg.D = e->conv_delta[l]; wg.dW = e->grad + c.w.off; wg.nimg = B; wg.g = c.g;
+    wg.M = c.w.K + 1; wg.N = c.g.Cout; wg.K = B * c.g.OH * c.g.OW; wg.vecA = (c.g.Cin % 4 == 0); wg.vecB = (c.g.Cout % 4 == 0);
+    snprintf(nm, sizeof nm, "conv%d_wgrad", l + 1);
+    double fl = 2.0 * wg.M * wg.N * wg.K;
+    double by = (double)B * c.g.IH * c.g.IW * c.g.Cin * (wg.x_u8 ? 1 : 4) + 4.0 * wg.K * wg.N + 4.0 * wg.M * wg.N;
+    if (!tc_conv_wgrad(e, nm, wg, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
+    if (l > 0) {
+      ConvDgradOp dg{};
+      dg.D = e->conv_delta[l]; dg.W = e->theta + c.w.off; dg.dX = e->conv_delta[l - 1]; dg.Yprev = e->on.conv_out[l - 1];
+      dg.act = e->convs[l - 1].w.act; dg.apply_act = 1; dg.nimg = B; dg.g = c.g;
+      dg.vecA = (c.g.Cout % 4 == 0); dg.vecB = (c.g.Cout % 4 == 0);
+      snprintf(nm, sizeof nm, "conv%d_dgrad", l + 1);
+      fl = 2.0 * B * c.g.OH * c.g.OW * c.g.Cout * c.w.K;
+      by = 4.0 * ((double)B * c.g.OH * c.g.OW * c.g.Cout + (double)c.w.K * c.g.Cout + 2.0 * B * c.g.IH * c.g.IW * c.g.Cin);
+      if (!tc_conv_dgrad(e, nm, dg, fl, by)) launch_igemm(e, nm, dg, dg, c.g.S * c.g.S, false, fl, by);
+    }
+  }
+}
+
+void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for the indices in idx_d
+  {
+    Scope sc(e, "batch_meta", 0, e->B * 40.0);
+    batch_meta_kernel<<<(e->B + 255) / 256, 256, 0, e->stream>>>(e->idx_d, e->B, e->tree, e->P, e->act, e->rew, e->done, e->st,
+                                                                e->cfg.beta, e->a_b, e->r_b, e->d_b, e->w_b);
+    CK(cudaGetLastError());
+  }
+  {
+    const long long rb = e->obs_row_bytes;
+    const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
+    dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
+    Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
+    gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb);
+    CK(cudaGetLastError());
+  }
+}
+
+void enqueue_step(E* e, bool sample) {
+  const int B = e->B;
+  if (sample) {
+    int HT = 1; while (HT < 4 * B) HT <<= 1;
+    Scope sc(e, "sumtree_sample", 0, B * 8.0 * 22);
+    sample_kernel<<<1, (B + 31) / 32 * 32, 2 * HT * sizeof(int), e->stream>>>(e->tree, e->P, B, e->cfg.seed, e->st, 0, 0, e->idx_d);
+    CK(cudaGetLastError());
+  }
+  enqueue_batch_prep(e);
+  forward(e, e->theta, e->xb, e->elem_bytes == 1, 2 * B, e->on, "online");
+  forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target");
+  {
+    HeadArgs h{};
+    const int L = e->depth - 1;
+    if (e->cfg.dueling) { h.V_on = e->on.tow_out[0][L]; h.A_on = e->on.tow_out[1][L]; h.V_tg = e->tg.tow_out[0][L]; h.A_tg = e->tg.tow_out[1][L];
+                          h.dV = e->tow_delta[0][L]; h.dA = e->tow_delta[1][L]; h.act_v = e->tow[0][L].act; h.act_a = e->tow[1][L].act; }
+    else { h.A_on = e->on.tow_out[0][L]; h.A_tg = e->tg.tow_out[0][L]; h.dA = e->tow_delta[0][L]; h.act_a = e->tow[0][L].act; }
+    h.a_b = e->a_b; h.r_b = e->r_b; h.d_b = e->d_b; h.w_b = e->w_b;
+    h.q_s = e->q_s; h.q_sp_on = e->q_sp_on; h.q_sp_tg = e->q_sp_tg; h.y = e->y; h.best_a = e->best_a; h.td = e->td; h.newp = e->newp;
+    h.B = B; h.nA = e->cfg.n_actions; h.dueling = e->cfg.dueling; h.double_q = e->cfg.double_q;
+    h.gamma = e->cfg.discount; h.alpha = e->cfg.alpha; h.eps = e->cfg.eps;
+    h.inv_world_B = 1.0f / ((float)B * (float)e->cfg.world);
+    h.st = e->st;
+    Scope sc(e, "head_loss", 0, B * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
+    head_loss_kernel<<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
+    CK(cudaGetLastError());
+  }
+  backward(e);
+  if (e->cfg.world > 1) {
+    Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
+    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)e->nint, ncclFloat, ncclSum, e->comm, e->stream);
+    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  {
+    Scope sc(e, "adam", 0, 7.0 * e->nint * 4);
+    adam_kernel<<<2 * e->nsm * 2, 256, 0, e->stream>>>(e->theta, e->adam_m, e->adam_v, e->grad, e->nint / 4,
+                                                       (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st);
+    CK(cudaGetLastError());
+  }
+  {
+    Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
+    tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
+                                                                               1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0);
+    CK(cudaGetLastError());
+  }
+  {
+    Scope sc(e, "publish", 0, 12);
+    publish_kernel<<<1, 1, 0, e->stream>>>(e->st, e->host_out_dev);
+    CK(cudaGetLastError());
+  }
+}
+
+void run_step(E* e, bool sample) {
+  if (e->curr_size < e->B) fail(DQN_ERR_STATE, "replay holds %lld transitions, batch_size is %d (PER:83 @assert r._curr_size >= r.batch_size)", e->curr_size, e->B);
+  cudaGraphExec_t& gx = sample ? e->graph_sample : e->graph_idx;
+  if (e->cfg.use_graph && !e->profiling) {
+    if (!gx) {
+      cudaGraph_t g = nullptr;
+      e->capturing = true;
+      e->counting = 1; e->launches = 0;
+      CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      try { enqueue_step(e, sample); } catch (...) { cudaStreamEndCapture(e->stream, &g); if (g) cudaGraphDestroy(g); e->capturing = false; e->counting = 0; throw; }
+      CK(cudaStreamEndCapture(e->stream, &g));
+      e->capturing = false; e->counting = 0; e->launches_per_step = e->launches;
+      CK(cudaGraphInstantiate(&gx, g, 0));
+      CK(cudaGraphDestroy(g));
+    }
+    CK(cudaGraphLaunch(gx, e->stream));
+  } else {
+    e->counting = 1; e->launches = 0;
+    enqueue_step(e, sample);
+    e->counting = 0; e->launches_per_step = e->launches;
+  }
+}
+
+void fetch_scalars(E* e, float* loss, float* gn) {
+  CK(cudaStreamSynchronize(e->stream));
+  const int err = reinterpret_cast<int*>(e->host_out)[2];
+  if (loss) *loss = e->host_out[0];
+  if (gn) *gn = e->host_out[1];
+  if (err) {
+    int zero = 0;
+    CK(cudaMemcpy(&e->st->error, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    reinterpret_cast<int*>(e->host_out)[2] = 0;
+    if (err & 1) fail(DQN_ERR_STATE, "sum-tree sampler did not reach %d distinct indices", e->B);
+    if (err & 2) fail(DQN_ERR_STATE, "non-positive priority (PER:78 @assert all(new_priorities .> 0f0))");
+    if (err & 4) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
+    if (err & 8) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+  }
+}
+
+void check_dev_errors(E* e) {
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, &e->st->error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (err) {
+    int zero = 0;
+    CK(cudaMemcpy(&e->st->error, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    if (err & 2) fail(DQN_ERR_STATE, "non-positive priority (PER:78 @assert all(new_priorities .> 0f0))");
+    if (err & 4) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
+    if (err & 8) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+    fail(DQN_ERR_STATE, "device error flags %d", err);
+  }
+}
+
+void ensure_stage(E* e, long long bytes) {
+  if (bytes <= e->stage_bytes) return;
+  if (e->stage) CK(cudaFree(e->stage));
+  e->stage = nullptr; e->stage_bytes = 0;
+  CK(cudaMalloc(&e->stage, bytes));
+  e->stage_bytes = bytes;
+}
+
+void rebuild_tree(E* e) {
+  for (long long lo = e->P / 2; lo >= 1; lo /= 2) {
+    tree_level_kernel<<<(unsigned)((lo + 255) / 256), 256, 0, e->stream>>>(e->tree, lo);
+    CK(cudaGetLastError());
+  }
+}
+
+void set_curr_size(E* e) {
+  CK(cudaMemcpyAsync(&e->st->curr_size, &e->curr_size, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+}
+
+// n transitions already on the device (Flux layout) -> ring
+void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const uint8_t* sp, const uint8_t* d, const float* td0, long long n, long long* slots) {
+  const int C = e->hwc ? e->cfg.obs_c : 1;
+  const int HW = e->hwc ? e->cfg.obs_h * e->cfg.obs_w : (int)e->obs_elems;
+  if (n > e->cap) fail(DQN_ERR_INVALID, "adding %lld transitions to a buffer of %lld", n, e->cap);
+  const long long new_size = std::min(e->cap, e->curr_size + n);
+  for (long long t0 = 0; t0 < n; t0 += 32768) {
+    const long long cnt = std::min<long long>(32768, n - t0);
+    dim3 grid((unsigned)std::min<long long>((e->obs_elems + 255) / 256, 64), (unsigned)cnt);
+    ingest_kernel<<<grid, 256, 0, e->stream>>>(s, sp, a, r, d, td0, t0, e->cursor, e->cap, C, HW, e->elem_bytes, e->store_s, e->store_sp,
+                                               e->act, e->rew, e->done, e->tree, e->P, slots, e->cfg.alpha, e->cfg.eps, e->cfg.n_actions, new_size, e->st);
+    CK(cudaGetLastError());
+  }
+  if (n <= 4096) {
+    tree_update_kernel<<<1, 1024, 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0);
+    CK(cudaGetLastError());
+  } else rebuild_tree(e);
+  e->cursor = (e->cursor + n) % e->cap;
+  e->curr_size = new_size;
+}
+
+void relayout(E* e, const void* in, void* out, long long rows, int in_u8, int out_f32_from_u8, int dir) {
+  const int C = e->hwc ? e->cfg.obs_c : 1;
+  const int HW = e->hwc ? e->cfg.obs_h * e->cfg.obs_w : (int)e->obs_elems;
+  const long long total = rows * e->obs_elems;
+  relayout_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 8LL * e->nsm), 256, 0, e->stream>>>((const uint8_t*)in, (uint8_t*)out, rows, C, HW, in_u8, out_f32_from_u8, dir);
+  CK(cudaGetLastError());
+}
+
+// ---- topology -----------------------------------------------------------------------------------
+void build_topology(E* e) {
+  const dqn_config_t& c = e->cfg;
+  if (c.n_layers < 1 || c.n_layers > DQN_MAX_LAYERS) fail(DQN_ERR_INVALID, "n_layers must be in 1..%d", DQN_MAX_LAYERS);
+  int i = 0, H = c.obs_h, W = c.obs_w, C = c.obs_c;
+  std::vector<dqn_layer_t> dense;
+  while (i < c.n_layers && c.layers[i].kind == DQN_LAYER_CONV) {
+    const dqn_layer_t& l = c.layers[i];
+    if (l.in != C) fail(DQN_ERR_INVALID, "conv layer %d expects %d input channels, gets %d", i + 1, l.in, C);
+    if (l.kh < 1 || l.kw < 1 || l.stride < 1 || l.kh > H || l.kw > W) fail(DQN_ERR_INVALID, "conv layer %d geometry", i + 1);
+    ConvL cl{};
+    cl.g = ConvGeom{H, W, C, (H - l.kh) / l.stride + 1, (W - l.kw) / l.stride + 1, l.out, l.kh, l.kw, l.stride};
+    cl.w = Mat{0, l.kh * l.kw * C, l.out, l.act};
+    e->convs.push_back(cl);
+    H = cl.g.OH; W = cl.g.OW; C = l.out; ++i;
+  }
+  e->hwc = !e->convs.empty();
+  e->feat = H * W * C;
+  for (; i < c.n_layers; ++i) {
+    const dqn_layer_t& l = c.layers[i];
+    if (l.kind == DQN_LAYER_FLATTEN) { if (!dense.empty()) fail(DQN_ERR_UNSUPPORTED, "flattenbatch after a Dense layer"); continue; }
+    if (l.kind != DQN_LAYER_DENSE) fail(DQN_ERR_UNSUPPORTED, "layer %d: only Conv* [flattenbatch] Dense+ chains are supported", i + 1);
+    dense.push_back(l);
+  }
+  if (dense.empty()) fail(DQN_ERR_INVALID, "DeepQLearningError: the qnetwork provided is incompatible with dueling (no trailing Dense layer, DUEL:47-50)");
+  int in = e->feat;
+  for (auto& l : dense) { if (l.in != in) fail(DQN_ERR_INVALID, "Dense layer expects %d inputs, gets %d", l.in, in); in = l.out; }
+  if (dense.back().out != c.n_actions) fail(DQN_ERR_INVALID, "last Dense has %d outputs, n_actions is %d", dense.back().out, c.n_actions);
+  if (c.n_actions < 1 || c.n_actions > HEAD_MAX_ACTIONS) fail(DQN_ERR_UNSUPPORTED, "n_actions must be in 1..%d", HEAD_MAX_ACTIONS);
+  e->depth = (int)dense.size();
+  e->ntow = c.dueling ? 2 : 1;
+  // internal flat layout: convs, then towers (val, adv), every matrix start aligned to 4 floats
+  long long off = 0;
+  auto place = [&](Mat& m) { m.off = off; off += ((long long)(m.K + 1) * m.N + 3) / 4 * 4; };
+  for (auto& cl : e->convs) place(cl.w);
+  for (int t = 0; t < e->ntow; ++t)
+    for (int l = 0; l < e->depth; ++l) {
+      Mat m{0, dense[l].in, dense[l].out, dense[l].act};
+      if (c.dueling && t == 0 && l == e->depth - 1) { m.N = 1; m.act = DQN_ACT_IDENTITY; }   // fresh Dense(k, 1), DUEL:53-54
+      place(m);
+      e->tow[t][l] = m;
+    }
+  e->nint = off;
+  // Flux.params order -> internal index (DUEL:2-6,13: base, val, adv; weight then bias)
+  e->perm.clear();
+  for (auto& cl : e->convs) {
+    const ConvGeom& g = cl.g;
+    for (int co = 0; co < g.Cout; ++co) for (int ci = 0; ci < g.Cin; ++ci) for (int kh = 0; kh < g.KH; ++kh) for (int kw = 0; kw < g.KW; ++kw) {
+      const int j = g.KH - 1 - kh, ii = g.KW - 1 - kw;      // true convolution -> cross-correlation taps
+      e->perm.push_back(cl.w.off + ((long long)(j * g.KW + ii) * g.Cin + ci) * g.Cout + co);
+    }
+    for (int co = 0; co < g.Cout; ++co) e->perm.push_back(cl.w.off + (long long)cl.w.K * g.Cout + co);
+  }
+  const int HWt = H * W;
+  for (int t = 0; t < e->ntow; ++t)
+    for (int l = 0; l < e->depth; ++l) {
+      const Mat& m = e->tow[t][l];
+      for (int ki = 0; ki < m.K; ++ki) {
+        int row = ki;
+        if (l == 0 && e->hwc) { const int ch = ki / HWt, hw = ki % HWt; row = hw * C + ch; }   // Flux flatten (w + W h + W H c) -> HWC
+        for (int o = 0; o < m.N; ++o) e->perm.push_back(m.off + (long long)row * m.N + o);
+      }
+      for (int o = 0; o < m.N; ++o) e->perm.push_back(m.off + (long long)m.K * m.N + o);
+    }
+  e->nflux = (long long)e->perm.size();
+}
+
+void allocate(E* e) {
+  const dqn_config_t& c = e->cfg;
+  const int B = e->B = c.batch_size;
+  e->rows_on = std::max(2 * B, c.max_act_rows > 0 ? c.max_act_rows : 2 * B);
+  e->elem_bytes = c.obs_dtype == DQN_OBS_U8 ? 1 : 4;
+  e->obs_elems = (long long)c.obs_c * c.obs_h * c.obs_w;
+  e->obs_row_bytes = e->obs_elems * e->elem_bytes;
+  e->theta = dalloc<float>(e->nint); e->theta_t = dalloc<float>(e->nint);
+  e->adam_m = dalloc<float>(e->nint); e->adam_v = dalloc<float>(e->nint); e->grad = dalloc<float>(e->nint);
+  e->cap = c.buffer_size;
+  int P = 2; while (P < e->cap) P <<= 1;
+  e->P = P;
+  e->store_s = dalloc<uint8_t>(e->cap * e->obs_row_bytes);
+  e->store_sp = dalloc<uint8_t>(e->cap * e->obs_row_bytes);
+  e->act = dalloc<int>(e->cap); e->rew = dalloc<float>(e->cap); e->done = dalloc<uint8_t>(e->cap);
+  e->tree = dalloc<float>(2LL * P);
+  e->st = dalloc<DevState>(1);
+  DevState init{}; init.b1p = c.adam_beta1; init.b2p = c.adam_beta2;
+  CK(cudaMemcpy(e->st, &init, sizeof init, cudaMemcpyHostToDevice));
+  e->idx_d = dalloc<long long>(B);
+  e->xb = dalloc<uint8_t>((long long)e->rows_on * e->obs_row_bytes);
+  e->a_b = dalloc<int>(B); e->r_b = dalloc<float>(B); e->d_b = dalloc<float>(B); e->w_b = dalloc<float>(B);
+  for (auto& cl : e->convs) {
+    const long long per = (long long)cl.g.OH * cl.g.OW * cl.g.Cout;
+    e->on.conv_out.push_back(dalloc<float>(e->rows_on * per));
+    e->tg.conv_out.push_back(dalloc<float>(B * per));
+    e->conv_delta.push_back(dalloc<float>(B * per));
+  }
+  for (int t = 0; t < e->ntow; ++t)
+    for (int l = 0; l < e->depth; ++l) {
+      e->on.tow_out[t][l] = dalloc<float>((long long)e->rows_on * e->tow[t][l].N);
+      e->tg.tow_out[t][l] = dalloc<float>((long long)B * e->tow[t][l].N);
+      e->tow_delta[t][l] = dalloc<float>((long long)B * e->tow[t][l].N);
+    }
+  const int nA = c.n_actions;
+  e->q_s = dalloc<float>((long long)B * nA); e->q_sp_on = dalloc<float>((long long)B * nA); e->q_sp_tg = dalloc<float>((long long)B * nA);
+  e->y = dalloc<float>(B); e->td = dalloc<float>(B); e->newp = dalloc<float>(B); e->best_a = dalloc<int>(B);
+  e->ws_floats = 16LL << 20;      // 64 MB split-K workspace
+  e->ws = dalloc<float>(e->ws_floats);
+  CK(cudaHostAlloc(&e->host_out, 16, cudaHostAllocMapped));
+  memset(e->host_out, 0, 16);
+  CK(cudaHostGetDevicePointer(&e->host_out_dev, e->host_out, 0));
+  CK(cudaHostAlloc(&e->idx_h, sizeof(long long) * B, cudaHostAllocDefault));
+  CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1));
+}
+
+void destroy(E* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->graph_sample) cudaGraphExecDestroy(e->graph_sample);
+  if (e->graph_idx) cudaGraphExecDestroy(e->graph_idx);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  tc_destroy(e);
+  void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
+                  e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws,
+                  e->stage, e->flush_buf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto p : e->on.conv_out) cudaFree(p);
+  for (auto p : e->tg.conv_out) cudaFree(p);
+  for (auto p : e->conv_delta) cudaFree(p);
+  for (int t = 0; t < 2; ++t) for (int l = 0; l < MAXD; ++l) { if (e->on.tow_out[t][l]) cudaFree(e->on.tow_out[t][l]); if (e->tg.tow_out[t][l]) cudaFree(e->tg.tow_out[t][l]); if (e->tow_delta[t][l]) cudaFree(e->tow_delta[t][l]); }
+  if (e->host_out) cudaFreeHost(e->host_out);
+  if (e->idx_h) cudaFreeHost(e->idx_h);
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (e->t0) cudaEventDestroy(e->t0);
+  if (e->t1) cudaEventDestroy(e->t1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+// host <-> internal parameter images
+void scatter_params(E* e, float* dev, const float* flat) {
+  std::vector<float> h((size_t)e->nint, 0.f);
+  for (long long i = 0; i < e->nflux; ++i) h[(size_t)e->perm[(size_t)i]] = flat[i];
+  CK(cudaMemcpyAsync(dev, h.data(), sizeof(float) * e->nint, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+}
+void gather_params(E* e, const float* dev, float* flat) {
+  std::vector<float> h((size_t)e->nint);
+  CK(cudaMemcpyAsync(h.data(), dev, sizeof(float) * e->nint, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (long long i = 0; i < e->nflux; ++i) flat[i] = h[(size_t)e->perm[(size_t)i]];
+}
+
+template <class F> int guard(E* e, F&& f) {
+  try {
+    if (!e) return DQN_ERR_INVALID;
+    CK(cudaSetDevice(e->cfg.device));
+    f();
+    return DQN_OK;
+  } catch (const Err& x) {
+    if (e) e->err = x.msg;
+    return x.code;
+  } catch (const std::exception& x) {
+    if (e) e->err = x.what();
+    return DQN_ERR_INVALID;
+  }
+}
+
+template <class T> void d2h(E* e, T* dst, const T* src, long long n) {
+  CK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+}
+
+}  // namespace
+
+// tensor-core path (tc_gemm.cuh) needs the engine definition
+#include "tc_gemm_impl.cuh"
+
+// =================================================================================================
+extern "C" {
+
+int dqn_config_default(dqn_config_t* c) {
+  if (!c) return DQN_ERR_INVALID;
+  memset(c, 0, sizeof *c);
+  c->abi_version = DQN_ABI_VERSION;
+  c->obs_h = c->obs_w = 1; c->obs_dtype = DQN_OBS_F32;
+  c->dueling = c->double_q = c->prioritized_replay = 1;          // SOLVER:10,11,16
+  c->batch_size = 32; c->buffer_size = 1000;                     // SOLVER:5,20
+  c->alpha = 0.6f; c->beta = 0.4f; c->eps = 1e-3f;               // PER:43-45 (the solver's own PER fields are dead)
+  c->learning_rate = 1e-4f; c->discount = 1.0f;                  // SOLVER:3; default_discount HELPERS:83
+  c->adam_beta1 = 0.9; c->adam_beta2 = 0.999; c->adam_eps = 1e-8;
+  c->seed = 0; c->math_mode = DQN_MATH_FP32; c->use_graph = 1; c->rank = 0; c->world = 1;
+  return DQN_OK;
+}
+
+const char* dqn_last_error(const dqn_engine_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dqn_device_count(int* n) { return cudaGetDeviceCount(n) == cudaSuccess ? DQN_OK : DQN_ERR_CUDA; }
+
+int dqn_nccl_unique_id(uint8_t id_out[DQN_NCCL_ID_BYTES]) {
+  std::string why;
+  if (!g_nccl.load(why)) { g_create_error = why; return DQN_ERR_NCCL; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return DQN_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) == DQN_NCCL_ID_BYTES, "ncclUniqueId size");
+  memcpy(id_out, &id, DQN_NCCL_ID_BYTES);
+  return DQN_OK;
+}
+
+int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return DQN_ERR_INVALID; }
+  *out = nullptr;
+  E* e = new E();
+  try {
+    if (cfg->abi_version != DQN_ABI_VERSION) fail(DQN_ERR_INVALID, "abi_version %d, library is %d", cfg->abi_version, DQN_ABI_VERSION);
+    e->cfg = *cfg;
+    if (cfg->batch_size < 1 || cfg->batch_size > 1024) fail(DQN_ERR_INVALID, "batch_size must be in 1..1024");
+    if (cfg->buffer_size < cfg->batch_size) fail(DQN_ERR_STATE, "max_size < batch_size (PER:84 @assert)");
+    if (cfg->buffer_size > (1LL << 30)) fail(DQN_ERR_UNSUPPORTED, "buffer_size above 2^30");
+    if (cfg->obs_c < 1 || cfg->obs_h < 1 || cfg->obs_w < 1) fail(DQN_ERR_INVALID, "observation shape");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) fail(DQN_ERR_INVALID, "rank/world");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) fail(DQN_ERR_CUDA, "no CUDA device: libdqn_b200 has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) fail(DQN_ERR_INVALID, "device %d of %d", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) fail(DQN_ERR_UNSUPPORTED, "compute capability %d.%d: this library is built for sm_100a only", prop.major, prop.minor);
+    e->nsm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    build_topology(e);
+    allocate(e);
+    tc_init(e);
+    if (cfg->world > 1) {
+      std::string why;
+      if (!g_nccl.load(why)) fail(DQN_ERR_NCCL, "%s", why.c_str());
+      ncclUniqueId id; memcpy(&id, cfg->nccl_id, DQN_NCCL_ID_BYTES);
+      ncclResult_t r = g_nccl.CommInitRank(&e->comm, cfg->world, id, cfg->rank);
+      if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return DQN_OK;
+  } catch (const Err& x) {
+    g_create_error = x.msg;
+    destroy(e);
+    return x.code;
+  }
+}
+
+void dqn_engine_destroy(dqn_engine_t* h) { destroy(h); }
+
+int64_t dqn_num_params(const dqn_engine_t* h) { return h ? h->nflux : 0; }
+int64_t dqn_tree_nodes(const dqn_engine_t* h) { return h ? 2LL * h->P : 0; }
+
+int dqn_set_params(dqn_engine_t* h, int which, const float* flat, int64_t n) {
+  return guard(h, [&] {
+    if (n != h->nflux || !flat) fail(DQN_ERR_INVALID, "expected %lld parameters, got %lld", h->nflux, (long long)n);
+    scatter_params(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, flat);
+    tc_params_changed(h);
+  });
+}
+int dqn_get_params(dqn_engine_t* h, int which, float* flat, int64_t n) {
+  return guard(h, [&] {
+    if (n != h->nflux || !flat) fail(DQN_ERR_INVALID, "expected %lld parameters, got %lld", h->nflux, (long long)n);
+    gather_params(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, flat);
+  });
+}
+int dqn_sync_target(dqn_engine_t* h) {
+  return guard(h, [&] {
+    copy_f4_kernel<<<2 * h->nsm, 256, 0, h->stream>>>((float4*)h->theta_t, (const float4*)h->theta, h->nint / 4);
+    CK(cudaGetLastError());
+    tc_params_changed(h);
+  });
+}
+int dqn_get_adam_state(dqn_engine_t* h, float* m, float* v, double bp[2], int64_t n) {
+  return guard(h, [&] {
+    if (n != h->nflux) fail(DQN_ERR_INVALID, "expected %lld parameters", h->nflux);
+    if (m) gather_params(h, h->adam_m, m);
+    if (v) gather_params(h, h->adam_v, v);
+    if (bp) { DevState s; d2h(h, &s, h->st, 1); bp[0] = s.b1p; bp[1] = s.b2p; }
+  });
+}
+
+int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float* r, const void* sp, const uint8_t* done,
+                   const float* td0, int64_t n) {
+  return guard(h, [&] {
+    if (n < 0 || (n > 0 && (!s || !a || !r || !sp || !done || !td0))) fail(DQN_ERR_INVALID, "null argument");
+    const long long rb = h->obs_row_bytes;
+    const long long chunk = std::max<long long>(1, std::min<long long>(n, (256LL << 20) / std::max<long long>(1, 2 * rb)));
+    const long long per = 2 * rb + 4 + 4 + 1 + 4;
+    ensure_stage(h, chunk * per + 64 * 6 + chunk * 8);
+    for (long long t0 = 0; t0 < n; t0 += chunk) {
+      const long long c = std::min(chunk, n - t0);
+      uint8_t* p = h->stage;
+      auto carve = [&](long long bytes) { uint8_t* q = p; p += (bytes + 63) / 64 * 64; return q; };
+      uint8_t* ds = carve(c * rb); uint8_t* dsp = carve(c * rb);
+      int* da = (int*)carve(c * 4); float* dr = (float*)carve(c * 4); float* dtd = (float*)carve(c * 4); uint8_t* dd = carve(c);
+      long long* slots = (long long*)carve(c * 8);
+      CK(cudaMemcpyAsync(ds, (const uint8_t*)s + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(dsp, (const uint8_t*)sp + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(da, a + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(dr, r + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(dtd, td0 + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(dd, done + t0, c, cudaMemcpyHostToDevice, h->stream));
+      ingest_device(h, ds, da, dr, dsp, dd, dtd, c, slots);
+    }
+    check_dev_errors(h);
+  });
+}
+
+int dqn_replay_add_device(dqn_engine_t* h, const void* s, const int32_t* a, const float* r, const void* sp, const uint8_t* done,
+                          const float* td0, int64_t n) {
+  return guard(h, [&] {
+    if (n <= 0) return;
+    ensure_stage(h, n * 8);
+    ingest_device(h, (const uint8_t*)s, a, r, (const uint8_t*)sp, done, td0, n, (long long*)h->stage);
+    check_dev_errors(h);
+  });
+}
+
+int dqn_replay_size(const dqn_engine_t* h, int64_t* curr_size, int64_t* cursor) {
+  if (!h) return DQN_ERR_INVALID;
+  if (curr_size) *curr_size = h->curr_size;
+  if (cursor) *cursor = h->cursor;
+  return DQN_OK;
+}
+
+int dqn_replay_fill_synthetic(dqn_engine_t* h, int64_t n, uint64_t seed) {
+  return guard(h, [&] {
+    if (n < 0 || n > h->cap) fail(DQN_ERR_INVALID, "n outside 0..buffer_size");
+    const long long words = h->elem_bytes == 1 ? (h->obs_elems + 15) / 16 : (h->obs_elems + 3) / 4;
+    for (long long i0 = 0; i0 < n; i0 += 32768) {
+      const long long cnt = std::min<long long>(32768, n - i0);
+      dim3 grid((unsigned)std::min<long long>((words + 255) / 256, 16), (unsigned)cnt);
+      fill_synthetic_kernel<<<grid, 256, 0, h->stream>>>(h->store_s, h->store_sp, h->act, h->rew, h->done, h->tree, h->P, i0, h->obs_elems,
+                                                         h->elem_bytes == 1, h->cfg.n_actions, h->cfg.alpha, h->cfg.eps, seed);
+      CK(cudaGetLastError());
+    }
+    if (n < h->cap) { fill_u32_kernel<<<2 * h->nsm, 256, 0, h->stream>>>((uint32_t*)(h->tree + h->P + n), h->P - n, 0u); CK(cudaGetLastError()); }
+    rebuild_tree(h);
+    h->cursor = n % h->cap; h->curr_size = n;
+    set_curr_size(h);
+  });
+}
+
+int dqn_replay_read(dqn_engine_t* h, const int64_t* idx, int64_t n, void* s, int32_t* a, float* r, void* sp, uint8_t* done) {
+  return guard(h, [&] {
+    const long long rb = h->obs_row_bytes;
+    for (long long t = 0; t < n; ++t) {
+      const long long i = idx[t];
+      if (i < 0 || i >= h->cap) fail(DQN_ERR_INVALID, "index %lld outside the buffer", i);
+      ensure_stage(h, 2 * rb);
+      if (s) { relayout(h, h->store_s + i * rb, h->stage, 1, h->elem_bytes == 1, 0, 0); CK(cudaMemcpyAsync((uint8_t*)s + t * rb, h->stage, rb, cudaMemcpyDeviceToHost, h->stream)); }
+      if (sp) { relayout(h, h->store_sp + i * rb, h->stage + rb, 1, h->elem_bytes == 1, 0, 0); CK(cudaMemcpyAsync((uint8_t*)sp + t * rb, h->stage + rb, rb, cudaMemcpyDeviceToHost, h->stream)); }
+      if (a) CK(cudaMemcpyAsync(a + t, h->act + i, 4, cudaMemcpyDeviceToHost, h->stream));
+      if (r) CK(cudaMemcpyAsync(r + t, h->rew + i, 4, cudaMemcpyDeviceToHost, h->stream));
+      if (done) CK(cudaMemcpyAsync(done + t, h->done + i, 1, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
+
+static void upload_idx(dqn_engine_t* h, const int64_t* idx, long long n, long long* dst, long long limit) {
+  for (long long t = 0; t < n; ++t) if (idx[t] < 0 || idx[t] >= limit) fail(DQN_ERR_INVALID, "index %lld outside 0..%lld", (long long)idx[t], limit - 1);
+  CK(cudaMemcpyAsync(dst, idx, sizeof(long long) * n, cudaMemcpyHostToDevice, h->stream));
+}
+
+int dqn_update_priorities(dqn_engine_t* h, const int64_t* idx, const float* td, int64_t n) {
+  return guard(h, [&] {
+    if (n <= 0) return;
+    ensure_stage(h, n * 12 + 128);
+    long long* di = (long long*)h->stage; float* dp = (float*)(h->stage + (n * 8 + 63) / 64 * 64);
+    upload_idx(h, idx, n, di, h->cap);
+    CK(cudaMemcpyAsync(dp, td, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    td_to_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dp, n, h->cfg.alpha, h->cfg.eps);
+    CK(cudaGetLastError());
+    tree_update_kernel<<<1, 1024, 0, h->stream>>>(h->tree, h->P, di, dp, (int)n, 1, h->st, 0, 1.0, 1.0, 0);
+    CK(cudaGetLastError());
+    check_dev_errors(h);
+  });
+}
+
+int dqn_set_priorities(dqn_engine_t* h, const int64_t* idx, const float* prio, int64_t n) {
+  return guard(h, [&] {
+    if (n <= 0) return;
+    ensure_stage(h, n * 12 + 128);
+    long long* di = (long long*)h->stage; float* dp = (float*)(h->stage + (n * 8 + 63) / 64 * 64);
+    upload_idx(h, idx, n, di, h->cap);
+    CK(cudaMemcpyAsync(dp, prio, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    scatter_leaves_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->tree, h->P, di, dp, n);
+    CK(cudaGetLastError());
+    rebuild_tree(h);
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int dqn_get_priorities(dqn_engine_t* h, float* out, int64_t n) {
+  return guard(h, [&] { if (n < 0 || n > h->cap) fail(DQN_ERR_INVALID, "n"); d2h(h, out, h->tree + h->P, n); });
+}
+int dqn_get_tree(dqn_engine_t* h, float* out, int64_t n_nodes) {
+  return guard(h, [&] { if (n_nodes < 0 || n_nodes > 2LL * h->P) fail(DQN_ERR_INVALID, "n_nodes"); d2h(h, out, h->tree, n_nodes); });
+}
+
+int dqn_sample_indices(dqn_engine_t* h, uint64_t call, int64_t* idx_out) {
+  return guard(h, [&] {
+    if (h->curr_size < h->B) fail(DQN_ERR_STATE, "replay holds %lld transitions, batch_size is %d (PER:83)", h->curr_size, h->B);
+    ensure_stage(h, h->B * 8);
+    int HT = 1; while (HT < 4 * h->B) HT <<= 1;
+    sample_kernel<<<1, (h->B + 31) / 32 * 32, 2 * HT * sizeof(int), h->stream>>>(h->tree, h->P, h->B, h->cfg.seed, h->st, 1, call, (long long*)h->stage);
+    CK(cudaGetLastError());
+    d2h(h, (long long*)idx_out, (const long long*)h->stage, h->B);
+    check_dev_errors(h);
+  });
+}
+
+int dqn_get_batch(dqn_engine_t* h, const int64_t* idx, float* s, int32_t* a, float* r, float* sp, float* done, float* weights) {
+  return guard(h, [&] {
+    const int B = h->B;
+    upload_idx(h, idx, B, h->idx_d, h->curr_size > 0 ? h->curr_size : 1);
+    enqueue_batch_prep(h);
+    const long long fbytes = (long long)B * h->obs_elems * 4;
+    ensure_stage(h, 2 * fbytes);
+    relayout(h, h->xb, h->stage, 2LL * B, h->elem_bytes == 1, 1, 0);
+    if (s) CK(cudaMemcpyAsync(s, h->stage, fbytes, cudaMemcpyDeviceToHost, h->stream));
+    if (sp) CK(cudaMemcpyAsync(sp, h->stage + fbytes, fbytes, cudaMemcpyDeviceToHost, h->stream));
+    if (a) CK(cudaMemcpyAsync(a, h->a_b, 4LL * B, cudaMemcpyDeviceToHost, h->stream));
+    if (r) CK(cudaMemcpyAsync(r, h->r_b, 4LL * B, cudaMemcpyDeviceToHost, h->stream));
+    if (done) CK(cudaMemcpyAsync(done, h->d_b, 4LL * B, cudaMemcpyDeviceToHost, h->stream));
+    if (weights) CK(cudaMemcpyAsync(weights, h->w_b, 4LL * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int dqn_train_step(dqn_engine_t* h, float* loss, float* grad_norm) {
+  return guard(h, [&] { run_step(h, true); fetch_scalars(h, loss, grad_norm); });
+}
+int dqn_train_step_with_indices(dqn_engine_t* h, const int64_t* idx, float* loss, float* grad_norm) {
+  return guard(h, [&] {
+    upload_idx(h, idx, h->B, h->idx_d, h->curr_size > 0 ? h->curr_size : 1);
+    run_step(h, false);
+    fetch_scalars(h, loss, grad_norm);
+  });
+}
+int dqn_train_step_async(dqn_engine_t* h) { return guard(h, [&] { run_step(h, true); }); }
+int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm); }); }
+
+int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* q_out) {
+  return guard(h, [&] {
+    if (n < 0 || (n > 0 && (!obs || !q_out))) fail(DQN_ERR_INVALID, "null argument");
+    const long long rb = h->obs_row_bytes; const int nA = h->cfg.n_actions; const int L = h->depth - 1;
+    const int chunk = h->rows_on;
+    ensure_stage(h, (long long)chunk * rb);
+    for (long long t0 = 0; t0 < n; t0 += chunk) {
+      const int c = (int)std::min<long long>(chunk, n - t0);
+      CK(cudaMemcpyAsync(h->stage, (const uint8_t*)obs + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
+      relayout(h, h->stage, h->xb, c, h->elem_bytes == 1, 0, 1);
+      forward(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, c, h->on, "act");
+      float* q = h->on.tow_out[h->ntow - 1][L];
+      if (h->cfg.dueling) {
+        q = (float*)h->ws;
+        dueling_combine_kernel<<<(c + 255) / 256, 256, 0, h->stream>>>(h->on.tow_out[0][L], h->on.tow_out[1][L], c, nA, q);
+        CK(cudaGetLastError());
+      }
+      CK(cudaMemcpyAsync(q_out + t0 * nA, q, sizeof(float) * c * nA, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
+
+int dqn_get_last_indices(dqn_engine_t* h, int64_t* out) { return guard(h, [&] { d2h(h, (long long*)out, (const long long*)h->idx_d, h->B); }); }
+int dqn_get_td(dqn_engine_t* h, float* out) { return guard(h, [&] { d2h(h, out, (const float*)h->td, h->B); }); }
+int dqn_get_is_weights(dqn_engine_t* h, float* out) { return guard(h, [&] { d2h(h, out, (const float*)h->w_b, h->B); }); }
+int dqn_get_q(dqn_engine_t* h, int which, float* out) {
+  return guard(h, [&] {
+    const float* src = which == DQN_Q_S_ONLINE ? h->q_s : which == DQN_Q_SP_ONLINE ? h->q_sp_on : h->q_sp_tg;
+    d2h(h, out, src, (long long)h->B * h->cfg.n_actions);
+  });
+}
+int dqn_get_targets(dqn_engine_t* h, float* y, int32_t* best_a) {
+  return guard(h, [&] { if (y) d2h(h, y, (const float*)h->y, h->B); if (best_a) d2h(h, best_a, (const int*)h->best_a, h->B); });
+}
+int dqn_get_grads(dqn_engine_t* h, float* flat, int64_t n) {
+  return guard(h, [&] { if (n != h->nflux) fail(DQN_ERR_INVALID, "expected %lld", h->nflux); gather_params(h, h->grad, flat); });
+}
+
+int dqn_timer_start(dqn_engine_t* h) { return guard(h, [&] { CK(cudaEventRecord(h->t0, h->stream)); }); }
+int dqn_timer_stop(dqn_engine_t* h, float* ms) {
+  return guard(h, [&] { CK(cudaEventRecord(h->t1, h->stream)); CK(cudaEventSynchronize(h->t1)); CK(cudaEventElapsedTime(ms, h->t0, h->t1)); });
+}
+int dqn_launches_per_step(const dqn_engine_t* h) { return h ? h->launches_per_step : 0; }
+int dqn_set_profiling(dqn_engine_t* h, int on) {
+  return guard(h, [&] {
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->prof.clear();
+    h->profiling = on;
+  });
+}
+int dqn_get_profile(dqn_engine_t* h, char* buf, int64_t buflen) {
+  return guard(h, [&] {
+    CK(cudaStreamSynchronize(h->stream));
+    struct Agg { double ms = 0, flops = 0, bytes = 0; int n = 0; int order = 0; };
+    std::map<std::string, Agg> agg; int order = 0;
+    for (auto& r : h->prof) {
+      float ms = 0; CK(cudaEventElapsedTime(&ms, r.a, r.b));
+      Agg& a = agg[r.name]; if (a.n == 0) a.order = order++;
+      a.ms += ms; a.flops = r.flops; a.bytes = r.bytes; a.n++;
+    }
+    std::vector<std::pair<std::string, Agg>> v(agg.begin(), agg.end());
+    std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.order < y.second.order; });
+    std::string s;
+    char line[256];
+    for (auto& kv : v) {
+      snprintf(line, sizeof line, "%s %.6f %d %.0f %.0f\n", kv.first.c_str(), kv.second.ms / kv.second.n, kv.second.n, kv.second.bytes, kv.second.flops);
+      s += line;
+    }
+    if ((int64_t)s.size() + 1 > buflen) fail(DQN_ERR_INVALID, "profile needs %zu bytes", s.size() + 1);
+    memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+int dqn_flush_l2(dqn_engine_t* h) {
+  return guard(h, [&] {
+    if (!h->flush_buf) { h->flush_n = (256LL << 20) / 4; h->flush_buf = dalloc<uint32_t>(h->flush_n); }
+    fill_u32_kernel<<<4 * h->nsm, 256, 0, h->stream>>>(h->flush_buf, h->flush_n, 1u);
+    CK(cudaGetLastError());
+  });
+}
+void* dqn_stream(dqn_engine_t* h) { return h ? (void*)h->stream : nullptr; }
+
+int dqn_host_alloc(void** p, int64_t bytes) { return cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? DQN_OK : DQN_ERR_CUDA; }
+int dqn_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? DQN_OK : DQN_ERR_CUDA; }
+
+}  // extern "C"

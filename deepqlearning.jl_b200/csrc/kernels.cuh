@@ -1,0 +1,423 @@
+// kernels.cuh - the HBM-bound / latency-bound kernels of the step: sum-tree sampling and refresh,
+// transition gather, fused dueling + Double-Q + Bellman target + IS-Huber head, fused Adam.
+// Reference lines are cited per kernel (PER = src/prioritized_experience_replay.jl, SOLVER = src/solver.jl).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "igemm.cuh"
+
+namespace dqn {
+
+// Device-resident scalar state (everything a captured graph must read or advance without new arguments).
+struct DevState {
+  long long curr_size;            // r._curr_size                      PER:26
+  unsigned long long sample_call; // Philox counter word: number of sampling calls so far
+  double b1p, b2p;                // Adam running beta powers, Float64
+  unsigned int gradmax_bits;      // max |g| of this step as fp32 bits (globalnorm, HELPERS:38-46)
+  float loss;                     // loss_val SOLVER:223-224
+  int error;                      // sticky error flags raised by kernels (bit 0: sampler did not converge,
+                                  //   bit 1: non-positive priority PER:78, bit 2: td0+eps <= 0 PER:66, bit 3: bad action)
+  int pad;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11); oracle/philox.py restates it and checks the Random123 vectors.
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = mulhi32(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__host__ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t call, uint32_t slot, uint32_t attempt) {
+  uint32_t c[4] = {slot, attempt, (uint32_t)call, (uint32_t)(call >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (float)(c[0] >> 8) * 5.9604644775390625e-08f;   // 2^-24, exact
+}
+
+// Float32 ^ Float32 through Float64, rounded once (the reference's Float32 pow; oracle pow_f32)
+__device__ __forceinline__ float pow_f32(float x, float y) { return (float)pow((double)x, (double)y); }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Sum-tree.  tree[1] root, children of k at 2k, 2k+1, leaves at P + i.  Internal nodes are always
+// recomputed as fl(left + right) - the tree is a pure function of its leaves (bit-exact vs oracle/sumtree.py).
+__device__ __forceinline__ int tree_descend(const float* __restrict__ tree, int P, float u) {
+  float v = __fmul_rn(u, tree[1]);
+  int node = 1;
+  while (node < P) {
+    const float2 ch = *reinterpret_cast<const float2*>(tree + 2 * node);
+    const bool left = (v < ch.x) || (ch.y == 0.f);
+    if (!left) v = __fsub_rn(v, ch.x);
+    node = 2 * node + (left ? 0 : 1);
+  }
+  return node - P;
+}
+
+// B draws without replacement (StatsBase.sample(...; replace=false), PER:85): slot j redraws while a slot
+// i < j holds the same leaf; one check per round over a shared hash table.  One CTA, B <= 1024 threads.
+constexpr int SAMPLE_MAX_ROUNDS = 64;
+__global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint64_t seed, DevState* st,
+                              int use_call, uint64_t call_in, long long* __restrict__ idx_out) {
+  extern __shared__ int sh[];
+  int HT = 1; while (HT < 4 * B) HT <<= 1;      // hash table: HT keys + HT owners (dynamic smem = 2*HT ints)
+  int* keys = sh;
+  int* owner = sh + HT;
+  const int j = threadIdx.x;
+  const uint64_t call = use_call ? call_in : st->sample_call;
+  uint32_t attempt = 0;
+  int leaf = (j < B) ? tree_descend(tree, P, philox_uniform(seed, call, j, 0)) : -1;
+  int round = 0;
+  for (; round < SAMPLE_MAX_ROUNDS; ++round) {
+    for (int t = threadIdx.x; t < HT; t += blockDim.x) { keys[t] = -1; owner[t] = 0x7fffffff; }
+    __syncthreads();
+    int slot = -1;
+    if (j < B) {
+      unsigned h = ((unsigned)leaf * 2654435761u) & (HT - 1);
+      while (true) {
+        int prev = atomicCAS(&keys[h], -1, leaf);
+        if (prev == -1 || prev == leaf) { slot = h; break; }
+        h = (h + 1) & (HT - 1);
+      }
+      atomicMin(&owner[slot], j);
+    }
+    __syncthreads();
+    const int rej = (j < B) && (owner[slot] < j);
+    const int any = __syncthreads_or(rej);
+    if (!any) break;
+    if (rej) { ++attempt; leaf = tree_descend(tree, P, philox_uniform(seed, call, j, attempt)); }
+  }
+  if (j < B) idx_out[j] = leaf;
+  if (j == 0 && round >= SAMPLE_MAX_ROUNDS) atomicOr(&st->error, 1);
+}
+
+// Per-sample metadata gather + importance weights (get_batch, PER:91-102):
+//   w_i = (n * prio_i / sum prio)^(-beta), sum prio = tree root, n = curr_size.
+__global__ void batch_meta_kernel(const long long* __restrict__ idx, int B, const float* __restrict__ tree, int P,
+                                  const int* __restrict__ act, const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                  const DevState* __restrict__ st, float beta,
+                                  int* __restrict__ a_b, float* __restrict__ r_b, float* __restrict__ d_b, float* __restrict__ w_b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  const long long i = idx[j];
+  a_b[j] = act[i];
+  r_b[j] = rew[i];
+  d_b[j] = done[i] ? 1.f : 0.f;
+  const float p = __fdiv_rn(tree[P + i], tree[1]);
+  w_b[j] = pow_f32(__fmul_rn((float)st->curr_size, p), -beta);
+}
+
+// Observation gather: rows idx[j] of the s / s' stores -> contiguous batch (s rows 0..B-1, s' rows B..2B-1).
+// 16-byte loads, 4 in flight per thread; grid = (chunks, 2B).
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ store_s, const uint8_t* __restrict__ store_sp,
+                                                           const long long* __restrict__ idx, int B, long long row_bytes,
+                                                           uint8_t* __restrict__ out) {
+  const int row = blockIdx.y;
+  const long long i = idx[row < B ? row : row - B];
+  const uint8_t* src = (row < B ? store_s : store_sp) + i * row_bytes;
+  uint8_t* dst = out + (long long)row * row_bytes;
+  if ((row_bytes & 15) == 0) {
+    const long long nvec = row_bytes >> 4;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    long long v0 = ((long long)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+    int4 tmp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { long long v = v0 + (long long)u * blockDim.x; if (v < nvec) tmp[u] = __ldg(s4 + v); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { long long v = v0 + (long long)u * blockDim.x; if (v < nvec) d4[v] = tmp[u]; }
+  } else {
+    for (long long b = (long long)blockIdx.x * blockDim.x * 4 + threadIdx.x; b < row_bytes && b < ((long long)blockIdx.x + 1) * blockDim.x * 4; b += blockDim.x)
+      dst[b] = src[b];
+  }
+}
+
+// Refresh of the touched leaf-to-root paths, one CTA: every level is recomputed from its children after a
+// barrier, so the result is independent of thread order.  Also the end-of-step bookkeeping (beta powers,
+// sampling-call counter) so that a captured graph advances its own state.
+__global__ void tree_update_kernel(float* __restrict__ tree, int P, const long long* __restrict__ idx, const float* __restrict__ newp,
+                                   int n, int write_leaves, DevState* st, int end_of_step, double beta1, double beta2,
+                                   int advance_sampler) {
+  const int j = threadIdx.x;
+  if (write_leaves) {
+    for (int t = j; t < n; t += blockDim.x) {
+      const float p = newp[t];
+      if (!(p > 0.f)) atomicOr(&st->error, 2);
+      tree[P + idx[t]] = p;
+    }
+  }
+  __syncthreads();
+  if (n > 0) {
+    for (int shift = 1; (P >> shift) >= 1; ++shift) {
+      for (int t = j; t < n; t += blockDim.x) {
+        const long long node = (P + idx[t]) >> shift;
+        tree[node] = __fadd_rn(tree[2 * node], tree[2 * node + 1]);
+      }
+      __syncthreads();
+    }
+  }
+  if (end_of_step && j == 0) {
+    st->b1p *= beta1; st->b2p *= beta2;
+    if (advance_sampler) st->sample_call += 1;
+  }
+}
+
+// Full rebuild, level by level (used after bulk fills): parents[k] = fl(tree[2k] + tree[2k+1]) for k in [lo, 2lo)
+__global__ void tree_level_kernel(float* __restrict__ tree, long long lo) {
+  const long long k = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < 2 * lo) tree[k] = __fadd_rn(tree[2 * k], tree[2 * k + 1]);
+}
+
+// add_exp! for n transitions already on the device in Flux layout (C,H,W per sample): transposes to the
+// store's HWC layout, writes a/r/done and the new leaf priority (td0+eps)^alpha (PER:65-74).
+__global__ void ingest_kernel(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ sp_in, const int* __restrict__ a_in,
+                              const float* __restrict__ r_in, const uint8_t* __restrict__ d_in, const float* __restrict__ td0,
+                              long long t0, long long cursor, long long cap, int C, int HW, int elem_bytes,
+                              uint8_t* __restrict__ store_s, uint8_t* __restrict__ store_sp, int* __restrict__ act, float* __restrict__ rew,
+                              uint8_t* __restrict__ done, float* __restrict__ tree, int P, long long* __restrict__ slot_idx,
+                              float alpha, float eps, int n_actions, long long new_size, DevState* st) {
+  const long long t = t0 + blockIdx.y;      // transition
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) st->curr_size = new_size;
+  const long long slot = (cursor + t) % cap;
+  const long long elems = (long long)C * HW;
+  const uint8_t* si = s_in + t * elems * elem_bytes;
+  const uint8_t* pi = sp_in + t * elems * elem_bytes;
+  uint8_t* so = store_s + slot * elems * elem_bytes;
+  uint8_t* po = store_sp + slot * elems * elem_bytes;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
+    const long long hw = e / C, c = e % C;            // e indexes the HWC store
+    const long long src = c * HW + hw;                // CHW input
+    if (elem_bytes == 1) { so[e] = si[src]; po[e] = pi[src]; }
+    else { ((float*)so)[e] = ((const float*)si)[src]; ((float*)po)[e] = ((const float*)pi)[src]; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int a = a_in[t];
+    if (a < 1 || a > n_actions) atomicOr(&st->error, 8);
+    act[slot] = a; rew[slot] = r_in[t]; done[slot] = d_in[t] ? 1 : 0;
+    const float base = __fadd_rn(td0[t], eps);
+    if (!(base > 0.f)) atomicOr(&st->error, 4);
+    tree[P + slot] = pow_f32(base, alpha);
+    slot_idx[t] = slot;
+  }
+}
+
+// Synthetic replay fill, transition i a pure function of (seed, i): obs bytes / floats from
+// Philox(key = seed, counter = (word, i_lo, i_hi, stream)); a ~ U{1..|A|}; r ~ U(-1,1); done ~ Bern(0.01);
+// priority (|r|+eps)^alpha.  oracle/synthetic.py regenerates any transition on the CPU.
+__global__ void fill_synthetic_kernel(uint8_t* __restrict__ store_s, uint8_t* __restrict__ store_sp, int* __restrict__ act,
+                                      float* __restrict__ rew, uint8_t* __restrict__ done, float* __restrict__ tree, int P,
+                                      long long i0, long long elems, int obs_u8, int n_actions, float alpha, float eps, uint64_t seed) {
+  const long long i = i0 + blockIdx.y;
+  const long long words = obs_u8 ? (elems + 15) / 16 : (elems + 3) / 4;     // one Philox block = 16 bytes or 4 floats
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int stream = 0; stream < 2; ++stream) {
+      uint32_t c[4] = {(uint32_t)w, (uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      uint8_t* base = (stream == 0 ? store_s : store_sp);
+      if (obs_u8) {
+        uint8_t* o = base + i * elems + w * 16;
+        if ((elems & 15) == 0) { *reinterpret_cast<uint4*>(o) = make_uint4(c[0], c[1], c[2], c[3]); continue; }   // little-endian bytes
+        for (int q = 0; q < 4; ++q)
+          for (int b = 0; b < 4; ++b) { long long e = w * 16 + q * 4 + b; if (e < elems) o[q * 4 + b] = (uint8_t)(c[q] >> (8 * b)); }
+      } else {
+        float* o = (float*)base + i * elems + w * 4;
+        for (int q = 0; q < 4; ++q) { long long e = w * 4 + q; if (e < elems) o[q] = ((float)(c[q] >> 8) * 5.9604644775390625e-08f) * 2.f - 1.f; }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t c[4] = {0xFFFFFFFFu, (uint32_t)i, (uint32_t)(i >> 32), 2u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    act[i] = 1 + (int)(c[0] % (uint32_t)n_actions);
+    const float r = ((float)(c[1] >> 8) * 5.9604644775390625e-08f) * 2.f - 1.f;
+    rew[i] = r;
+    done[i] = ((c[2] >> 8) < 167772u) ? 1 : 0;          // 167772 / 2^24 ~ 0.01
+    tree[P + i] = pow_f32(__fadd_rn(fabsf(r), eps), alpha);
+  }
+}
+
+// Store (HWC, u8 or f32) rows -> Float32 Flux layout (CHW) on the way out (get_batch / replay_read), or
+// host CHW observations -> HWC compute layout on the way in (q_values).  dir 0: HWC->CHW, 1: CHW->HWC.
+__global__ void relayout_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long rows, int C, int HW,
+                                int in_u8, int out_f32_from_u8, int dir) {
+  const long long elems = (long long)C * HW;
+  const long long total = rows * elems;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / elems, e = t % elems;
+    long long src, dst;
+    if (dir == 0) { const long long c = e / HW, hw = e % HW; src = hw * C + c; dst = e; }      // e indexes CHW output
+    else          { const long long hw = e / C, c = e % C; src = c * HW + hw; dst = e; }       // e indexes HWC output
+    if (in_u8) {
+      const uint8_t v = in[row * elems + src];
+      if (out_f32_from_u8) ((float*)out)[row * elems + dst] = u8_to_f32(v); else out[row * elems + dst] = v;
+    } else ((float*)out)[row * elems + dst] = ((const float*)in)[row * elems + src];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused head: dueling combine, Double-Q argmax, Bellman target, IS-weighted Huber loss, dQ seed, TD errors
+// and new priorities.  One thread per sample, one CTA (B <= 1024).   SOLVER:209-225, DUEL:8-11, HELPERS:14-19,
+// PER:76-80; evaluation order as SURVEY App. A steps 4-9, 12 (no FMA contraction on the target).
+struct HeadArgs {
+  // tower outputs; dueling: V [rows][1], A [rows][nA]; else Q in A_* and V_* unused
+  const float* V_on; const float* A_on;      // online net, rows 0..B-1 = s, B..2B-1 = s'
+  const float* V_tg; const float* A_tg;      // target net, rows 0..B-1 = s'
+  const int* a_b; const float* r_b; const float* d_b; const float* w_b;
+  float* dV; float* dA;                      // dL/d(last-layer outputs), already times act'(out)
+  float* q_s; float* q_sp_on; float* q_sp_tg;// (B, nA) diagnostics
+  float* y; int* best_a; float* td; float* newp;
+  int B, nA, dueling, double_q, act_v, act_a;
+  float gamma, alpha, eps, inv_world_B;      // inv_world_B = 1/(B*world): data-parallel ranks form one batch of B*world
+  DevState* st;
+};
+constexpr int HEAD_MAX_ACTIONS = 64;
+
+__device__ __forceinline__ void dueling_q(const float* V, const float* A, int row, int nA, int dueling, float* q) {
+  if (dueling) {
+    float m = A[(long long)row * nA];
+    for (int k = 1; k < nA; ++k) m = __fadd_rn(m, A[(long long)row * nA + k]);
+    m = __fdiv_rn(m, (float)nA);
+    const float v = V[row];
+    for (int k = 0; k < nA; ++k) q[k] = __fsub_rn(__fadd_rn(v, A[(long long)row * nA + k]), m);
+  } else {
+    for (int k = 0; k < nA; ++k) q[k] = A[(long long)row * nA + k];
+  }
+}
+
+__global__ void head_loss_kernel(HeadArgs h) {
+  __shared__ float red[32];
+  const int i = threadIdx.x;
+  float hub = 0.f;
+  if (i < h.B) {
+    float q[HEAD_MAX_ACTIONS];
+    const int nA = h.nA;
+    // s' online / target
+    dueling_q(h.V_on, h.A_on, h.B + i, nA, h.dueling, q);
+    for (int k = 0; k < nA; ++k) h.q_sp_on[(long long)i * nA + k] = q[k];
+    int best = 0;
+    for (int k = 1; k < nA; ++k) if (q[k] > q[best]) best = k;          // first maximal index (Julia argmax)
+    dueling_q(h.V_tg, h.A_tg, i, nA, h.dueling, q);
+    for (int k = 0; k < nA; ++k) h.q_sp_tg[(long long)i * nA + k] = q[k];
+    float qsp;
+    if (h.double_q) qsp = q[best];
+    else { best = 0; for (int k = 1; k < nA; ++k) if (q[k] > q[best]) best = k; qsp = q[best]; }
+    // y = r + ((1 - d) * gamma) * q'
+    const float y = __fadd_rn(h.r_b[i], __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.d_b[i]), h.gamma), qsp));
+    // s online
+    dueling_q(h.V_on, h.A_on, i, nA, h.dueling, q);
+    for (int k = 0; k < nA; ++k) h.q_s[(long long)i * nA + k] = q[k];
+    const int a = h.a_b[i] - 1;
+    const float td = __fsub_rn(q[a], y);
+    const float w = h.w_b[i];
+    const float x = __fmul_rn(w, td);
+    const float ax = fabsf(x), quad = fminf(ax, 1.f), lin = __fsub_rn(ax, quad);
+    hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), lin);
+    const float g = __fmul_rn(__fmul_rn(w, fminf(fmaxf(x, -1.f), 1.f)), h.inv_world_B);
+    if (h.dueling) {
+      h.dV[i] = g * act_deriv(h.V_on[i], h.act_v);
+      const float gm = __fdiv_rn(g, (float)nA);
+      for (int k = 0; k < nA; ++k) {
+        const float d = (k == a ? g : 0.f) - gm;
+        h.dA[(long long)i * nA + k] = d * act_deriv(h.A_on[(long long)i * nA + k], h.act_a);
+      }
+    } else {
+      for (int k = 0; k < nA; ++k) h.dA[(long long)i * nA + k] = (k == a ? g : 0.f) * act_deriv(h.A_on[(long long)i * nA + k], h.act_a);
+    }
+    h.y[i] = y; h.best_a[i] = best + 1; h.td[i] = td;
+    h.newp[i] = pow_f32(__fadd_rn(fabsf(td), h.eps), h.alpha);
+  }
+  // loss = sum(huber) / B  (block reduction; fp32)
+  float s = hub;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) { h.st->loss = __fdiv_rn(s, (float)h.B); h.st->gradmax_bits = 0u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused Adam + max|g| (Flux.Optimise.Adam with Float64 scalars; globalnorm HELPERS:38-46).
+// One pass: read w,m,v,g - write w,m,v (+ optionally the target copy).  Per element, in Float64:
+//   m = b1 m + (1-b1) g ; v = b2 v + ((1-b2) g) g ; d = m/(1-b1p) / (sqrt(v/(1-b2p)) + eps) * eta ; w -= d
+// with m, v, d each rounded to Float32 on store exactly as the reference's broadcasts do.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ g, long long n4, double eta, double beta1, double beta2,
+                                                    double eps, float gscale, DevState* st) {
+  const double c1 = 1.0 - st->b1p, c2 = 1.0 - st->b2p;
+  const double omb1 = 1.0 - beta1, omb2 = 1.0 - beta2;
+  float gmax = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 W = reinterpret_cast<float4*>(w)[i], Mv = reinterpret_cast<float4*>(m)[i], Vv = reinterpret_cast<float4*>(v)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float* wp = &W.x; float* mp = &Mv.x; float* vp = &Vv.x; const float* gp = &G.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gf = gp[k] * gscale;
+      gmax = fmaxf(gmax, fabsf(gf));
+      const double gd = (double)gf;
+      const float mt = (float)(beta1 * (double)mp[k] + omb1 * gd);
+      const float vt = (float)(beta2 * (double)vp[k] + (omb2 * gd) * gd);
+      const float d = (float)((double)mt / c1 / (sqrt((double)vt / c2) + eps) * eta);
+      mp[k] = mt; vp[k] = vt; wp[k] = wp[k] - d;
+    }
+    reinterpret_cast<float4*>(w)[i] = W; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) gmax = fmaxf(gmax, red[k]);
+    atomicMax(&st->gradmax_bits, __float_as_uint(gmax));     // non-negative floats order like their bits
+  }
+}
+
+
+// update_priorities! (PER:76-80) standalone: td -> (|td|+eps)^alpha in place
+__global__ void td_to_priority_kernel(float* __restrict__ p, long long n, float alpha, float eps) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = pow_f32(__fadd_rn(fabsf(p[i]), eps), alpha);
+}
+__global__ void scatter_leaves_kernel(float* __restrict__ tree, int P, const long long* __restrict__ idx, const float* __restrict__ p, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) tree[P + idx[i]] = p[i];
+}
+// Q = (V + A) - mean(A)  for the acting path (DUEL:8-11)
+__global__ void dueling_combine_kernel(const float* __restrict__ V, const float* __restrict__ A, int rows, int nA, float* __restrict__ q) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float tmp[HEAD_MAX_ACTIONS];
+  dueling_q(V, A, r, nA, 1, tmp);
+  for (int k = 0; k < nA; ++k) q[(long long)r * nA + k] = tmp[k];
+}
+
+__global__ void copy_f4_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, long long n, uint32_t v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+// scalars of the finished step -> mapped/pinned host words (loss, grad_norm, error flags)
+__global__ void publish_kernel(const DevState* __restrict__ st, float* __restrict__ out) {
+  out[0] = st->loss; out[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(out)[2] = st->error;
+}
+#endif  // __CUDACC__
+
+}  // namespace dqn

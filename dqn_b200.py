@@ -1,0 +1,11 @@
+"""Import shim: `import dqn_b200` loads the package that lives in ./deepqlearning.jl_b200/ (a directory name
+Python's import statement cannot spell)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "deepqlearning.jl_b200")
+_spec = importlib.util.spec_from_file_location("dqn_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["dqn_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,119 @@
+// CPU check of the implicit-GEMM operand functors (index algebra only; no GPU, no CUDA calls).
+// Each op is run through dqn::igemm_host - the same loadA/loadB/store calls the kernel makes - and compared
+// with a direct formula written independently here.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../deepqlearning.jl_b200/csrc/igemm.cuh"
+using namespace dqn;
+
+static unsigned long long s_ = 88172645463325252ull;
+static float rnd() { s_ ^= s_ << 13; s_ ^= s_ >> 7; s_ ^= s_ << 17; return (float)((s_ >> 11) % 2001) / 1000.f - 1.f; }
+static int fails = 0;
+static void cmp(const char* name, const std::vector<float>& a, const std::vector<float>& b, float tol = 2e-4f) {
+  double mx = 0; size_t at = 0;
+  if (a.size() != b.size()) { printf("FAIL %s size\n", name); ++fails; return; }
+  for (size_t i = 0; i < a.size(); ++i) { double d = std::fabs((double)a[i] - b[i]); if (d > mx) { mx = d; at = i; } }
+  if (mx > tol || mx != mx) { printf("FAIL %s maxdiff %g at %zu (%g vs %g)\n", name, mx, at, a[at], b[at]); ++fails; }
+  else printf("ok   %s maxdiff %g\n", name, mx);
+}
+
+static void test_dense(int M, int K, int N, int act, bool u8) {
+  std::vector<float> X(M * K), W((K + 1) * N), C(M * N), R(M * N);
+  std::vector<uint8_t> X8(M * K);
+  for (auto& v : X) v = rnd();
+  for (auto& v : X8) v = (uint8_t)(rand() & 255);
+  for (auto& v : W) v = rnd();
+  auto x = [&](int m, int k) { return u8 ? (float)X8[m * K + k] / 255.f : X[m * K + k]; };
+  DenseFwdOp op{}; op.X = u8 ? (const void*)X8.data() : (const void*)X.data(); op.ldx = K; op.x_u8 = u8; op.W = W.data(); op.C = C.data(); op.ldc = N; op.act = act;
+  op.M = M; op.N = N; op.K = K; op.vecA = K % 4 == 0; op.vecB = N % 4 == 0;
+  igemm_host(op);
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { double s = W[K * N + n]; for (int k = 0; k < K; ++k) s += (double)x(m, k) * W[k * N + n]; R[m * N + n] = act_apply((float)s, act); }
+  cmp("dense_fwd", C, R);
+  // wgrad
+  std::vector<float> D(M * N), dW((K + 1) * N), RW((K + 1) * N);
+  for (auto& v : D) v = rnd();
+  DenseWgradOp wg{}; wg.X = op.X; wg.ldx = K; wg.x_u8 = u8; wg.D = D.data(); wg.ldd = N; wg.dW = dW.data(); wg.M = K + 1; wg.N = N; wg.K = M; wg.vecA = K % 4 == 0; wg.vecB = N % 4 == 0;
+  igemm_host(wg);
+  for (int k = 0; k <= K; ++k) for (int n = 0; n < N; ++n) { double s = 0; for (int m = 0; m < M; ++m) s += (double)(k < K ? x(m, k) : 1.f) * D[m * N + n]; RW[k * N + n] = (float)s; }
+  cmp("dense_wgrad", dW, RW);
+  // dgrad (with act' of a previous layer output Y and accumulate)
+  std::vector<float> Y(M * K), dX(M * K), RX(M * K);
+  for (auto& v : Y) v = rnd();
+  for (auto& v : dX) v = rnd();
+  RX = dX;
+  DenseDgradOp dg{}; dg.D = D.data(); dg.ldd = N; dg.W = W.data(); dg.dX = dX.data(); dg.ldx = K; dg.Y = Y.data(); dg.ldy = K; dg.act = ACT_TANH; dg.accumulate = 1; dg.apply_act = 1;
+  dg.M = M; dg.N = K; dg.K = N; dg.vecA = N % 4 == 0; dg.vecB = N % 4 == 0;
+  igemm_host(dg);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { double s = 0; for (int n = 0; n < N; ++n) s += (double)D[m * N + n] * W[k * N + n]; RX[m * K + k] = (float)((s + RX[m * K + k]) * act_deriv(Y[m * K + k], ACT_TANH)); }
+  cmp("dense_dgrad", dX, RX);
+}
+
+static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int KW, int S, bool u8) {
+  ConvGeom g{IH, IW, Cin, (IH - KH) / S + 1, (IW - KW) / S + 1, Cout, KH, KW, S};
+  const int K = KH * KW * Cin, P = nimg * g.OH * g.OW;
+  std::vector<float> X(nimg * IH * IW * Cin), W((K + 1) * Cout), Y(P * Cout), R(P * Cout);
+  std::vector<uint8_t> X8(X.size());
+  for (auto& v : X) v = rnd();
+  for (auto& v : X8) v = (uint8_t)(rand() & 255);
+  for (auto& v : W) v = rnd();
+  auto x = [&](int n, int h, int w, int c) { size_t o = ((size_t)(n * IH + h) * IW + w) * Cin + c; return u8 ? (float)X8[o] / 255.f : X[o]; };
+  ConvFwdOp op{}; op.X = u8 ? (const void*)X8.data() : (const void*)X.data(); op.x_u8 = u8; op.W = W.data(); op.Y = Y.data(); op.act = ACT_RELU; op.nimg = nimg; op.g = g;
+  op.M = P; op.N = Cout; op.K = K; op.vecA = Cin % 4 == 0; op.vecB = Cout % 4 == 0;
+  igemm_host(op);
+  for (int n = 0; n < nimg; ++n) for (int oh = 0; oh < g.OH; ++oh) for (int ow = 0; ow < g.OW; ++ow) for (int co = 0; co < Cout; ++co) {
+    double s = W[K * Cout + co];
+    for (int kh = 0; kh < KH; ++kh) for (int kw = 0; kw < KW; ++kw) for (int ci = 0; ci < Cin; ++ci)
+      s += (double)x(n, oh * S + kh, ow * S + kw, ci) * W[((kh * KW + kw) * Cin + ci) * Cout + co];
+    R[((n * g.OH + oh) * g.OW + ow) * Cout + co] = act_apply((float)s, ACT_RELU);
+  }
+  cmp("conv_fwd", Y, R);
+  // wgrad
+  std::vector<float> D(P * Cout), dW((K + 1) * Cout), RW((K + 1) * Cout, 0.f);
+  for (auto& v : D) v = rnd();
+  ConvWgradOp wg{}; wg.X = op.X; wg.x_u8 = u8; wg.D = D.data(); wg.dW = dW.data(); wg.nimg = nimg; wg.g = g; wg.M = K + 1; wg.N = Cout; wg.K = P; wg.vecA = Cin % 4 == 0; wg.vecB = Cout % 4 == 0;
+  igemm_host(wg);
+  {
+    std::vector<double> acc((K + 1) * Cout, 0.0);
+    for (int n = 0; n < nimg; ++n) for (int oh = 0; oh < g.OH; ++oh) for (int ow = 0; ow < g.OW; ++ow) for (int co = 0; co < Cout; ++co) {
+      const double d = D[((n * g.OH + oh) * g.OW + ow) * Cout + co];
+      for (int kh = 0; kh < KH; ++kh) for (int kw = 0; kw < KW; ++kw) for (int ci = 0; ci < Cin; ++ci)
+        acc[((kh * KW + kw) * Cin + ci) * Cout + co] += d * x(n, oh * S + kh, ow * S + kw, ci);
+      acc[K * Cout + co] += d;
+    }
+    for (size_t i = 0; i < acc.size(); ++i) RW[i] = (float)acc[i];
+  }
+  cmp("conv_wgrad", dW, RW, 1e-3f);
+  // dgrad over all parity classes
+  if (!u8) {
+    std::vector<float> dX(X.size(), 123.f), RX(X.size()), Yp(X.size());
+    for (auto& v : Yp) v = rnd();
+    ConvDgradOp dg{}; dg.D = D.data(); dg.W = W.data(); dg.dX = dX.data(); dg.Yprev = Yp.data(); dg.act = ACT_RELU; dg.apply_act = 1; dg.nimg = nimg; dg.g = g;
+    dg.vecA = Cout % 4 == 0; dg.vecB = Cout % 4 == 0;
+    for (int z = 0; z < S * S; ++z) igemm_host(dg, z);
+    std::vector<double> acc(X.size(), 0.0);
+    for (int n = 0; n < nimg; ++n) for (int oh = 0; oh < g.OH; ++oh) for (int ow = 0; ow < g.OW; ++ow) for (int co = 0; co < Cout; ++co) {
+      const double d = D[((n * g.OH + oh) * g.OW + ow) * Cout + co];
+      for (int kh = 0; kh < KH; ++kh) for (int kw = 0; kw < KW; ++kw) for (int ci = 0; ci < Cin; ++ci)
+        acc[((size_t)(n * IH + oh * S + kh) * IW + ow * S + kw) * Cin + ci] += d * W[((kh * KW + kw) * Cin + ci) * Cout + co];
+    }
+    for (size_t i = 0; i < acc.size(); ++i) RX[i] = (float)(acc[i] * act_deriv(Yp[i], ACT_RELU));
+    cmp("conv_dgrad", dX, RX, 1e-3f);
+  }
+}
+
+int main() {
+  test_dense(7, 12, 8, ACT_RELU, false);
+  test_dense(5, 2, 32, ACT_IDENTITY, false);     // README net first layer
+  test_dense(9, 32, 1, ACT_IDENTITY, false);     // value head
+  test_dense(6, 13, 5, ACT_TANH, false);         // nothing aligned
+  test_dense(4, 16, 6, ACT_SIGMOID, true);       // u8 observations
+  test_conv(2, 20, 20, 4, 8, 8, 8, 4, true);     // conv1-like, u8 input
+  test_conv(2, 9, 9, 8, 12, 4, 4, 2, false);     // conv2-like, stride 2
+  test_conv(2, 7, 7, 8, 8, 3, 3, 1, false);      // conv3-like
+  test_conv(1, 12, 11, 3, 5, 4, 3, 2, false);    // odd everything (scalar paths, uneven parity classes)
+  test_conv(1, 10, 10, 4, 4, 3, 3, 2, false);    // KH % S != 0
+  printf(fails ? "FAILED %d\n" : "ALL OK\n", fails);
+  return fails ? 1 : 0;
+}

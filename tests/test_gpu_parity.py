@@ -1,0 +1,306 @@
+"""GPU parity tests: the CUDA path, driven through the C-ABI, against the oracle on identical seeded inputs.
+
+Tolerances (stated once, used everywhere):
+  * sampled leaf indices, ring contents, actions, best_a, sum-tree nodes: BIT-EXACT
+  * Q-values, TD errors, targets, IS weights, loss: normwise relative error <= 1e-5  (north_star)
+  * gradients: normwise relative error <= 1e-4 per step (fp32 accumulation order differs; the distance of both
+    sides to the fp64 evaluation is asserted to be of the same order)
+  * Adam: given the engine's own gradients, the updated parameters match the oracle's Flux-Adam to 1 ulp
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import util
+
+pytestmark = pytest.mark.gpu
+
+SEED = 2
+QTOL = 1e-5
+GTOL = 1e-4
+
+
+def make_engine(lib, spec, dueling=True, double_q=True, per=True, use_graph=True, math_mode=0, B=None, N=None, gamma=0.99):
+    cfg = lib.make_config(util.layer_descs(spec), tuple(reversed(spec["obs"])), spec["nA"], obs_dtype="u8" if spec["u8"] else "f32",
+                          dueling=dueling, double_q=double_q, prioritized_replay=per, batch_size=B or spec["B"],
+                          buffer_size=N or spec["N"], learning_rate=spec["lr"], discount=gamma, seed=SEED, use_graph=use_graph,
+                          math_mode=math_mode)
+    return lib.Engine(cfg)
+
+
+def setup_pair(lib, name, dueling=True, double_q=True, per=True, n_fill=None, **kw):
+    spec = dict(util.SPECS[name])
+    if "B" in kw and kw["B"]:
+        spec["B"] = kw["B"]
+    net = util.make_oracle_net(spec, dueling, seed=21)
+    tgt = util.perturbed_copy(net, seed=22)
+    buf = util.make_oracle_replay(spec)
+    eng = make_engine(lib, spec, dueling, double_q, per, **kw)
+    assert eng.num_params == O.num_params(net)
+    eng.set_params(O.flat_params(net), 0)
+    eng.set_params(O.flat_params(tgt), 1)
+    n = n_fill or (spec["N"] + 37)                       # wraps the ring
+    s, a, r, sp, done = util.random_transitions(spec, n, seed=23)
+    td0 = np.abs(r)
+    k = n // 3
+    for lo, hi in ((0, k), (k, n)):                      # two calls: cursor carried across calls
+        eng.replay_add(s[lo:hi], a[lo:hi], r[lo:hi], sp[lo:hi], done[lo:hi], td0[lo:hi])
+    buf.add_batch(s, a, r, sp, done, td0)
+    return spec, net, tgt, buf, eng
+
+
+def test_params_roundtrip_and_layout(lib):
+    for name, dueling in (("c1_gridworld", True), ("conv_small", True), ("conv_small", False), ("c3_conv", True)):
+        spec = util.SPECS[name]
+        eng = make_engine(lib, spec, dueling, N=64, B=8)
+        flat = np.random.default_rng(0).normal(size=eng.num_params).astype(np.float32)
+        eng.set_params(flat, 0)
+        assert np.array_equal(eng.get_params(0), flat)
+        eng.sync_target()
+        assert np.array_equal(eng.get_params(1), flat)
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["c1_gridworld", "testmdp", "conv_small"])
+def test_replay_ring_priorities_and_tree_bit_exact(lib, name):
+    spec, net, tgt, buf, eng = setup_pair(lib, name)
+    assert eng.replay_size() == (buf._curr_size, buf._idx)
+    assert np.array_equal(eng.get_priorities(), buf._priorities[:buf._curr_size])
+    tree = eng.get_tree()
+    assert np.array_equal(tree[1:], buf.tree.tree[1:])                      # every node, bit for bit
+    idx = np.arange(0, buf._curr_size, max(1, buf._curr_size // 50))
+    s, a, r, sp, d = eng.replay_read(idx)
+    assert np.array_equal(s, buf._s[idx]) and np.array_equal(sp, buf._sp[idx])
+    assert np.array_equal(a, buf._a[idx]) and np.array_equal(r, buf._r[idx]) and np.array_equal(d, buf._done[idx])
+    # update_priorities! (PER.jl:76-80)
+    td = np.random.default_rng(3).normal(0, 1, 20).astype(np.float32)
+    ii = np.random.default_rng(4).choice(buf._curr_size, 20, replace=False)
+    eng.update_priorities(ii, td)
+    buf.update_priorities(ii, td)
+    assert np.array_equal(eng.get_tree()[1:], buf.tree.tree[1:])
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["c1_gridworld", "testmdp", "conv_small", "c2_mlp"])
+def test_sampled_indices_bit_exact(lib, name):
+    spec, net, tgt, buf, eng = setup_pair(lib, name)
+    for call in (0, 1, 2, 17, 2**33 + 5):
+        got = eng.sample_indices(call)
+        want, _ = buf.tree.sample(spec["B"], SEED, call)
+        assert np.array_equal(got, want), f"call {call}"
+        assert len(set(got.tolist())) == spec["B"]
+    eng.close()
+
+
+def test_sampling_small_buffer_forces_redraws(lib):
+    # README-scale: n barely above B => many duplicates in round 0 (SURVEY 7 'Without-replacement semantics')
+    spec, net, tgt, buf, eng = setup_pair(lib, "c1_gridworld", n_fill=40)
+    for call in range(6):
+        got = eng.sample_indices(call)
+        want, att = buf.tree.sample(32, SEED, call)
+        assert np.array_equal(got, want)
+    assert att.max() >= 1
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["c1_gridworld", "testmdp", "conv_small"])
+def test_get_batch_matches_reference_get_batch(lib, name):
+    spec, net, tgt, buf, eng = setup_pair(lib, name)
+    idx, _ = buf.tree.sample(spec["B"], SEED, 5)
+    s, a, r, sp, d, _, w = eng.get_batch(idx)
+    so, ao, ro, spo, do, _, wo = buf.get_batch(idx, total="tree", dequant=util.dequant)
+    assert np.array_equal(s, so) and np.array_equal(sp, spo)                # k/255f0 exactly
+    assert np.array_equal(a, ao) and np.array_equal(r, ro) and np.array_equal(d, do)
+    assert np.array_equal(w, wo) or util.relerr(w, wo) < 1e-6
+    _, _, _, _, _, _, wj = buf.get_batch(idx, total="pairwise", dequant=util.dequant)   # Julia's pairwise sum(prio)
+    assert util.relerr(w, wj) < 1e-6
+    eng.close()
+
+
+def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, qtol=QTOL, gtol=GTOL):
+    B = spec["B"]
+    theta_before = eng.get_params(0)
+    m0, v0, bp0 = eng.get_adam_state()
+    O.set_params(net, theta_before)                                          # teacher forcing (see module docstring)
+    want_idx, _ = buf.tree.sample(B, SEED, call)
+    loss, gn = eng.train_step()
+    idx = eng.last_indices()
+    assert np.array_equal(idx, want_idx)
+    sb, ab, rb, spb, db, _, w = buf.get_batch(idx, total="tree", dequant=util.dequant)
+    out = O.forward_backward(net, tgt, sb, ab - 1, rb, spb, db, w, gamma, double_q, np.float32)
+    out64 = O.forward_backward(net, tgt, sb, ab - 1, rb, spb, db, w, gamma, double_q, np.float64)
+    assert util.relerr(eng.is_weights(), w) < 1e-6
+    q, qo, qt = eng.q(0), eng.q(1), eng.q(2)
+    scale = max(np.abs(out["q"]).max(), np.abs(out["q_target_sp"]).max())
+    for got, key in ((q, "q"), (qo, "q_online_sp"), (qt, "q_target_sp")):
+        assert np.abs(got - out[key]).max() <= qtol * scale, key
+    y, best = eng.targets()
+    src = out["q_online_sp"] if double_q else out["q_target_sp"]
+    top2 = np.sort(src, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4 * scale                         # argmax well separated
+    assert np.array_equal(best[clear] - 1, out["best_a"][clear]) and clear.mean() > 0.9
+    same = (best - 1) == out["best_a"]
+    assert np.abs(y[same] - out["y"][same]).max() <= qtol * scale
+    td = eng.td()
+    assert np.abs(td[same] - out["td"][same]).max() <= 2 * qtol * scale
+    if same.all():
+        assert abs(loss - out["loss"]) <= 1e-5 * max(abs(out["loss"]), 1e-3)
+        g = eng.grads()
+        gref = np.concatenate([x.ravel() for x in out["grads"]])
+        g64 = np.concatenate([x.ravel() for x in out64["grads"]])
+        o = 0
+        for arr in out["grads"]:
+            sl = slice(o, o + arr.size)
+            den = max(np.abs(g64[sl]).max(), 1e-6 * np.abs(g64).max())
+            assert np.abs(g[sl] - gref[sl]).max() <= gtol * den, ("grad array at", o)
+            assert np.abs(g[sl] - g64[sl]).max() <= gtol * den
+            o += arr.size
+        assert abs(gn - out["grad_norm"]) <= gtol * out["grad_norm"]
+        assert gn == np.float32(np.abs(g).max())                             # globalnorm is max|g| (helpers.jl:38-46)
+    # Adam in isolation: oracle Flux-Adam applied to the engine's own gradient
+    g = eng.grads()
+    ps = [p.copy() for p in net.params()]
+    shapes = [p.shape for p in ps]
+    gl, o = [], 0
+    for shp in shapes:
+        n = int(np.prod(shp)); gl.append(g[o:o + n].reshape(shp)); o += n
+    adam = O.Adam(spec["lr"])
+    o = 0
+    for k, shp in enumerate(shapes):
+        n = int(np.prod(shp))
+        adam.state[k] = [m0[o:o + n].reshape(shp).copy(), v0[o:o + n].reshape(shp).copy(), [bp0[0], bp0[1]]]
+        o += n
+    adam.apply(ps, gl)
+    theta_after = eng.get_params(0)
+    want = np.concatenate([p.ravel() for p in ps])
+    ulp = np.spacing(np.abs(want).astype(np.float32)) + np.float32(1e-12)
+    assert (np.abs(theta_after - want) <= 2 * ulp).all(), "Adam update differs from Flux.Optimise.Adam by more than 1-2 ulp"
+    m1, v1, bp1 = eng.get_adam_state()
+    assert bp1 == (bp0[0] * 0.9, bp0[1] * 0.999)
+    assert np.array_equal(m1, np.concatenate([adam.state[k][0].ravel() for k in range(len(shapes))]))
+    # priorities: (|td|+eps)^alpha from the engine's td, tree bit-exact
+    if per:
+        buf.update_priorities(idx, td)
+    assert np.array_equal(eng.get_tree()[1:], buf.tree.tree[1:])
+    return loss, gn
+
+
+CASES = [("c1_gridworld", True, True, True), ("c1_gridworld", False, True, True), ("c1_gridworld", True, False, False),
+         ("testmdp", True, True, True), ("conv_small", True, True, True), ("conv_small", False, False, True), ("c2_mlp", True, True, True)]
+
+
+@pytest.mark.parametrize("name,dueling,double_q,per", CASES)
+def test_batch_train_step_parity(lib, name, dueling, double_q, per):
+    spec, net, tgt, buf, eng = setup_pair(lib, name, dueling, double_q, per)
+    opt = O.Adam(spec["lr"])
+    for call in range(4):
+        check_step(spec, net, tgt, buf, eng, opt, call, double_q, per)
+        if call == 1:                                                        # Flux.loadparams!(target_q, ...) solver.jl:142-145
+            eng.sync_target()
+            O.set_params(tgt, eng.get_params(0))
+            assert np.array_equal(eng.get_params(1), eng.get_params(0))
+    eng.close()
+
+
+def test_batch_train_step_parity_c3_full_batch(lib):
+    # BASELINE.json configs[2] network at its full batch (256); small buffer so the oracle finishes in seconds
+    spec, net, tgt, buf, eng = setup_pair(lib, "c3_conv", n_fill=600)
+    opt = O.Adam(spec["lr"])
+    for call in range(2):
+        check_step(spec, net, tgt, buf, eng, opt, call, True, True)
+    eng.close()
+
+
+def test_graph_and_eager_are_bit_identical(lib):
+    res = []
+    for use_graph in (True, False):
+        spec, net, tgt, buf, eng = setup_pair(lib, "conv_small", use_graph=use_graph)
+        out = [eng.train_step() for _ in range(3)]
+        res.append((out, eng.get_params(0), eng.get_tree(), eng.td()))
+        eng.close()
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert np.array_equal(a, b)
+
+
+def test_train_step_with_indices_equals_sampled_step(lib):
+    spec, net, tgt, buf, eng = setup_pair(lib, "testmdp")
+    spec2, net2, tgt2, buf2, eng2 = setup_pair(lib, "testmdp")
+    idx = eng.sample_indices(0)
+    a = eng.train_step()
+    b = eng2.train_step_with_indices(idx)
+    assert a == b and np.array_equal(eng.get_params(0), eng2.get_params(0))
+    eng.close(); eng2.close()
+
+
+@pytest.mark.parametrize("name,dueling", [("c1_gridworld", True), ("conv_small", True), ("conv_small", False), ("testmdp", True)])
+def test_acting_q_values(lib, name, dueling):
+    spec, net, tgt, buf, eng = setup_pair(lib, name, dueling)
+    s, a, r, sp, done = util.random_transitions(spec, 70, seed=31)         # more rows than one chunk for c1
+    q = eng.q_values(s, 0)
+    want = net(util.dequant(s))
+    assert np.abs(q - want).max() <= QTOL * np.abs(want).max()
+    qt = eng.q_values(s[:3], 1)
+    assert np.abs(qt - tgt(util.dequant(s[:3]))).max() <= QTOL * np.abs(want).max()
+    eng.close()
+
+
+def test_error_codes_mirror_the_reference_asserts(lib):
+    spec = util.SPECS["c1_gridworld"]
+    eng = make_engine(lib, spec)
+    s, a, r, sp, done = util.random_transitions(spec, 10, seed=1)
+    eng.replay_add(s, a, r, sp, done, np.abs(r))
+    with pytest.raises(lib.DQNError) as ei:                                  # PER.jl:83 @assert r._curr_size >= r.batch_size
+        eng.train_step()
+    assert ei.value.code == lib._capi.DQN_ERR_STATE
+    with pytest.raises(lib.DQNError) as ei:                                  # PER.jl:66 @assert td_err + eps > 0
+        eng.replay_add(s[:1], a[:1], r[:1], sp[:1], done[:1], np.array([-1.0], np.float32))
+    assert ei.value.code == lib._capi.DQN_ERR_STATE
+    with pytest.raises(lib.DQNError):
+        eng.replay_add(s[:1], np.array([9], np.int32), r[:1], sp[:1], done[:1], np.abs(r[:1]))
+    with pytest.raises(lib.DQNError):
+        eng.set_params(np.zeros(3, np.float32))
+    with pytest.raises(lib.DQNError):                                        # dueling on a chain without a trailing Dense (dueling.jl:47-50)
+        lib.Engine(lib.make_config([dict(kind=2, act=0, in_=0, out=0)], (2,), 4))
+    eng.close()
+
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_engine_against_committed_golden_vectors(lib, path):
+    g = np.load(path)
+    base = os.path.basename(path)[:-4]
+    name, flags = base.rsplit("_", 1)
+    dueling, double_q = flags[1] == "1", flags[3] == "1"
+    spec = util.SPECS[name]
+    eng = make_engine(lib, spec, dueling, double_q)
+    eng.set_params(g["theta0"], 0)
+    eng.set_params(g["theta_t"], 1)
+    eng.replay_add(g["s"], g["a"], g["r"], g["sp"], g["done"], np.abs(g["r"]))
+    assert np.array_equal(eng.sample_indices(0), g["idx"])
+    loss, gn = eng.train_step()
+    assert np.array_equal(eng.last_indices(), g["idx"])
+    scale = np.abs(g["q"]).max()
+    assert np.abs(eng.q(0) - g["q"]).max() <= QTOL * scale
+    assert np.abs(eng.q(0) - g["q64"]).max() <= QTOL * scale
+    assert np.array_equal(eng.targets()[1] - 1, g["best_a"])
+    assert np.abs(eng.td() - g["td"]).max() <= 2 * QTOL * scale
+    assert abs(loss - g["loss"]) <= 1e-5 * abs(g["loss"])
+    assert util.relerr(eng.grads(), g["grads64"]) <= GTOL
+    assert abs(gn - g["grad_norm"]) <= GTOL * g["grad_norm"]
+    assert np.abs(eng.get_priorities() - g["prio1"][:eng.replay_size()[0]]).max() <= 1e-5
+    eng.close()
+
+
+def test_learning_signal_fixed_batch(lib):
+    # repeated steps on the same indices drive the loss down (sanity of sign conventions end to end)
+    spec, net, tgt, buf, eng = setup_pair(lib, "testmdp")
+    idx = eng.sample_indices(0)
+    losses = [eng.train_step_with_indices(idx)[0] for _ in range(60)]
+    assert losses[-1] < 0.5 * losses[0]
+    eng.close()
