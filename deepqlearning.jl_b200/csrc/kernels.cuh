@@ -371,9 +371,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
       const float gf = gp[k] * gscale;
       gmax = fmaxf(gmax, fabsf(gf));
       const double gd = (double)gf;
-      const float mt = (float)(beta1 * (double)mp[k] + omb1 * gd);
-      const float vt = (float)(beta2 * (double)vp[k] + (omb2 * gd) * gd);
-      const float d = (float)((double)mt / c1 / (sqrt((double)vt / c2) + eps) * eta);
+      // explicit _rn intrinsics: no FMA contraction, every Float64 op rounds separately as the reference's broadcast does
+      const float mt = (float)__dadd_rn(__dmul_rn(beta1, (double)mp[k]), __dmul_rn(omb1, gd));
+      const float vt = (float)__dadd_rn(__dmul_rn(beta2, (double)vp[k]), __dmul_rn(__dmul_rn(omb2, gd), gd));
+      const float d = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, c1), __dadd_rn(__dsqrt_rn(__ddiv_rn((double)vt, c2)), eps)), eta);
       mp[k] = mt; vp[k] = vt; wp[k] = wp[k] - d;
     }
     reinterpret_cast<float4*>(w)[i] = W; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
