@@ -205,11 +205,22 @@ def test_batch_train_step_parity(lib, name, dueling, double_q, per):
     eng.close()
 
 
-def test_batch_train_step_parity_c3_full_batch(lib):
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fp32", "3xtf32"])
+def test_batch_train_step_parity_c3_full_batch(lib, math_mode):
     # BASELINE.json configs[2] network at its full batch (256); small buffer so the oracle finishes in seconds
-    spec, net, tgt, buf, eng = setup_pair(lib, "c3_conv", n_fill=600)
+    spec, net, tgt, buf, eng = setup_pair(lib, "c3_conv", n_fill=600, math_mode=math_mode)
     opt = O.Adam(spec["lr"])
     for call in range(2):
+        check_step(spec, net, tgt, buf, eng, opt, call, True, True)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["conv_small", "c2_mlp", "testmdp"])
+def test_batch_train_step_parity_tcgen05(lib, name):
+    # the tensor-core (3xTF32) path takes every contraction it covers; the rest stays on the fp32 kernels
+    spec, net, tgt, buf, eng = setup_pair(lib, name, math_mode=1)
+    opt = O.Adam(spec["lr"])
+    for call in range(3):
         check_step(spec, net, tgt, buf, eng, opt, call, True, True)
     eng.close()
 
