@@ -1,0 +1,26 @@
+"""A few eager (non-graph) batch_train! steps of config 3 for ncu captures: python scripts/one_step.py <math_mode> [steps]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dqn_b200 as lib       # noqa: E402
+import oracle as O           # noqa: E402
+import util                  # noqa: E402
+
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+spec = util.SPECS["c3_conv"]
+cfg = lib.make_config(util.layer_descs(spec), (84, 84, 4), 6, obs_dtype="u8", batch_size=256, buffer_size=N, learning_rate=1e-4,
+                      discount=0.99, seed=2, math_mode=mode, use_graph=False)
+eng = lib.Engine(cfg)
+eng.set_params(O.flat_params(util.make_oracle_net(spec, True, seed=1)), 0)
+eng.sync_target()
+eng.replay_fill_synthetic(N, 1000)
+for _ in range(steps):
+    print(eng.train_step())
+eng.close()
