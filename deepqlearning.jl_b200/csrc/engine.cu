@@ -126,6 +126,7 @@ struct dqn_engine {
   int profiling = 0; std::vector<ProfRec> prof; std::vector<cudaEvent_t> ev_pool;
   uint32_t* flush_buf = nullptr; long long flush_n = 0;
   bool capturing = false;
+  int tc_variant = 0;
 };
 
 namespace {
@@ -481,7 +482,10 @@ void build_topology(E* e) {
     if (l.in != C) fail(DQN_ERR_INVALID, "conv layer %d expects %d input channels, gets %d", i + 1, l.in, C);
     if (l.kh < 1 || l.kw < 1 || l.stride < 1 || l.kh > H || l.kw > W) fail(DQN_ERR_INVALID, "conv layer %d geometry", i + 1);
     ConvL cl{};
-    cl.g = ConvGeom{H, W, C, (H - l.kh) / l.stride + 1, (W - l.kw) / l.stride + 1, l.out, l.kh, l.kw, l.stride};
+    cl.g.IH = H; cl.g.IW = W; cl.g.Cin = C; cl.g.OH = (H - l.kh) / l.stride + 1; cl.g.OW = (W - l.kw) / l.stride + 1;
+    cl.g.Cout = l.out; cl.g.KH = l.kh; cl.g.KW = l.kw; cl.g.S = l.stride;
+    if (l.stride > 4) fail(DQN_ERR_UNSUPPORTED, "conv stride above 4");
+    cl.g.init();
     cl.w = Mat{0, l.kh * l.kw * C, l.out, l.act};
     e->convs.push_back(cl);
     H = cl.g.OH; W = cl.g.OW; C = l.out; ++i;

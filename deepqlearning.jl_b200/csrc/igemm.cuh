@@ -47,40 +47,101 @@ DQN_HD float act_deriv(float y, int act) {
   }
 }
 
+// Float32(k)/255f0 without a division: q = k*r, one Newton correction q + fma(-q,255,k)*r.  Exhaustively equal to
+// the IEEE quotient for all 256 byte values (checked on the CPU in tests/test_oracle_cpu.py and on the GPU by the
+// bit-exact get_batch test).
 DQN_HD float u8_to_f32(uint8_t k) {
+  const float kf = (float)k, r = 0.00392156885936856269836425781250f;   // fl(1/255)
+  const float q = kf * r;
 #ifdef __CUDA_ARCH__
-  return __fdiv_rn((float)k, 255.f);       // exactly Float32(k)/255f0, never a reciprocal multiply
+  return __fmaf_rn(__fmaf_rn(-q, 255.f, kf), r, q);
 #else
-  return (float)k / 255.f;
+  return (float)((double)(float)((double)(-q) * 255.0 + (double)kf) * (double)r + (double)q);
 #endif
 }
 
 DQN_HD float4 make4(float a, float b, float c, float d) { float4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 
+// division by a runtime-constant divisor: q = umulhi(n, mul) >> shr, exact for n < 2^31 (mul = ceil(2^p/d), p = 31 + ceil(log2 d))
+struct FastDiv {
+  uint32_t d, mul, shr;
+  void init(uint32_t dd) {
+    d = dd; mul = 0; shr = 0;
+    if (dd <= 1) return;
+    uint32_t lg = 0; while ((1u << lg) < dd) ++lg;
+    const uint32_t p = 31 + lg;
+    mul = (uint32_t)(((1ull << p) + dd - 1) / dd);
+    shr = p - 32;
+  }
+  DQN_HD uint32_t div(uint32_t n) const {
+    if (d <= 1) return n;
+#ifdef __CUDA_ARCH__
+    return __umulhi(n, mul) >> shr;
+#else
+    return (uint32_t)(((uint64_t)n * mul) >> 32) >> shr;
+#endif
+  }
+  DQN_HD void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
+// read-only global loads (operands are never written by the kernel that gathers them)
+DQN_HD float4 ldg4(const float* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(reinterpret_cast<const float4*>(p));
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+DQN_HD float ldg1(const float* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+DQN_HD uchar4 ldg4u(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(reinterpret_cast<const uchar4*>(p));
+#else
+  return *reinterpret_cast<const uchar4*>(p);
+#endif
+}
+DQN_HD uint8_t ldg1u(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // Load 4 consecutive elements p[0..3] of an fp32 or u8 array with a count guard (cnt = how many are in range).
 DQN_HD float4 load4_f32(const float* p, int cnt, bool vec_ok) {
-  if (cnt >= 4 && vec_ok) return *reinterpret_cast<const float4*>(p);
+  if (cnt >= 4 && vec_ok) return ldg4(p);
   float4 v = make4(0.f, 0.f, 0.f, 0.f);
-  if (cnt > 0) v.x = p[0];
-  if (cnt > 1) v.y = p[1];
-  if (cnt > 2) v.z = p[2];
-  if (cnt > 3) v.w = p[3];
+  if (cnt > 0) v.x = ldg1(p);
+  if (cnt > 1) v.y = ldg1(p + 1);
+  if (cnt > 2) v.z = ldg1(p + 2);
+  if (cnt > 3) v.w = ldg1(p + 3);
   return v;
 }
 DQN_HD float4 load4_u8(const uint8_t* p, int cnt, bool vec_ok) {
   if (cnt >= 4 && vec_ok) {
-    uchar4 q = *reinterpret_cast<const uchar4*>(p);
+    const uchar4 q = ldg4u(p);
     return make4(u8_to_f32(q.x), u8_to_f32(q.y), u8_to_f32(q.z), u8_to_f32(q.w));
   }
   float4 v = make4(0.f, 0.f, 0.f, 0.f);
-  if (cnt > 0) v.x = u8_to_f32(p[0]);
-  if (cnt > 1) v.y = u8_to_f32(p[1]);
-  if (cnt > 2) v.z = u8_to_f32(p[2]);
-  if (cnt > 3) v.w = u8_to_f32(p[3]);
+  if (cnt > 0) v.x = u8_to_f32(ldg1u(p));
+  if (cnt > 1) v.y = u8_to_f32(ldg1u(p + 1));
+  if (cnt > 2) v.z = u8_to_f32(ldg1u(p + 2));
+  if (cnt > 3) v.w = u8_to_f32(ldg1u(p + 3));
   return v;
 }
+// set element j (0..3) of a float4 without dynamic indexing (keeps the value in registers)
+DQN_HD void set4(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else if (j == 3) v.w = x; }
 
+// Per-row (m) and per-column-of-A (k) decode contexts, hoisted out of the inner loops by the kernels.
 struct ACtx { long long base; int i0, i1; int valid; };
+struct KCtx { long long off; int t0, t1, t2; };
 
 // ------------------------------------------------------------------------------------------------
 // Dense forward:  C[m][n] = act( sum_k X[m][k] W[k][n] + W[K][n] )
@@ -93,17 +154,24 @@ struct DenseFwdOp {
   int vecA, vecB;
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldx; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD float4 loadA(const ACtx& c, int, int k) const {
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx&, int, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     if (x_u8) return load4_u8((const uint8_t*)X + c.base + k, K - k, vecA);
     return load4_f32((const float*)X + c.base + k, K - k, vecA);
   }
-  DQN_HD float4 loadB(int k, int n) const {
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(W + (long long)k * N + n, N - n, vecB);
   }
   DQN_HD void store(int m, int n, float v) const {
     C[(long long)m * ldc + n] = act_apply(v + W[(long long)K * N + n], act);
+  }
+  DQN_HD bool can_store4() const { return (N % 4 == 0) && (ldc % 4 == 0); }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    const float4 b = ldg4(W + (long long)K * N + n);
+    *reinterpret_cast<float4*>(C + (long long)m * ldc + n) =
+        make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
   }
 };
 
@@ -118,11 +186,12 @@ struct DenseDgradOp {
   int vecA, vecB;
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD float4 loadA(const ACtx& c, int, int k) const {
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx&, int, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     return load4_f32(D + c.base + k, K - k, vecA);
   }
-  DQN_HD float4 loadB(int k, int n) const {      // 4 consecutive k at column n
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {      // 4 consecutive k at column n
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(W + (long long)n * K + k, K - k, vecB);
   }
@@ -131,6 +200,16 @@ struct DenseDgradOp {
     if (accumulate) v += dX[o];
     if (apply_act) v *= act_deriv(Y[(long long)m * ldy + n], act);
     dX[o] = v;
+  }
+  DQN_HD bool can_store4() const { return (ldx % 4 == 0) && (ldy % 4 == 0) && (N % 4 == 0); }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    float4* o = reinterpret_cast<float4*>(dX + (long long)m * ldx + n);
+    if (accumulate) { const float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    if (apply_act) {
+      const float4 y = *reinterpret_cast<const float4*>(Y + (long long)m * ldy + n);
+      v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
+    }
+    *o = v;
   }
 };
 
@@ -144,26 +223,40 @@ struct DenseWgradOp {
   int vecA, vecB;
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = m; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD float4 loadA(const ACtx& c, int m, int k) const {   // 4 consecutive m at batch row k
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int m, int k) const {   // 4 consecutive m at batch row k
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     const int kin = M - 1;
-    int cnt = kin - m;                                      // real features left
+    const int cnt = kin - m;                                // real features left
     float4 v;
     if (cnt <= 0) v = make4(0, 0, 0, 0);
-    else if (x_u8) v = load4_u8((const uint8_t*)X + (long long)k * ldx + m, cnt, vecA);
-    else v = load4_f32((const float*)X + (long long)k * ldx + m, cnt, vecA);
-    if (cnt >= 0 && cnt < 4) { float* f = &v.x; f[cnt] = 1.f; }   // the ones column that yields db
+    else if (x_u8) v = load4_u8((const uint8_t*)X + kc.off + m, cnt, vecA);
+    else v = load4_f32((const float*)X + kc.off + m, cnt, vecA);
+    if (cnt >= 0 && cnt < 4) set4(v, cnt, 1.f);             // the ones column that yields db
     return v;
   }
-  DQN_HD float4 loadB(int k, int n) const {
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * ldd + n, N - n, vecB);
   }
   DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v; }
+  DQN_HD bool can_store4() const { return N % 4 == 0; }
+  DQN_HD void store4(int m, int n, float4 v) const { *reinterpret_cast<float4*>(dW + (long long)m * N + n) = v; }
 };
 
 // ------------------------------------------------------------------------------------------------
-struct ConvGeom { int IH, IW, Cin, OH, OW, Cout, KH, KW, S; };
+struct ConvGeom {
+  int IH, IW, Cin, OH, OW, Cout, KH, KW, S;
+  FastDiv fCin, fKW, fOW, fOH, fCout;          // filled by init()
+  FastDiv fBW[4], fAH[4], fTW[4];              // dgrad parity classes (S <= 4)
+  void init() {
+    fCin.init(Cin); fKW.init(KW); fOW.init(OW); fOH.init(OH); fCout.init(Cout);
+    for (int p = 0; p < 4; ++p) {
+      const int bw = p < S ? (IW - p + S - 1) / S : 1, ah = p < S ? (IH - p + S - 1) / S : 1, tw = p < S ? (KW - p + S - 1) / S : 1;
+      fBW[p].init(bw > 0 ? bw : 1); fAH[p].init(ah > 0 ? ah : 1); fTW[p].init(tw > 0 ? tw : 1);
+    }
+  }
+};
 
 // Conv forward (NHWC, weights [(KH*KW*Cin+1)][Cout], taps already flipped to cross-correlation order)
 struct ConvFwdOp {
@@ -176,32 +269,41 @@ struct ConvFwdOp {
   DQN_HD ACtx prepA(int m) const {
     ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = 0;
     if (c.valid) {
-      int ow = m % g.OW; int t = m / g.OW; int oh = t % g.OH; int n = t / g.OH;
+      uint32_t t, ow, n, oh;
+      g.fOW.divmod((uint32_t)m, t, ow); g.fOH.divmod(t, n, oh);
       c.base = (((long long)n * g.IH + oh * g.S) * g.IW + ow * g.S) * g.Cin;
     }
     return c;
   }
   DQN_HD long long koff(int k) const {
-    int ci = k % g.Cin; int t = k / g.Cin; int kw = t % g.KW; int kh = t / g.KW;
+    uint32_t t, ci, kh, kw;
+    g.fCin.divmod((uint32_t)k, t, ci); g.fKW.divmod(t, kh, kw);
     return ((long long)kh * g.IW + kw) * g.Cin + ci;
   }
-  DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(((const uint8_t*)X)[o]) : ((const float*)X)[o]; }
-  DQN_HD float4 loadA(const ACtx& c, int, int k) const {
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k < K ? koff(k) : 0; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(ldg1u((const uint8_t*)X + o)) : ldg1((const float*)X + o); }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     if (vecA) {     // Cin % 4 == 0: the four k are four channels of one tap
-      long long o = c.base + koff(k);
-      return x_u8 ? load4_u8((const uint8_t*)X + o, 4, true) : load4_f32((const float*)X + o, 4, true);
+      const long long o = c.base + kc.off;
+      return x_u8 ? load4_u8((const uint8_t*)X + o, 4, true) : ldg4((const float*)X + o);
     }
-    float4 v = make4(0, 0, 0, 0); float* f = &v.x;
-    for (int j = 0; j < 4 && k + j < K; ++j) f[j] = ld1(c.base + koff(k + j));
+    float4 v = make4(0, 0, 0, 0);
+    for (int j = 0; j < 4 && k + j < K; ++j) set4(v, j, ld1(c.base + koff(k + j)));
     return v;
   }
-  DQN_HD float4 loadB(int k, int n) const {
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(W + (long long)k * N + n, N - n, vecB);
   }
   DQN_HD void store(int m, int n, float v) const {
     Y[(long long)m * N + n] = act_apply(v + W[(long long)K * N + n], act);
+  }
+  DQN_HD bool can_store4() const { return N % 4 == 0; }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    const float4 b = ldg4(W + (long long)K * N + n);
+    *reinterpret_cast<float4*>(Y + (long long)m * N + n) =
+        make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
   }
 };
 
@@ -214,31 +316,40 @@ struct ConvWgradOp {
   int vecA, vecB;
   DQN_HD void set_class(int) {}
   DQN_HD long long moff(int m) const {
-    int ci = m % g.Cin; int t = m / g.Cin; int kw = t % g.KW; int kh = t / g.KW;
+    uint32_t t, ci, kh, kw;
+    g.fCin.divmod((uint32_t)m, t, ci); g.fKW.divmod(t, kh, kw);
     return ((long long)kh * g.IW + kw) * g.Cin + ci;
   }
   DQN_HD ACtx prepA(int m) const { ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = (c.valid && m < M - 1) ? moff(m) : 0; return c; }
-  DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(((const uint8_t*)X)[o]) : ((const float*)X)[o]; }
-  DQN_HD float4 loadA(const ACtx& c, int m, int k) const {   // 4 consecutive m at pixel k
-    if (!c.valid || k >= K) return make4(0, 0, 0, 0);
-    int ow = k % g.OW; int t = k / g.OW; int oh = t % g.OH; int n = t / g.OH;
-    long long pb = (((long long)n * g.IH + oh * g.S) * g.IW + ow * g.S) * g.Cin;
-    const int kk = M - 1;
-    int cnt = kk - m;
-    float4 v = make4(0, 0, 0, 0); float* f = &v.x;
-    if (cnt >= 4 && vecA) {
-      v = x_u8 ? load4_u8((const uint8_t*)X + pb + c.base, 4, true) : load4_f32((const float*)X + pb + c.base, 4, true);
-    } else {
-      for (int j = 0; j < 4 && j < cnt; ++j) f[j] = ld1(pb + moff(m + j));
+  DQN_HD KCtx prepK(int k) const {          // pixel -> offset of its receptive field origin
+    KCtx c; c.t0 = c.t1 = c.t2 = 0; c.off = 0;
+    if (k < K) {
+      uint32_t t, ow, n, oh;
+      g.fOW.divmod((uint32_t)k, t, ow); g.fOH.divmod(t, n, oh);
+      c.off = (((long long)n * g.IH + oh * g.S) * g.IW + ow * g.S) * g.Cin;
     }
-    if (cnt >= 0 && cnt < 4) f[cnt] = 1.f;
+    return c;
+  }
+  DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(ldg1u((const uint8_t*)X + o)) : ldg1((const float*)X + o); }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int m, int k) const {   // 4 consecutive m at pixel k
+    if (!c.valid || k >= K) return make4(0, 0, 0, 0);
+    const int cnt = (M - 1) - m;
+    float4 v = make4(0, 0, 0, 0);
+    if (cnt >= 4 && vecA) {
+      v = x_u8 ? load4_u8((const uint8_t*)X + kc.off + c.base, 4, true) : ldg4((const float*)X + kc.off + c.base);
+    } else {
+      for (int j = 0; j < 4 && j < cnt; ++j) set4(v, j, ld1(kc.off + moff(m + j)));
+    }
+    if (cnt >= 0 && cnt < 4) set4(v, cnt, 1.f);
     return v;
   }
-  DQN_HD float4 loadB(int k, int n) const {
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * N + n, N - n, vecB);
   }
   DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v; }
+  DQN_HD bool can_store4() const { return N % 4 == 0; }
+  DQN_HD void store4(int m, int n, float4 v) const { *reinterpret_cast<float4*>(dW + (long long)m * N + n) = v; }
 };
 
 // Conv dgrad by stride-parity class (ph,pw): rows are the input pixels with ih%S==ph, iw%S==pw, and only
@@ -247,56 +358,75 @@ struct ConvDgradOp {
   static constexpr bool A_MCONTIG = false, B_KCONTIG = true, Z_IS_CLASS = true;
   const float* D; const float* W; float* dX; const float* Yprev; int act; int apply_act; int nimg; ConvGeom g;
   int ph, pw, AH, BW, TH, TW;
+  FastDiv fbw, fah, ftw;     // the class's divisors, picked by set_class with static indices (no local-memory copy)
   int M, N, K;               // set by set_class: M = nimg*AH*BW, N = Cin, K = TH*TW*Cout
   int vecA, vecB;
   DQN_HD void set_class(int z) {
-    ph = z / g.S; pw = z % g.S;
+    ph = z / g.S; pw = z - ph * g.S;
     AH = (g.IH - ph + g.S - 1) / g.S; BW = (g.IW - pw + g.S - 1) / g.S;
     TH = (g.KH - ph + g.S - 1) / g.S; TW = (g.KW - pw + g.S - 1) / g.S;
     if (TH < 0) TH = 0; if (TW < 0) TW = 0;
+    fbw = pw == 0 ? g.fBW[0] : pw == 1 ? g.fBW[1] : pw == 2 ? g.fBW[2] : g.fBW[3];
+    ftw = pw == 0 ? g.fTW[0] : pw == 1 ? g.fTW[1] : pw == 2 ? g.fTW[2] : g.fTW[3];
+    fah = ph == 0 ? g.fAH[0] : ph == 1 ? g.fAH[1] : ph == 2 ? g.fAH[2] : g.fAH[3];
     M = nimg * AH * BW; N = g.Cin; K = TH * TW * g.Cout;
   }
   DQN_HD ACtx prepA(int m) const {
     ACtx c; c.valid = m < M; c.base = 0; c.i0 = c.i1 = 0;
-    if (c.valid) { int b = m % BW; int t = m / BW; int a = t % AH; int n = t / AH; c.i0 = a; c.i1 = b; c.base = n; }
+    if (c.valid) { uint32_t t, b, n, a; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, n, a); c.i0 = (int)a; c.i1 = (int)b; c.base = n; }
     return c;
   }
-  DQN_HD float4 loadA(const ACtx& c, int, int k) const {     // 4 consecutive co of one tap
+  DQN_HD KCtx prepK(int k) const {      // k -> (th, tw, co)
+    KCtx c; c.off = 0; c.t0 = c.t1 = c.t2 = 0;
+    if (k < K) { uint32_t t, co, th, tw; g.fCout.divmod((uint32_t)k, t, co); ftw.divmod(t, th, tw); c.t0 = (int)th; c.t1 = (int)tw; c.t2 = (int)co; }
+    return c;
+  }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int, int k) const {     // 4 consecutive co of one tap
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
-    float4 v = make4(0, 0, 0, 0); float* f = &v.x;
     if (vecA) {
-      int co = k % g.Cout; int t = k / g.Cout; int tw = t % TW; int th = t / TW;
-      int oh = c.i0 - th, ow = c.i1 - tw;
-      if (oh < 0 || oh >= g.OH || ow < 0 || ow >= g.OW) return v;
-      return load4_f32(D + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + co, 4, true);
+      const int oh = c.i0 - kc.t0, ow = c.i1 - kc.t1;
+      if (oh < 0 || oh >= g.OH || ow < 0 || ow >= g.OW) return make4(0, 0, 0, 0);
+      return ldg4(D + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + kc.t2);
     }
+    float4 v = make4(0, 0, 0, 0);
     for (int j = 0; j < 4 && k + j < K; ++j) {
-      int co = (k + j) % g.Cout; int t = (k + j) / g.Cout; int tw = t % TW; int th = t / TW;
-      int oh = c.i0 - th, ow = c.i1 - tw;
-      if (oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW) f[j] = D[(((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + co];
+      const KCtx q = prepK(k + j);
+      const int oh = c.i0 - q.t0, ow = c.i1 - q.t1;
+      if (oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW) set4(v, j, ldg1(D + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + q.t2));
     }
     return v;
   }
-  DQN_HD float4 loadB(int k, int n) const {                  // 4 consecutive k (= co) at ci = n
+  DQN_HD float4 loadB(const KCtx& kc, int k, int n) const {                  // 4 consecutive k (= co) at ci = n
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
-    float4 v = make4(0, 0, 0, 0); float* f = &v.x;
     if (vecB) {
-      int co = k % g.Cout; int t = k / g.Cout; int tw = t % TW; int th = t / TW;
-      int kh = ph + th * g.S, kw = pw + tw * g.S;
-      return load4_f32(W + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + co, 4, true);
+      const int kh = ph + kc.t0 * g.S, kw = pw + kc.t1 * g.S;
+      return ldg4(W + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + kc.t2);
     }
+    float4 v = make4(0, 0, 0, 0);
     for (int j = 0; j < 4 && k + j < K; ++j) {
-      int co = (k + j) % g.Cout; int t = (k + j) / g.Cout; int tw = t % TW; int th = t / TW;
-      int kh = ph + th * g.S, kw = pw + tw * g.S;
-      f[j] = W[(((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + co];
+      const KCtx q = prepK(k + j);
+      const int kh = ph + q.t0 * g.S, kw = pw + q.t1 * g.S;
+      set4(v, j, ldg1(W + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + q.t2));
     }
     return v;
+  }
+  DQN_HD long long out_off(int m, int n) const {
+    uint32_t t, b, img, a; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, img, a);
+    return (((long long)img * g.IH + a * g.S + ph) * g.IW + b * g.S + pw) * g.Cin + n;
   }
   DQN_HD void store(int m, int n, float v) const {
-    int b = m % BW; int t = m / BW; int a = t % AH; int img = t / AH;
-    long long o = (((long long)img * g.IH + a * g.S + ph) * g.IW + b * g.S + pw) * g.Cin + n;
+    const long long o = out_off(m, n);
     if (apply_act) v *= act_deriv(Yprev[o], act);
     dX[o] = v;
+  }
+  DQN_HD bool can_store4() const { return g.Cin % 4 == 0; }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    const long long o = out_off(m, n);
+    if (apply_act) {
+      const float4 y = *reinterpret_cast<const float4*>(Yprev + o);
+      v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
+    }
+    *reinterpret_cast<float4*>(dX + o) = v;
   }
 };
 
@@ -353,12 +483,20 @@ igemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_st
   float4 ra[A_PER], rb[B_PER];
   auto gload = [&](int kt) {
     const int k0 = kt * BK;
+    if (!Op::A_MCONTIG) {
+      const KCtx kc = op.prepK(k0 + a_k[0]);                 // every A fragment of this thread sits in the same k chunk
 #pragma unroll
-    for (int i = 0; i < A_PER; ++i) ra[i] = op.loadA(actx[i], m0 + a_m[i], k0 + a_k[i]);
+      for (int i = 0; i < A_PER; ++i) ra[i] = op.loadA(actx[i], kc, m0 + a_m[i], k0 + a_k[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) { const KCtx kc = op.prepK(k0 + a_k[i]); ra[i] = op.loadA(actx[i], kc, m0 + a_m[i], k0 + a_k[i]); }
+    }
+    KCtx kb; kb.off = 0; kb.t0 = kb.t1 = kb.t2 = 0;
+    if (Op::B_KCONTIG) kb = op.prepK(k0 + b_k[0]);
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       int e = tid + i * NT;
-      rb[i] = (e < B_F4) ? op.loadB(k0 + b_k[i], n0 + b_n[i]) : make4(0, 0, 0, 0);
+      rb[i] = (e < B_F4) ? op.loadB(kb, k0 + b_k[i], n0 + b_n[i]) : make4(0, 0, 0, 0);
     }
   };
   auto sstore = [&](int buf) {
@@ -413,16 +551,21 @@ igemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_st
   }
 
   // epilogue
+  const bool v4 = (nsplit == 1) && op.can_store4();
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
     if (m >= op.M) continue;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
+    for (int j = 0; j < TN; j += 4) {
       const int n = n0 + tx * TN + j;
-      if (n >= op.N) continue;
-      if (nsplit > 1) ws[(long long)blockIdx.z * ws_stride + (long long)m * op.N + n] = acc[i][j];
-      else op.store(m, n, acc[i][j]);
+      if (v4 && n + 3 < op.N) { op.store4(m, n, make4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3])); continue; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (n + q >= op.N) continue;
+        if (nsplit > 1) ws[(long long)blockIdx.z * ws_stride + (long long)m * op.N + n + q] = acc[i][j + q];
+        else op.store(m, n + q, acc[i][j + q]);
+      }
     }
   }
 }
@@ -452,11 +595,11 @@ inline void igemm_host(Op op, int zclass = 0) {
         float av[4], bv[4];
         if (Op::A_MCONTIG) {
           for (int j = 0; j < 4; ++j) {
-            int mb = (m / 4) * 4; ACtx c = op.prepA(mb); float4 v = op.loadA(c, mb, k4 + j); av[j] = (&v.x)[m - mb];
+            int mb = (m / 4) * 4; ACtx c = op.prepA(mb); KCtx kc = op.prepK(k4 + j); float4 v = op.loadA(c, kc, mb, k4 + j); av[j] = (&v.x)[m - mb];
           }
-        } else { ACtx c = op.prepA(m); float4 v = op.loadA(c, m, k4); av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w; }
-        if (Op::B_KCONTIG) { float4 v = op.loadB(k4, n); bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w; }
-        else { for (int j = 0; j < 4; ++j) { int nb = (n / 4) * 4; float4 v = op.loadB(k4 + j, nb); bv[j] = (&v.x)[n - nb]; } }
+        } else { ACtx c = op.prepA(m); KCtx kc = op.prepK(k4); float4 v = op.loadA(c, kc, m, k4); av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w; }
+        if (Op::B_KCONTIG) { KCtx kc = op.prepK(k4); float4 v = op.loadB(kc, k4, n); bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w; }
+        else { for (int j = 0; j < 4; ++j) { int nb = (n / 4) * 4; KCtx kc = op.prepK(k4 + j); float4 v = op.loadB(kc, k4 + j, nb); bv[j] = (&v.x)[n - nb]; } }
         for (int j = 0; j < 4; ++j) acc += (double)av[j] * (double)bv[j];
       }
       op.store(m, n, (float)acc);

@@ -60,8 +60,8 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+  for (uint32_t spins = 1; !mbar_try(bar, parity); ++spins) {
+    if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -117,8 +117,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <int BN, class Op>
-__global__ void __launch_bounds__(THREADS, (Lay<BN>::SMEM <= 110 * 1024) ? 2 : 1)
+__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+// R   : number of interleaved main accumulators (k-step j accumulates into accumulator j % R).  The tensor core adds
+//       into its fp32 accumulator with truncation, a one-sided error of up to 1 ulp(acc) per MMA; spreading the k-steps
+//       over R accumulators that are summed with round-to-nearest in the epilogue divides that bias by R.
+// SEP : the two small correction products (A_lo B_hi, A_hi B_lo) go to their own accumulator, so the main accumulator
+//       sees one truncating add per k-step instead of three.
+template <int BN, int R, bool SEP, class Op>
+__global__ void __launch_bounds__(THREADS, (Lay<BN>::SMEM <= 110 * 1024 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
 tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride) {
   static_assert(!Op::A_MCONTIG, "A must be K-contiguous for this kernel");
   using L = Lay<BN>;
@@ -139,7 +146,9 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   const int nk = max(kt1 - kt0, 0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int TCOLS = BN < 32 ? 32 : BN;
+  constexpr int NACC = R + (SEP ? 1 : 0);
+  constexpr int TCOLS = pow2_cols(BN * NACC);
+  static_assert(BN * NACC <= 512, "TMEM columns");
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, PROD); mbar_init(bars + 8 * (STAGES + s), 1); }
@@ -154,59 +163,57 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 
   if (warp < 4) {
     // ================= producers =================
-    constexpr int A_PER = BM * KCH / PROD;                     // 8
+    constexpr int A_PER = BM * KCH / PROD;                     // 8 sixteen-byte chunks of A per thread per stage
+    constexpr int B_PER = BN / 16;                             // chunks of B per thread per stage (both B layouts)
     ACtx actx[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (PROD / 8));
     const int ac = tid & 7;
+    auto gload = [&](int it, float4 (&va)[A_PER], float4 (&vb)[B_PER]) {
+      const int k0 = (kt0 + it) * BK;
+      const KCtx kc = op.prepK(k0 + ac * 4);                   // this thread's k chunk: one decode per stage
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) va[i] = op.loadA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + ac * 4);
+      if (Op::B_KCONTIG) {
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+          const int r = (tid >> 3) + i * (PROD / 8);           // same chunk index ac as A
+          vb[i] = op.loadB(kc, k0 + ac * 4, n0 + r);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+          const int e = tid + i * PROD, n4 = e % (BN / 4), k = e / (BN / 4);
+          vb[i] = op.loadB(kc, k0 + k, n0 + n4 * 4);
+        }
+      }
+    };
+    float4 va[A_PER], vb[B_PER];
+    if (nk > 0) gload(0, va, vb);
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
+      float4 na[A_PER], nb[B_PER];
+      if (it + 1 < nk) gload(it + 1, na, nb);                  // next stage's global loads fly while this one is split and stored
       mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
       const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo = a_hi + L::A_BYTES;
       const uint32_t b_hi = a_lo + L::A_BYTES, b_lo = b_hi + L::B_BYTES;
-      const int k0 = (kt0 + it) * BK;
-      float4 va[A_PER];
-#pragma unroll
-      for (int i = 0; i < A_PER; ++i) va[i] = op.loadA(actx[i], m0 + (tid >> 3) + i * (PROD / 8), k0 + ac * 4);
       if (Op::B_KCONTIG) {
-        constexpr int B_PER = (BN * KCH + PROD - 1) / PROD;
-        float4 vb[B_PER];
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) {
-          const int e = tid + i * PROD, r = e >> 3;
-          vb[i] = (r < BN) ? op.loadB(k0 + (e & 7) * 4, n0 + r) : make4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int e = tid + i * PROD, r = e >> 3, c = e & 7;
-          if (r < BN) {
-            float4 hi, lo; split4(vb[i], hi, lo);
-            const uint32_t off = c * L::B_PLANE + (r >> 3) * L::B_SBO + (r & 7) * 16;
-            sts128(b_hi + off, hi); sts128(b_lo + off, lo);
-          }
+          const int r = (tid >> 3) + i * (PROD / 8);
+          float4 hi, lo; split4(vb[i], hi, lo);
+          const uint32_t off = ac * L::B_PLANE + (r >> 3) * L::B_SBO + (r & 7) * 16;
+          sts128(b_hi + off, hi); sts128(b_lo + off, lo);
         }
       } else {
-        constexpr int B_PER = (BK * (BN / 4) + PROD - 1) / PROD;
-        float4 vb[B_PER];
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) {
           const int e = tid + i * PROD, n4 = e % (BN / 4), k = e / (BN / 4);
-          vb[i] = (k < BK) ? op.loadB(k0 + k, n0 + n4 * 4) : make4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int e = tid + i * PROD, n4 = e % (BN / 4), k = e / (BN / 4);
-          if (k < BK) {
-            float4 hi, lo; split4(vb[i], hi, lo);
-            const float* fh = &hi.x; const float* fl = &lo.x;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = n4 * 4 + j;
-              const uint32_t off = (k >> 2) * L::B_PLANE + (n >> 3) * L::B_SBO + (n & 7) * 16 + (k & 3) * 4;
-              sts32(b_hi + off, fh[j]); sts32(b_lo + off, fl[j]);
-            }
-          }
+          float4 hi, lo; split4(vb[i], hi, lo);
+          const uint32_t off = (k >> 2) * L::B_PLANE + (n4 >> 1) * L::B_SBO + ((n4 & 1) * 4) * 16 + (k & 3) * 4;
+          sts32(b_hi + off, hi.x); sts32(b_hi + off + 16, hi.y); sts32(b_hi + off + 32, hi.z); sts32(b_hi + off + 48, hi.w);
+          sts32(b_lo + off, lo.x); sts32(b_lo + off + 16, lo.y); sts32(b_lo + off + 32, lo.z); sts32(b_lo + off + 48, lo.w);
         }
       }
 #pragma unroll
@@ -218,6 +225,12 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * s);
+      if (it + 1 < nk) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) va[i] = na[i];
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) vb[i] = nb[i];
+      }
     }
     // ================= epilogue =================
     mbar_wait(bar_done, 0);
@@ -226,19 +239,33 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t r[16];
-      if (nk > 0) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
-      else {
+      if (nk > 0) {
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) {                       // sum the interleaved accumulators with round-to-nearest adds
+          uint32_t q[16];
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, q);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
+        }
+      } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = 0u;
       }
       if (m < op.M) {
+        if (nsplit == 1 && op.can_store4() && n0 + c0 + 15 < op.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < op.N) {
-            const float v = __uint_as_float(r[j]);
-            if (nsplit > 1) ws[(long long)blockIdx.z * ws_stride + (long long)m * op.N + n] = v;
-            else op.store(m, n, v);
+          for (int j = 0; j < 16; j += 4)
+            op.store4(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < op.N) {
+              const float v = __uint_as_float(r[j]);
+              if (nsplit > 1) ws[(long long)blockIdx.z * ws_stride + (long long)m * op.N + n] = v;
+              else op.store(m, n, v);
+            }
           }
         }
       }
@@ -261,9 +288,18 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
           const uint64_t dal = make_desc(a_lo + 2 * j * L::A_PLANE, L::A_PLANE, L::A_SBO);
           const uint64_t dbh = make_desc(b_hi + 2 * j * L::B_PLANE, L::B_PLANE, L::B_SBO);
           const uint64_t dbl = make_desc(b_lo + 2 * j * L::B_PLANE, L::B_PLANE, L::B_SBO);
-          umma_tf32(tmem, dal, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
-          umma_tf32(tmem, dah, dbl, idesc, 1u);
-          umma_tf32(tmem, dah, dbh, idesc, 1u);
+          const int ks = it * (BK / 8) + j;                     // global k-step index of this CTA
+          const uint32_t dm = tmem + (uint32_t)((ks % R) * BN);
+          if (SEP) {
+            const uint32_t dc = tmem + (uint32_t)(R * BN);
+            umma_tf32(dc, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+            umma_tf32(dc, dah, dbl, idesc, 1u);
+            umma_tf32(dm, dah, dbh, idesc, ks >= R ? 1u : 0u);
+          } else {
+            umma_tf32(dm, dal, dbh, idesc, ks >= R ? 1u : 0u);
+            umma_tf32(dm, dah, dbl, idesc, 1u);
+            umma_tf32(dm, dah, dbh, idesc, 1u);
+          }
         }
         umma_commit(bars + 8 * (STAGES + s));                   // frees the smem slot when these MMAs retire
         if (it == nk - 1) umma_commit(bar_done);
@@ -281,16 +317,24 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 
 namespace {
 
-template <int BN, class Op>
-void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
+template <int BN, int R, bool SEP, class Op>
+void tc_launch_v(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
   using L = tc::Lay<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, SEP, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set = true;
   }
-  tc::tc_gemm_kernel<BN, Op><<<grid, tc::THREADS, L::SMEM, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+  tc::tc_gemm_kernel<BN, R, SEP, Op><<<grid, tc::THREADS, L::SMEM, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
   CK(cudaGetLastError());
+}
+template <int BN, class Op>
+void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
+  switch (e->tc_variant) {
+    case 1: tc_launch_v<BN, 4, false, Op>(e, grid, a, b, nsplit, ws_stride); break;
+    case 2: tc_launch_v<BN, 2, true, Op>(e, grid, a, b, nsplit, ws_stride); break;
+    default: tc_launch_v<BN, 1, false, Op>(e, grid, a, b, nsplit, ws_stride); break;
+  }
 }
 
 template <class Op>
@@ -339,7 +383,10 @@ bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, 
 }
 bool tc_dense_wgrad(dqn_engine*, const char*, const dqn::DenseWgradOp*, int, double, double) { return false; }
 bool tc_conv_wgrad(dqn_engine*, const char*, const dqn::ConvWgradOp&, double, double) { return false; }
-void tc_init(dqn_engine*) {}
+void tc_init(dqn_engine* e) {
+  const char* v = getenv("DQN_TC_VARIANT");          // accumulator scheme: 0 single, 1 four interleaved, 2 two interleaved + corrections apart
+  e->tc_variant = v ? atoi(v) : 2;
+}
 void tc_destroy(dqn_engine*) {}
 void tc_params_changed(dqn_engine*) {}
 

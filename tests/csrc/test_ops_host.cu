@@ -51,7 +51,7 @@ static void test_dense(int M, int K, int N, int act, bool u8) {
 }
 
 static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int KW, int S, bool u8) {
-  ConvGeom g{IH, IW, Cin, (IH - KH) / S + 1, (IW - KW) / S + 1, Cout, KH, KW, S};
+  ConvGeom g{}; g.IH = IH; g.IW = IW; g.Cin = Cin; g.OH = (IH - KH) / S + 1; g.OW = (IW - KW) / S + 1; g.Cout = Cout; g.KH = KH; g.KW = KW; g.S = S; g.init();
   const int K = KH * KW * Cin, P = nimg * g.OH * g.OW;
   std::vector<float> X(nimg * IH * IW * Cin), W((K + 1) * Cout), Y(P * Cout), R(P * Cout);
   std::vector<uint8_t> X8(X.size());
@@ -103,7 +103,21 @@ static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int K
   }
 }
 
+static void test_fastdiv_and_u8() {
+  for (uint32_t d : {1u, 2u, 3u, 4u, 5u, 7u, 9u, 20u, 32u, 49u, 64u, 81u, 84u, 400u, 3136u, 102400u}) {
+    FastDiv f; f.init(d);
+    for (uint32_t n : {0u, 1u, d - 1, d, d + 1, 12345u, 204799u, 1000003u, 0x7fffffffu, 0x7ffffffeu, 7u * d, 7u * d - 1}) {
+      if (n > 0x7fffffffu) continue;
+      uint32_t q, r; f.divmod(n, q, r);
+      if (q != n / d || r != n % d) { printf("FAIL fastdiv %u / %u\n", n, d); ++fails; }
+    }
+  }
+  for (int k = 0; k < 256; ++k) if (u8_to_f32((uint8_t)k) != (float)k / 255.f) { printf("FAIL u8_to_f32 %d\n", k); ++fails; }
+  printf("ok   fastdiv/u8\n");
+}
+
 int main() {
+  test_fastdiv_and_u8();
   test_dense(7, 12, 8, ACT_RELU, false);
   test_dense(5, 2, 32, ACT_IDENTITY, false);     // README net first layer
   test_dense(9, 32, 1, ACT_IDENTITY, false);     // value head
