@@ -73,21 +73,6 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dist_setup(n):
-    """Control plane only (id broadcast, barrier, max over ranks); the gradient all-reduce is NCCL inside the engine."""
-    if n <= 1 or "RANK" not in os.environ:
-        return None, 0, 1, 0
-    import torch.distributed as dist
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("gloo")
-    return dist, dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
-
-
-def c3_layers(lib):
-    import util
-    return util.layer_descs(util.SPECS["c3_conv"]), util.SPECS["c3_conv"]
-
-
 def run_reference(args):
     """The reference's CPU path on this box's host cores (Flux-equivalent restatement, torch-CPU, all threads)."""
     rank = int(os.environ.get("RANK", 0))
@@ -135,32 +120,27 @@ def main():
 
     import dqn_b200 as lib
     import util
-    dist, rank, world, local = dist_setup(args.gpus)
+    cp = lib.ControlPlane(args.gpus)
+    rank, world, local = cp.rank, cp.world, cp.local_rank
     peaks = load_peaks()
     spec = util.SPECS["c3_conv"]
     nccl_id = None
     if world > 1:
-        import torch
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            idt = torch.tensor(list(lib.nccl_unique_id()), dtype=torch.uint8)
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.tolist())
-    math_mode = {"auto": lib.MATH_3XTF32 if os.environ.get("DQN_DEFAULT_TC", "0") == "1" else lib.MATH_FP32, "fp32": lib.MATH_FP32, "3xtf32": lib.MATH_3XTF32}[args.math]
+        nccl_id = cp.broadcast_bytes(lib.nccl_unique_id() if rank == 0 else None, 128)
+    seeds = lib.shard_seeds(0, rank)
+    math_mode = {"auto": lib.MATH_3XTF32, "fp32": lib.MATH_FP32, "3xtf32": lib.MATH_3XTF32}[args.math]
     args.math = "3xtf32 (tcgen05 kind::tf32, 3-pass split)" if math_mode == lib.MATH_3XTF32 else "fp32 (CUDA-core FMA)"
     cfg = lib.make_config(util.layer_descs(spec), (84, 84, 4), 6, obs_dtype="u8", batch_size=256, buffer_size=args.buffer, learning_rate=1e-4,
-                          discount=0.99, seed=2 + rank, device=local, math_mode=math_mode, use_graph=not args.no_graph, rank=rank, world=world, nccl_id=nccl_id)
+                          discount=0.99, seed=seeds["sampler"], device=local, math_mode=math_mode, use_graph=not args.no_graph, rank=rank, world=world, nccl_id=nccl_id)
     eng = lib.Engine(cfg)
-    net = util.make_oracle_net(spec, True, seed=1)                 # glorot-uniform weights from seed 1 (same on every rank)
+    net = util.make_oracle_net(spec, True, seed=seeds["weights"])   # glorot-uniform weights from seed 1 (same on every rank)
     import oracle as O
     theta = O.flat_params(net)
     eng.set_params(theta, 0)
     eng.sync_target()
-    eng.replay_fill_synthetic(args.buffer, seed=1000 + rank)       # per-GPU shard
+    eng.replay_fill_synthetic(args.buffer, seed=seeds["replay"])    # per-GPU shard
 
-    def barrier():
-        if dist:
-            dist.barrier()
+    barrier = cp.barrier
 
     # ---- device-resident throughput (value) ------------------------------------------------------
     for _ in range(args.warmup):
@@ -177,11 +157,7 @@ def main():
     loss, gn = eng.sync()
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    if dist:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+    ms = cp.max_over_ranks(ms)
     launches = eng.launches_per_step() * args.steps
     value = world * args.steps / (ms * 1e-3)
 
@@ -206,11 +182,7 @@ def main():
         eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
         loss, gn = eng.train_step()
     e2e_s = time.perf_counter() - t0
-    if dist:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    e2e_s = cp.max_over_ranks(e2e_s)
     e2e = world * args.steps / e2e_s
 
     # ---- per-kernel timing (eager launches bracketed by CUDA events on the engine's stream) -> roofline ---
@@ -256,8 +228,7 @@ def main():
                           "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
                           "last_loss": loss, "last_grad_norm": gn}))
     eng.close()
-    if dist:
-        dist.destroy_process_group()
+    cp.close()
 
 
 if __name__ == "__main__":

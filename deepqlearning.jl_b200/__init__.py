@@ -10,6 +10,7 @@ from ._capi import DQNError, MATH_FP32, MATH_3XTF32
 from .engine import Engine, make_config, nccl_unique_id
 from .flux import (Chain, Dense, Conv, flattenbatch, DuelingNetwork, create_dueling_network, isrecurrent, flat_params,
                    load_flat_params, identity, relu, tanh, sigmoid)
+from .dist import ControlPlane, shard_seeds
 from .replay import PrioritizedReplayBuffer, DQExperience
 from .solver import (DeepQLearningSolver, solve, dqn_train, batch_train, NNPolicy, EpsGreedyPolicy, LinearDecaySchedule,
                      basic_evaluation, getnetwork, actionvalues, action, value, initialize_replay_buffer, populate_replay_buffer)
