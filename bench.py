@@ -187,13 +187,14 @@ def main():
 
     # ---- per-kernel timing (eager launches bracketed by CUDA events on the engine's stream) -> roofline ---
     roof, kernels = None, None
+    eng.set_profiling(1)                 # every rank runs the profiled steps (they contain the collective); rank 0 reports
+    for _ in range(10):
+        eng.train_step_async()
+    eng.sync()
+    prof = eng.get_profile()
+    eng.set_profiling(0)
+    barrier()
     if rank == 0:
-        eng.set_profiling(1)
-        for _ in range(10):
-            eng.train_step_async()
-        eng.sync()
-        prof = eng.get_profile()
-        eng.set_profiling(0)
         tot = sum(k["ms"] * 1 for k in prof)
         kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"])][:12]
         top = max(prof, key=lambda k: k["ms"])

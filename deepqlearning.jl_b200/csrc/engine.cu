@@ -79,6 +79,9 @@ constexpr int MAXD = DQN_MAX_LAYERS;
 struct ActBufs {
   std::vector<float*> conv_out;
   float* tow_out[2][MAXD] = {};
+  // hi planes of the same tensors in the tensor-core operand arena (empty / null in DQN_MATH_FP32)
+  std::vector<float*> conv_out_s;
+  float* tow_out_s[2][MAXD] = {};
 };
 
 }  // namespace
@@ -126,7 +129,11 @@ struct dqn_engine {
   int profiling = 0; std::vector<ProfRec> prof; std::vector<cudaEvent_t> ev_pool;
   uint32_t* flush_buf = nullptr; long long flush_n = 0;
   bool capturing = false;
-  int tc_variant = 0;
+  // tensor-core operand arena: hi planes at arena + offset, lo planes lo_delta floats later
+  float* arena = nullptr; long long lo_delta = 0;
+  float* xb_f = nullptr; std::vector<float*> conv_delta_s; float* tow_delta_s[2][MAXD] = {};
+  float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
+  long long w_scale_lo = 0, w_scale_hi = 0;
 };
 
 namespace {
@@ -197,8 +204,11 @@ void launch_igemm(E* e, const char* name, Op a, Op b, int nz, bool allow_split, 
 }
 
 // ---- network schedule ---------------------------------------------------------------------------
-void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag) {
+// Xs / Wsplit: hi planes of the input batch and of this parameter vector (null => fp32 CUDA-core kernels only)
+void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag, const float* Xs, const float* Wsplit) {
   const void* cur = X; int cur_u8 = x_u8;
+  const float* cur_s = Xs;
+  const bool tcm = Xs && Wsplit;
   char nm[64];
   for (size_t l = 0; l < e->convs.size(); ++l) {
     const ConvL& c = e->convs[l];
@@ -206,11 +216,12 @@ void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& b
     op.X = cur; op.x_u8 = cur_u8; op.W = P + c.w.off; op.Y = bufs.conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
     op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
     op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
+    if (tcm) { op.Xs = cur_s; op.Ws = Wsplit + c.w.off; op.Ys = (c.g.Cout % 4 == 0) ? bufs.conv_out_s[l] : nullptr; op.lo_delta = e->lo_delta; op.a_single = (l == 0 && cur_u8); }
     snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, tag);
     const double fl = 2.0 * op.M * op.N * op.K;
     const double by = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8 ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
     if (!tc_conv_fwd(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
-    cur = bufs.conv_out[l]; cur_u8 = 0;
+    cur = bufs.conv_out[l]; cur_u8 = 0; cur_s = op.Ys;
   }
   for (int l = 0; l < e->depth; ++l) {
     DenseFwdOp ops[2];
@@ -220,6 +231,10 @@ void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& b
       op.X = l == 0 ? cur : (const void*)bufs.tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8 : 0;
       op.W = P + w.off; op.C = bufs.tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
       op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
+      if (tcm) {
+        op.Xs = l == 0 ? ((cur_u8 && e->convs.empty()) ? nullptr : cur_s) : ((e->tow[t][l - 1].N % 4 == 0) ? bufs.tow_out_s[t][l - 1] : nullptr);
+        op.Ws = Wsplit + w.off; op.Cs = (w.N % 4 == 0) ? bufs.tow_out_s[t][l] : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
+      }
     }
     if (e->ntow == 1) ops[1] = ops[0];
     snprintf(nm, sizeof nm, "dense%d_fwd_%s", l + 1, tag);
@@ -244,6 +259,12 @@ void backward(E* e) {
       else { op.X = e->on.tow_out[t][l - 1]; op.x_u8 = 0; }
       op.ldx = w.K; op.D = e->tow_delta[t][l]; op.ldd = w.N; op.dW = e->grad + w.off; op.M = w.K + 1; op.N = w.N; op.K = B;
       op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
+      if (e->arena) {
+        const bool raw_bytes = (l == 0 && !trunk && e->elem_bytes == 1);
+        op.Xs = l == 0 ? (trunk ? e->on.conv_out_s.back() : (raw_bytes ? nullptr : e->xb_f)) : ((e->tow[t][l - 1].N % 4 == 0) ? e->on.tow_out_s[t][l - 1] : nullptr);
+        op.Ds = (l < e->depth - 1 && w.N % 4 == 0) ? e->tow_delta_s[t][l] : nullptr;      // the head kernel writes the last layer's delta unsplit
+        op.ones = e->ones; op.lo_delta = e->lo_delta; op.a_single = 0; op.out_scale = 0.f;
+      }
     }
     if (e->ntow == 1) wg[1] = wg[0];
     snprintf(nm, sizeof nm, "dense%d_wgrad", l + 1);
@@ -259,12 +280,16 @@ void backward(E* e) {
         op.D = e->tow_delta[t][l]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = e->tow_delta[t][l - 1]; op.ldx = w.K;
         op.Y = e->on.tow_out[t][l - 1]; op.ldy = w.K; op.act = wp.act; op.accumulate = 0; op.apply_act = 1;
         op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
+        if (e->arena) {
+          op.Ds = (l < e->depth - 1 && w.N % 4 == 0) ? e->tow_delta_s[t][l] : nullptr; op.Ws = e->w_on_s + w.off;
+          op.dXs = (w.K % 4 == 0) ? e->tow_delta_s[t][l - 1] : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
+        }
       }
       if (e->ntow == 1) dg[1] = dg[0];
       snprintf(nm, sizeof nm, "dense%d_dgrad", l + 1);
       double fl = 0, by = 0;
       for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * B * dg[t].N * dg[t].K; by += 4.0 * ((double)B * dg[t].K + (double)dg[t].N * dg[t].K + 2.0 * B * dg[t].N); }
-      launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
+      if (!tc_dense_dgrad2(e, nm, dg, e->ntow, fl, by)) launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
     } else if (trunk) {
       for (int t = 0; t < e->ntow; ++t) {       // towers accumulate into the trunk gradient in a fixed order
         const Mat& w = e->tow[t][0];
@@ -272,6 +297,10 @@ void backward(E* e) {
         op.D = e->tow_delta[t][0]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = dfeat; op.ldx = w.K;
         op.Y = e->on.conv_out.back(); op.ldy = w.K; op.act = e->convs.back().w.act; op.accumulate = t > 0; op.apply_act = (t == e->ntow - 1);
         op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
+        if (e->arena) {
+          op.Ds = (e->depth > 1 && w.N % 4 == 0) ? e->tow_delta_s[t][0] : nullptr; op.Ws = e->w_on_s + w.off;
+          op.dXs = (t == e->ntow - 1 && w.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
+        }
         snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
         const double fl = 2.0 * B * op.N * op.K, by = 4.0 * ((double)B * op.K + (double)op.N * op.K + 2.0 * B * op.N);
         if (!tc_dense_dgrad(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
@@ -284,6 +313,10 @@ void backward(E* e) {
     wg.X = l == 0 ? (const void*)e->xb : (const void*)e->on.conv_out[l - 1]; wg.x_u8 = l == 0 ? (e->elem_bytes == 1) : 0;
     wg.D = e->conv_delta[l]; wg.dW = e->grad + c.w.off; wg.nimg = B; wg.g = c.g;
     wg.M = c.w.K + 1; wg.N = c.g.Cout; wg.K = B * c.g.OH * c.g.OW; wg.vecA = (c.g.Cin % 4 == 0); wg.vecB = (c.g.Cout % 4 == 0);
+    if (e->arena) {
+      wg.Xs = l == 0 ? e->xb_f : e->on.conv_out_s[l - 1]; wg.Ds = e->conv_delta_s[l]; wg.ones = e->ones; wg.lo_delta = e->lo_delta;
+      wg.a_single = (l == 0 && e->elem_bytes == 1); wg.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
+    }
     snprintf(nm, sizeof nm, "conv%d_wgrad", l + 1);
     double fl = 2.0 * wg.M * wg.N * wg.K;
     double by = (double)B * c.g.IH * c.g.IW * c.g.Cin * (wg.x_u8 ? 1 : 4) + 4.0 * wg.K * wg.N + 4.0 * wg.M * wg.N;
@@ -293,6 +326,7 @@ void backward(E* e) {
       dg.D = e->conv_delta[l]; dg.W = e->theta + c.w.off; dg.dX = e->conv_delta[l - 1]; dg.Yprev = e->on.conv_out[l - 1];
       dg.act = e->convs[l - 1].w.act; dg.apply_act = 1; dg.nimg = B; dg.g = c.g;
       dg.vecA = (c.g.Cout % 4 == 0); dg.vecB = (c.g.Cout % 4 == 0);
+      if (e->arena) { dg.Ds = e->conv_delta_s[l]; dg.Ws = e->w_on_s + c.w.off; dg.dXs = (c.g.Cin % 4 == 0) ? e->conv_delta_s[l - 1] : nullptr; dg.lo_delta = e->lo_delta; dg.a_single = 0; }
       snprintf(nm, sizeof nm, "conv%d_dgrad", l + 1);
       fl = 2.0 * B * c.g.OH * c.g.OW * c.g.Cout * c.w.K;
       by = 4.0 * ((double)B * c.g.OH * c.g.OW * c.g.Cout + (double)c.w.K * c.g.Cout + 2.0 * B * c.g.IH * c.g.IW * c.g.Cin);
@@ -313,7 +347,7 @@ void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for the indices in i
     const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
     dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
     Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
-    gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb);
+    gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0) ? e->xb_f : nullptr, e->lo_delta, e->elem_bytes == 1);
     CK(cudaGetLastError());
   }
 }
@@ -327,8 +361,9 @@ void enqueue_step(E* e, bool sample) {
     CK(cudaGetLastError());
   }
   enqueue_batch_prep(e);
-  forward(e, e->theta, e->xb, e->elem_bytes == 1, 2 * B, e->on, "online");
-  forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target");
+  const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? e->xb_f : nullptr;
+  forward(e, e->theta, e->xb, e->elem_bytes == 1, 2 * B, e->on, "online", xs, e->w_on_s);
+  forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s);
   {
     HeadArgs h{};
     const int L = e->depth - 1;
@@ -354,7 +389,8 @@ void enqueue_step(E* e, bool sample) {
   {
     Scope sc(e, "adam", 0, 7.0 * e->nint * 4);
     adam_kernel<<<2 * e->nsm * 2, 256, 0, e->stream>>>(e->theta, e->adam_m, e->adam_v, e->grad, e->nint / 4,
-                                                       (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st);
+                                                       (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st,
+                                                       e->w_on_s, e->lo_delta, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
     CK(cudaGetLastError());
   }
   {
@@ -930,7 +966,7 @@ int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* 
       const int c = (int)std::min<long long>(chunk, n - t0);
       CK(cudaMemcpyAsync(h->stage, (const uint8_t*)obs + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
       relayout(h, h->stage, h->xb, c, h->elem_bytes == 1, 0, 1);
-      forward(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, c, h->on, "act");
+      forward(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, c, h->on, "act", nullptr, nullptr);
       float* q = h->on.tow_out[h->ntow - 1][L];
       if (h->cfg.dueling) {
         q = (float*)h->ws;

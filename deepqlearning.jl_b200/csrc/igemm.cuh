@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifndef DQN_HD
 #define DQN_HD __host__ __device__ __forceinline__
@@ -139,6 +140,26 @@ DQN_HD float4 load4_u8(const uint8_t* p, int cnt, bool vec_ok) {
 // set element j (0..3) of a float4 without dynamic indexing (keeps the value in registers)
 DQN_HD void set4(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else if (j == 3) v.w = x; }
 
+// x = hi + lo with hi, lo both exactly representable in TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32)
+DQN_HD float tf32_rna(float x) {
+#ifdef __CUDA_ARCH__
+  uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h);
+#else
+  uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r;
+#endif
+}
+DQN_HD void split_tf32(float x, float& hi, float& lo) { hi = tf32_rna(x); lo = tf32_rna(x - hi); }
+DQN_HD void split4(const float4& v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+// Pre-split tensors live in one arena: the lo plane of every tensor sits `lo_delta` floats after its hi plane, so a
+// single pointer names a 16-byte chunk of both planes.
+DQN_HD void store_split4(float* hi_ptr, long long lo_delta, const float4& v) {
+  float4 hi, lo; split4(v, hi, lo);
+  *reinterpret_cast<float4*>(hi_ptr) = hi;
+  *reinterpret_cast<float4*>(hi_ptr + lo_delta) = lo;
+}
+
 // Per-row (m) and per-column-of-A (k) decode contexts, hoisted out of the inner loops by the kernels.
 struct ACtx { long long base; int i0, i1; int valid; };
 struct KCtx { long long off; int t0, t1, t2; };
@@ -152,6 +173,11 @@ struct DenseFwdOp {
   float* C; long long ldc; int act;
   int M, N, K;
   int vecA, vecB;
+  // tensor-core path: pre-split operands (hi plane pointers into the arena; lo = hi + lo_delta) and split output
+  const float* Xs; const float* Ws; float* Cs; long long lo_delta; int a_single;
+  DQN_HD bool tc_ready() const { return Xs && Ws && (K % 4 == 0) && (N % 4 == 0) && (ldx % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int, int k) const { return (c.valid && k < K) ? Xs + c.base + k : nullptr; }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldx; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
@@ -170,8 +196,9 @@ struct DenseFwdOp {
   DQN_HD bool can_store4() const { return (N % 4 == 0) && (ldc % 4 == 0); }
   DQN_HD void store4(int m, int n, float4 v) const {
     const float4 b = ldg4(W + (long long)K * N + n);
-    *reinterpret_cast<float4*>(C + (long long)m * ldc + n) =
-        make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+    const float4 y = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+    *reinterpret_cast<float4*>(C + (long long)m * ldc + n) = y;
+    if (Cs) store_split4(Cs + (long long)m * ldc + n, lo_delta, y);
   }
 };
 
@@ -184,6 +211,10 @@ struct DenseDgradOp {
   const float* Y; long long ldy; int act; int accumulate; int apply_act;
   int M, N, K;
   int vecA, vecB;
+  const float* Ds; const float* Ws; float* dXs; long long lo_delta; int a_single;
+  DQN_HD bool tc_ready() const { return Ds && Ws && (K % 4 == 0) && (ldd % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int, int k) const { return (c.valid && k < K) ? Ds + c.base + k : nullptr; }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)n * K + k : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
@@ -210,6 +241,7 @@ struct DenseDgradOp {
       v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
     }
     *o = v;
+    if (dXs) store_split4(dXs + (long long)m * ldx + n, lo_delta, v);
   }
 };
 
@@ -221,6 +253,14 @@ struct DenseWgradOp {
   float* dW;                 // [(Kin+1)][N]
   int M, N, K;               // M = Kin+1, K = batch rows
   int vecA, vecB;
+  const float* Xs; const float* Ds; const float* ones; long long lo_delta; int a_single; float out_scale;   // out_scale: 1/255 when X holds raw bytes
+  DQN_HD bool tc_ready() const { return Xs && Ds && ones && ((M - 1) % 4 == 0) && (N % 4 == 0) && (ldx % 4 == 0) && (ldd % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int m, int k) const {     // 4 consecutive m at batch row k
+    if (!c.valid || k >= K) return nullptr;
+    const int cnt = (M - 1) - m;
+    return cnt >= 4 ? Xs + kc.off + m : (cnt == 0 ? ones : nullptr);
+  }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * ldd + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = m; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; return c; }
@@ -239,9 +279,13 @@ struct DenseWgradOp {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * ldd + n, N - n, vecB);
   }
-  DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v; }
+  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < M - 1) ? out_scale : 1.f; }
+  DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v * oscale(m); }
   DQN_HD bool can_store4() const { return N % 4 == 0; }
-  DQN_HD void store4(int m, int n, float4 v) const { *reinterpret_cast<float4*>(dW + (long long)m * N + n) = v; }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    const float sc = oscale(m);
+    *reinterpret_cast<float4*>(dW + (long long)m * N + n) = make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -265,6 +309,10 @@ struct ConvFwdOp {
   const float* W; float* Y; int act; int nimg; ConvGeom g;
   int M, N, K;
   int vecA, vecB;
+  const float* Xs; const float* Ws; float* Ys; long long lo_delta; int a_single;
+  DQN_HD bool tc_ready() const { return Xs && Ws && (g.Cin % 4 == 0) && (N % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const { return (c.valid && k < K) ? Xs + c.base + kc.off : nullptr; }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const {
     ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = 0;
@@ -302,8 +350,9 @@ struct ConvFwdOp {
   DQN_HD bool can_store4() const { return N % 4 == 0; }
   DQN_HD void store4(int m, int n, float4 v) const {
     const float4 b = ldg4(W + (long long)K * N + n);
-    *reinterpret_cast<float4*>(Y + (long long)m * N + n) =
-        make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+    const float4 y = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+    *reinterpret_cast<float4*>(Y + (long long)m * N + n) = y;
+    if (Ys) store_split4(Ys + (long long)m * N + n, lo_delta, y);
   }
 };
 
@@ -314,6 +363,14 @@ struct ConvWgradOp {
   const float* D; float* dW; int nimg; ConvGeom g;
   int M, N, K;               // M = KH*KW*Cin + 1, N = Cout, K = nimg*OH*OW
   int vecA, vecB;
+  const float* Xs; const float* Ds; const float* ones; long long lo_delta; int a_single; float out_scale;
+  DQN_HD bool tc_ready() const { return Xs && Ds && ones && (g.Cin % 4 == 0) && (N % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int m, int k) const {     // 4 consecutive m (channels of one tap) at pixel k
+    if (!c.valid || k >= K) return nullptr;
+    const int cnt = (M - 1) - m;
+    return cnt >= 4 ? Xs + kc.off + c.base : (cnt == 0 ? ones : nullptr);
+  }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * N + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD long long moff(int m) const {
     uint32_t t, ci, kh, kw;
@@ -347,9 +404,13 @@ struct ConvWgradOp {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * N + n, N - n, vecB);
   }
-  DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v; }
+  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < M - 1) ? out_scale : 1.f; }
+  DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v * oscale(m); }
   DQN_HD bool can_store4() const { return N % 4 == 0; }
-  DQN_HD void store4(int m, int n, float4 v) const { *reinterpret_cast<float4*>(dW + (long long)m * N + n) = v; }
+  DQN_HD void store4(int m, int n, float4 v) const {
+    const float sc = oscale(m);
+    *reinterpret_cast<float4*>(dW + (long long)m * N + n) = make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+  }
 };
 
 // Conv dgrad by stride-parity class (ph,pw): rows are the input pixels with ih%S==ph, iw%S==pw, and only
@@ -361,6 +422,19 @@ struct ConvDgradOp {
   FastDiv fbw, fah, ftw;     // the class's divisors, picked by set_class with static indices (no local-memory copy)
   int M, N, K;               // set by set_class: M = nimg*AH*BW, N = Cin, K = TH*TW*Cout
   int vecA, vecB;
+  const float* Ds; const float* Ws; float* dXs; long long lo_delta; int a_single;
+  DQN_HD bool tc_ready() const { return Ds && Ws && (g.Cout % 4 == 0); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const {
+    if (!c.valid || k >= K) return nullptr;
+    const int oh = c.i0 - kc.t0, ow = c.i1 - kc.t1;
+    if (oh < 0 || oh >= g.OH || ow < 0 || ow >= g.OW) return nullptr;
+    return Ds + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + kc.t2;
+  }
+  DQN_HD const float* ptrB(const KCtx& kc, int k, int n) const {
+    if (k >= K || n >= N) return nullptr;
+    const int kh = ph + kc.t0 * g.S, kw = pw + kc.t1 * g.S;
+    return Ws + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + kc.t2;
+  }
   DQN_HD void set_class(int z) {
     ph = z / g.S; pw = z - ph * g.S;
     AH = (g.IH - ph + g.S - 1) / g.S; BW = (g.IW - pw + g.S - 1) / g.S;
@@ -427,6 +501,7 @@ struct ConvDgradOp {
       v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
     }
     *reinterpret_cast<float4*>(dX + o) = v;
+    if (dXs) store_split4(dXs + o, lo_delta, v);
   }
 };
 
@@ -576,6 +651,17 @@ __global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __
   const int zi = blockIdx.y;
   Op op = zi == 0 ? opa : opb;
   const long long total = (long long)op.M * op.N;
+  if (op.can_store4()) {                     // N % 4 == 0: four columns per thread, vector epilogue (also writes the split planes)
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+      float4 s = make4(0, 0, 0, 0);
+      for (int k = 0; k < nsplit; ++k) {
+        const float4 p = *reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
+      op.store4((int)(i / op.N), (int)(i % op.N), s);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < nsplit; ++k) s += ws[((long long)(zi * nsplit + k)) * ws_stride + i];

@@ -119,9 +119,11 @@ __global__ void batch_meta_kernel(const long long* __restrict__ idx, int B, cons
 
 // Observation gather: rows idx[j] of the s / s' stores -> contiguous batch (s rows 0..B-1, s' rows B..2B-1).
 // 16-byte loads, 4 in flight per thread; grid = (chunks, 2B).
+// Tensor-core path: the same pass also writes the batch as fp32 operand planes - raw byte values k as floats (exact in
+// TF32, single plane; the 1/255 is folded into the first layer's weight planes) or the hi/lo split of fp32 observations.
 __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ store_s, const uint8_t* __restrict__ store_sp,
                                                            const long long* __restrict__ idx, int B, long long row_bytes,
-                                                           uint8_t* __restrict__ out) {
+                                                           uint8_t* __restrict__ out, float* __restrict__ out_f, long long lo_delta, int obs_u8) {
   const int row = blockIdx.y;
   const long long i = idx[row < B ? row : row - B];
   const uint8_t* src = (row < B ? store_s : store_sp) + i * row_bytes;
@@ -135,10 +137,38 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
 #pragma unroll
     for (int u = 0; u < 4; ++u) { long long v = v0 + (long long)u * blockDim.x; if (v < nvec) tmp[u] = __ldg(s4 + v); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { long long v = v0 + (long long)u * blockDim.x; if (v < nvec) d4[v] = tmp[u]; }
+    for (int u = 0; u < 4; ++u) {
+      long long v = v0 + (long long)u * blockDim.x;
+      if (v >= nvec) continue;
+      d4[v] = tmp[u];
+      if (out_f) {
+        if (obs_u8) {          // 16 bytes -> 16 floats
+          float* o = out_f + (long long)row * row_bytes + v * 16;
+          const uint32_t w[4] = {(uint32_t)tmp[u].x, (uint32_t)tmp[u].y, (uint32_t)tmp[u].z, (uint32_t)tmp[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(o + 4 * q) = make4((float)(w[q] & 255u), (float)((w[q] >> 8) & 255u), (float)((w[q] >> 16) & 255u), (float)(w[q] >> 24));
+        } else {               // 4 floats -> hi/lo planes
+          float* o = out_f + (long long)row * (row_bytes >> 2) + v * 4;
+          store_split4(o, lo_delta, make4(__int_as_float(tmp[u].x), __int_as_float(tmp[u].y), __int_as_float(tmp[u].z), __int_as_float(tmp[u].w)));
+        }
+      }
+    }
   } else {
     for (long long b = (long long)blockIdx.x * blockDim.x * 4 + threadIdx.x; b < row_bytes && b < ((long long)blockIdx.x + 1) * blockDim.x * 4; b += blockDim.x)
       dst[b] = src[b];
+  }
+}
+
+// theta -> operand planes (hi, lo) of the tensor-core path; [s0, s1) is the first layer's weight block when the
+// observations are raw bytes (scaled by 1/255 here instead of in the operand loader)
+__global__ void split_params_kernel(const float* __restrict__ w, float* __restrict__ hi, long long lo_delta, long long n4,
+                                    long long s0, long long s1, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(w)[i];
+    const long long e = i * 4;
+    if (e >= s0 && e < s1) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+    store_split4(hi + e, lo_delta, v);
   }
 }
 
@@ -358,7 +388,8 @@ __global__ void head_loss_kernel(HeadArgs h) {
 // with m, v, d each rounded to Float32 on store exactly as the reference's broadcasts do.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                                                     const float* __restrict__ g, long long n4, double eta, double beta1, double beta2,
-                                                    double eps, float gscale, DevState* st) {
+                                                    double eps, float gscale, DevState* st,
+                                                    float* __restrict__ w_hi, long long lo_delta, long long s0, long long s1, float scale) {
   const double c1 = 1.0 - st->b1p, c2 = 1.0 - st->b2p;
   const double omb1 = 1.0 - beta1, omb2 = 1.0 - beta2;
   float gmax = 0.f;
@@ -378,6 +409,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
       mp[k] = mt; vp[k] = vt; wp[k] = wp[k] - d;
     }
     reinterpret_cast<float4*>(w)[i] = W; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
+    if (w_hi) {                                   // refresh the tensor-core operand planes of the online weights in the same pass
+      const long long e = i * 4;
+      if (e >= s0 && e < s1) { W.x *= scale; W.y *= scale; W.z *= scale; W.w *= scale; }
+      store_split4(w_hi + e, lo_delta, W);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));

@@ -9,6 +9,7 @@ bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, doub
 bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int ntow, double flops, double bytes);
 bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double flops, double bytes);
 bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double flops, double bytes);
+bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double flops, double bytes);
 bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double flops, double bytes);
 bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double flops, double bytes);
 void tc_init(dqn_engine* e);

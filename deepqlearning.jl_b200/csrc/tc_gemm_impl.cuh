@@ -3,21 +3,23 @@
 // Same operand functors as the fp32 path (igemm.cuh), different engine: a warp-specialised CTA computes one
 // 128 x BN output tile with the 5th-generation tensor cores.
 //
-//   warps 0-3 (128 threads)  producers: gather A (128 x 32) and B (BN x 32) through op.loadA / op.loadB, split every
-//                            fp32 value into two TF32 terms  x = hi + lo  (cvt.rna, so both terms are exactly
-//                            representable and the split is unbiased), and lay them out in shared memory in the
-//                            UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices);
-//                            after the main loop the same warps run the epilogue (tcgen05.ld -> op.store).
+// Operands arrive PRE-SPLIT: every fp32 tensor that feeds a contraction is kept in HBM as two TF32-exact planes
+// x = hi + lo (cvt.rna, written by the epilogue of the kernel that produced the tensor, by the gather for the sampled
+// batch and by the Adam pass for the weights; both planes of a tensor sit lo_delta floats apart in one arena).  The
+// producers therefore never touch data with the ALU:
+//
+//   warps 0-3 (128 threads)  cp.async 16-byte chunks global -> shared straight into the UMMA canonical no-swizzle layout,
+//                            K-major (8-row x 16-byte core matrices, chunk = 4 consecutive k) or MN-major (chunk = 4
+//                            consecutive rows) depending on which way the source tensor is contiguous; im2col rows,
+//                            dgrad parity classes and the [x 1] bias column are just different chunk addresses
+//                            (op.ptrA / op.ptrB, nullptr = zero fill).  Completion is tracked by the stage's mbarrier
+//                            (cp.async.mbarrier.arrive).  After the main loop the same warps run the epilogue.
 //   warp 4                   one elected lane issues tcgen05.mma.kind::tf32, three per 8-wide k step:
 //                            D += A_lo B_hi + A_hi B_lo + A_hi B_hi   (error-compensated "3xTF32"; the dropped
-//                            A_lo B_lo term is O(2^-22)), accumulating in fp32 in TMEM.
-//   mbarriers                full[stage] (128 producer arrivals, preceded by fence.proxy.async so the generic-proxy
-//                            st.shared are visible to the tensor core's async proxy), empty[stage] and done
-//                            (tcgen05.commit arrivals).
-//
-// Gathering through functors instead of TMA is deliberate: the A operands of this workload are implicit im2col
-// rows of uint8 / fp32 NHWC tensors, stride-parity classes of the conv dgrad, and all of them need the hi/lo
-// split on the way in - a register pass is unavoidable, so the producer does the addressing too.
+//                            A_lo B_lo term is O(2^-22)); two when A is single-plane (raw byte values are TF32-exact).
+//   accumulators             fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
+//                            1 ulp per MMA), so the correction products get their own accumulator (SEP) and the main
+//                            product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
 #pragma once
 #include <cstdlib>
 
@@ -25,21 +27,32 @@ namespace tc {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-constexpr int KCH = BK / 4;      // 16-byte chunks per row per stage
 constexpr int PROD = 128;        // producer / epilogue threads
 constexpr int THREADS = 160;     // + 1 MMA warp
-constexpr int STAGES = 2;
 
-template <int BN> struct Lay {
-  static constexpr int A_SBO = 128;                          // bytes between 8-row groups
-  static constexpr int A_PLANE = (BM / 8) * A_SBO + 16;      // bytes between consecutive 16-byte k-chunks (LBO), +16: bank spread
-  static constexpr int B_SBO = 144;
-  static constexpr int B_PLANE = (BN / 8) * B_SBO + 16;
-  static constexpr int A_BYTES = KCH * A_PLANE;
-  static constexpr int B_BYTES = KCH * B_PLANE;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi, A_lo, B_hi, B_lo
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;          // + barriers / tmem address
-  static_assert(A_PLANE % 16 == 0 && B_PLANE % 16 == 0, "descriptor granularity");
+// shared-memory tile of one operand plane for one stage
+template <int ROWS, bool MN> struct Tile;
+template <int ROWS> struct Tile<ROWS, false> {                // K-major: chunk (row r, k-chunk c) at c*LBO + (r/8)*SBO + (r%8)*16
+  static constexpr int SBO = 128;
+  static constexpr int LBO = (ROWS / 8) * SBO + 16;           // +16 bytes: spreads the eight k-chunks of a row over all banks
+  static constexpr int BYTES = (BK / 4) * LBO;
+  static constexpr int KSTEP = 2 * LBO;                       // descriptor advance per 8-wide k step
+};
+template <int ROWS> struct Tile<ROWS, true> {                 // MN-major: chunk (k, row group g) at g*SBO + (k%8)*16 + (k/8)*LBO
+  static constexpr int SBO = 144;                             // 128 + 16: consecutive row groups land in different banks
+  static constexpr int LBO = (ROWS / 4) * SBO;
+  static constexpr int BYTES = (BK / 8) * LBO;
+  static constexpr int KSTEP = LBO;
+};
+
+template <int BN, bool A_MN, bool B_MN> struct Lay {
+  using TA = Tile<BM, A_MN>;
+  using TB = Tile<BN, B_MN>;
+  static constexpr int STAGE_BYTES = 2 * TA::BYTES + 2 * TB::BYTES;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int STAGES = (2 * (2 * STAGE_BYTES + 128) <= 226 * 1024) ? 2 : 3;
+  static constexpr int CTAS = STAGES == 2 ? 2 : 1;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;              // + barriers / tmem address
+  static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,34 +114,27 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = __fsub_rn(x, hi);                 // exact
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
-}
-__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive when this thread's prior cp.async have landed
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), major bits 15/16 (1 = MN-major), N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-// R   : number of interleaved main accumulators (k-step j accumulates into accumulator j % R).  The tensor core adds
-//       into its fp32 accumulator with truncation, a one-sided error of up to 1 ulp(acc) per MMA; spreading the k-steps
-//       over R accumulators that are summed with round-to-nearest in the epilogue divides that bias by R.
-// SEP : the two small correction products (A_lo B_hi, A_hi B_lo) go to their own accumulator, so the main accumulator
-//       sees one truncating add per k-step instead of three.
 template <int BN, int R, bool SEP, class Op>
-__global__ void __launch_bounds__(THREADS, (Lay<BN>::SMEM <= 110 * 1024 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
-tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride) {
-  static_assert(!Op::A_MCONTIG, "A must be K-contiguous for this kernel");
-  using L = Lay<BN>;
+__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>::CTAS == 2 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
+tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src) {
+  constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
+  using L = Lay<BN, A_MN, B_MN>;
+  using TA = typename L::TA;
+  using TB = typename L::TB;
+  constexpr int STAGES = L::STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + STAGES * L::STAGE_BYTES;        // full[STAGES], empty[STAGES], done : 8 bytes each
@@ -144,6 +150,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   const int per = (ktiles + nsplit - 1) / nsplit;
   const int kt0 = split * per, kt1 = min(ktiles, kt0 + per);
   const int nk = max(kt1 - kt0, 0);
+  const bool a_lo = !op.a_single;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NACC = R + (SEP ? 1 : 0);
@@ -162,75 +169,63 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    // ================= producers =================
-    constexpr int A_PER = BM * KCH / PROD;                     // 8 sixteen-byte chunks of A per thread per stage
-    constexpr int B_PER = BN / 16;                             // chunks of B per thread per stage (both B layouts)
-    ACtx actx[A_PER];
+    // ================= producers: address + cp.async only =================
+    constexpr int A_PER = BM * (BK / 4) / PROD;                // 8 chunks of A per thread per stage
+    constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/16 chunks of B
+    const long long lo_delta = op.lo_delta;
+    // A: chunk -> (row / row group, k) assignment and its shared-memory offset
+    ACtx actx[A_MN ? 1 : A_PER];
+    uint32_t a_off[A_PER]; int a_kk[A_PER];
+    if (A_MN) {
+      actx[0] = op.prepA(m0 + lane * 4);
 #pragma unroll
-    for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (PROD / 8));
-    const int ac = tid & 7;
-    auto gload = [&](int it, float4 (&va)[A_PER], float4 (&vb)[B_PER]) {
-      const int k0 = (kt0 + it) * BK;
-      const KCtx kc = op.prepK(k0 + ac * 4);                   // this thread's k chunk: one decode per stage
-#pragma unroll
-      for (int i = 0; i < A_PER; ++i) va[i] = op.loadA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + ac * 4);
-      if (Op::B_KCONTIG) {
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int r = (tid >> 3) + i * (PROD / 8);           // same chunk index ac as A
-          vb[i] = op.loadB(kc, k0 + ac * 4, n0 + r);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int e = tid + i * PROD, n4 = e % (BN / 4), k = e / (BN / 4);
-          vb[i] = op.loadB(kc, k0 + k, n0 + n4 * 4);
-        }
-      }
-    };
-    float4 va[A_PER], vb[B_PER];
-    if (nk > 0) gload(0, va, vb);
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      float4 na[A_PER], nb[B_PER];
-      if (it + 1 < nk) gload(it + 1, na, nb);                  // next stage's global loads fly while this one is split and stored
-      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
-      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo = a_hi + L::A_BYTES;
-      const uint32_t b_hi = a_lo + L::A_BYTES, b_lo = b_hi + L::B_BYTES;
-      if (Op::B_KCONTIG) {
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int r = (tid >> 3) + i * (PROD / 8);
-          float4 hi, lo; split4(vb[i], hi, lo);
-          const uint32_t off = ac * L::B_PLANE + (r >> 3) * L::B_SBO + (r & 7) * 16;
-          sts128(b_hi + off, hi); sts128(b_lo + off, lo);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const int e = tid + i * PROD, n4 = e % (BN / 4), k = e / (BN / 4);
-          float4 hi, lo; split4(vb[i], hi, lo);
-          const uint32_t off = (k >> 2) * L::B_PLANE + (n4 >> 1) * L::B_SBO + ((n4 & 1) * 4) * 16 + (k & 3) * 4;
-          sts32(b_hi + off, hi.x); sts32(b_hi + off + 16, hi.y); sts32(b_hi + off + 32, hi.z); sts32(b_hi + off + 48, hi.w);
-          sts32(b_lo + off, lo.x); sts32(b_lo + off + 16, lo.y); sts32(b_lo + off + 32, lo.z); sts32(b_lo + off + 48, lo.w);
-        }
-      }
+      for (int i = 0; i < A_PER; ++i) { a_kk[i] = (tid >> 5) + 4 * i; a_off[i] = lane * TA::SBO + (a_kk[i] & 7) * 16 + (a_kk[i] >> 3) * TA::LBO; }
+    } else {
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
         const int r = (tid >> 3) + i * (PROD / 8);
-        float4 hi, lo; split4(va[i], hi, lo);
-        const uint32_t off = ac * L::A_PLANE + (r >> 3) * L::A_SBO + (r & 7) * 16;
-        sts128(a_hi + off, hi); sts128(a_lo + off, lo);
+        actx[i] = op.prepA(m0 + r);
+        a_kk[i] = (tid & 7) * 4;
+        a_off[i] = (tid & 7) * TA::LBO + (r >> 3) * TA::SBO + (r & 7) * 16;
       }
-      fence_proxy_async();
+    }
+    uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + i * PROD;
+      if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = g * TB::SBO + (b_kk[i] & 7) * 16 + (b_kk[i] >> 3) * TB::LBO; }
+      else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
+    }
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const int k0 = (kt0 + it) * BK;
+      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
+      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + TA::BYTES;
+      const uint32_t b_hi = a_lo_s + TA::BYTES, b_lo_s = b_hi + TB::BYTES;
+      KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
+      if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                  // K-major: this thread's k chunk is the same for all its rows
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        const float* p;
+        if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
+        else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
+        const uint32_t nb = p ? 16u : 0u;
+        const float* q = p ? p : zero_src;
+        cp_async16(a_hi + a_off[i], q, nb);
+        if (a_lo) cp_async16(a_lo_s + a_off[i], q + (p ? lo_delta : 0), nb);
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
+                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
+        const uint32_t nb = p ? 16u : 0u;
+        const float* q = p ? p : zero_src;
+        cp_async16(b_hi + b_off[i], q, nb);
+        cp_async16(b_lo_s + b_off[i], q + (p ? lo_delta : 0), nb);
+      }
+      cp_async_arrive(bars + 8 * s);
       mbar_arrive(bars + 8 * s);
-      if (it + 1 < nk) {
-#pragma unroll
-        for (int i = 0; i < A_PER; ++i) va[i] = na[i];
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) vb[i] = nb[i];
-      }
     }
     // ================= epilogue =================
     mbar_wait(bar_done, 0);
@@ -242,7 +237,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       if (nk > 0) {
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
 #pragma unroll
-        for (int a = 1; a < NACC; ++a) {                       // sum the interleaved accumulators with round-to-nearest adds
+        for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
           uint32_t q[16];
           tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, q);
 #pragma unroll
@@ -257,6 +252,10 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             op.store4(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else if (nsplit > 1 && (op.N & 3) == 0 && n0 + c0 + 15 < op.N) {
+          float4* wp = reinterpret_cast<float4*>(ws + (long long)blockIdx.z * ws_stride + (long long)m * op.N + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) wp[j >> 2] = make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -273,31 +272,32 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
     tc_fence_before();
   } else {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc(BM, BN);
+    constexpr uint32_t idesc = make_idesc2(BM, BN, A_MN, B_MN);
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(bars + 8 * s, ph);
+      fence_proxy_async();                                      // cp.async wrote through the generic proxy; the MMA reads through the async proxy
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo = a_hi + L::A_BYTES;
-        const uint32_t b_hi = a_lo + L::A_BYTES, b_lo = b_hi + L::B_BYTES;
+        const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + TA::BYTES;
+        const uint32_t b_hi = a_lo_s + TA::BYTES, b_lo_s = b_hi + TB::BYTES;
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + 2 * j * L::A_PLANE, L::A_PLANE, L::A_SBO);
-          const uint64_t dal = make_desc(a_lo + 2 * j * L::A_PLANE, L::A_PLANE, L::A_SBO);
-          const uint64_t dbh = make_desc(b_hi + 2 * j * L::B_PLANE, L::B_PLANE, L::B_SBO);
-          const uint64_t dbl = make_desc(b_lo + 2 * j * L::B_PLANE, L::B_PLANE, L::B_SBO);
+          const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO);
+          const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO);
+          const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO);
+          const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO);
           const int ks = it * (BK / 8) + j;                     // global k-step index of this CTA
           const uint32_t dm = tmem + (uint32_t)((ks % R) * BN);
           if (SEP) {
             const uint32_t dc = tmem + (uint32_t)(R * BN);
-            umma_tf32(dc, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-            umma_tf32(dc, dah, dbl, idesc, 1u);
+            if (a_lo) umma_tf32(dc, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+            umma_tf32(dc, dah, dbl, idesc, (a_lo || ks > 0) ? 1u : 0u);
             umma_tf32(dm, dah, dbh, idesc, ks >= R ? 1u : 0u);
           } else {
-            umma_tf32(dm, dal, dbh, idesc, ks >= R ? 1u : 0u);
-            umma_tf32(dm, dah, dbl, idesc, 1u);
+            if (a_lo) umma_tf32(dm, dal, dbh, idesc, ks >= R ? 1u : 0u);
+            umma_tf32(dm, dah, dbl, idesc, (a_lo || ks >= R) ? 1u : 0u);
             umma_tf32(dm, dah, dbh, idesc, 1u);
           }
         }
@@ -317,29 +317,22 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 
 namespace {
 
-template <int BN, int R, bool SEP, class Op>
-void tc_launch_v(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
-  using L = tc::Lay<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, SEP, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
-    attr_set = true;
-  }
-  tc::tc_gemm_kernel<BN, R, SEP, Op><<<grid, tc::THREADS, L::SMEM, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
-  CK(cudaGetLastError());
-}
 template <int BN, class Op>
 void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
-  switch (e->tc_variant) {
-    case 1: tc_launch_v<BN, 4, false, Op>(e, grid, a, b, nsplit, ws_stride); break;
-    case 2: tc_launch_v<BN, 2, true, Op>(e, grid, a, b, nsplit, ws_stride); break;
-    default: tc_launch_v<BN, 1, false, Op>(e, grid, a, b, nsplit, ws_stride); break;
+  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    attr_set = true;
   }
+  tc::tc_gemm_kernel<BN, 2, true, Op><<<grid, tc::THREADS, L::SMEM, e->stream>>>(a, b, nsplit, e->ws, ws_stride, e->arena);
+  CK(cudaGetLastError());
 }
 
 template <class Op>
 bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_split, double flops, double bytes) {
-  if (e->cfg.math_mode != DQN_MATH_3XTF32) return false;
+  if (e->cfg.math_mode != DQN_MATH_3XTF32 || !e->arena) return false;
+  if (!a.tc_ready() || (nz == 2 && !Op::Z_IS_CLASS && !b.tc_ready())) return false;   // operand planes missing or shapes not 16-byte granular
   Op a0 = a;
   if (Op::Z_IS_CLASS) a0.set_class(0);
   int M = a0.M, N = a0.N, K = a0.K;
@@ -350,7 +343,7 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   int nsplit = 1;
   const int ktiles = (K + tc::BK - 1) / tc::BK;
   if (!Op::Z_IS_CLASS && (allow_split || ctas < e->nsm)) {     // splitk_reduce has no notion of dgrad parity classes
-    nsplit = (int)std::max<long long>(1, std::min<long long>({(2LL * e->nsm + ctas - 1) / ctas, (long long)ktiles / 8, 32LL}));
+    nsplit = (int)std::max<long long>(1, std::min<long long>({(2LL * e->nsm + ctas - 1) / ctas, (long long)ktiles / 8, 64LL}));
     const long long stride = (long long)M * N;
     if (nsplit > 1 && (long long)nz * nsplit * stride > e->ws_floats) nsplit = (int)std::max<long long>(1, e->ws_floats / (nz * stride));
   }
@@ -364,7 +357,7 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
-    dim3 g2((unsigned)std::min<long long>((ws_stride + 255) / 256, 4 * e->nsm), nz);
+    dim3 g2((unsigned)std::min<long long>((ws_stride / 4 + 255) / 256, 4 * e->nsm), nz);
     splitk_reduce_kernel<Op><<<g2, 256, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
     CK(cudaGetLastError());
   }
@@ -375,19 +368,61 @@ bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, doub
 bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int ntow, double fl, double by) {
   return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, false, fl, by);
 }
-bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double fl, double by) {
-  return launch_tc(e, name, op, op, 1, false, fl, by);
+bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, false, fl, by); }
+bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double fl, double by) {
+  return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, false, fl, by);
 }
 bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double fl, double by) {
   return launch_tc(e, name, op, op, op.g.S * op.g.S, false, fl, by);
 }
-bool tc_dense_wgrad(dqn_engine*, const char*, const dqn::DenseWgradOp*, int, double, double) { return false; }
-bool tc_conv_wgrad(dqn_engine*, const char*, const dqn::ConvWgradOp&, double, double) { return false; }
-void tc_init(dqn_engine* e) {
-  const char* v = getenv("DQN_TC_VARIANT");          // accumulator scheme: 0 single, 1 four interleaved, 2 two interleaved + corrections apart
-  e->tc_variant = v ? atoi(v) : 2;
+bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double fl, double by) {
+  return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, true, fl, by);
 }
-void tc_destroy(dqn_engine*) {}
-void tc_params_changed(dqn_engine*) {}
+bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, true, fl, by); }
+
+// (re)build the operand planes of both parameter vectors; the first conv layer's block is pre-scaled by 1/255 when it
+// consumes raw bytes
+void tc_split_params(dqn_engine* e, const float* theta, float* planes) {
+  split_params_kernel<<<2 * e->nsm, 256, 0, e->stream>>>(theta, planes, e->lo_delta, e->nint / 4, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
+  CK(cudaGetLastError());
+}
+void tc_params_changed(dqn_engine* e) {
+  if (!e->arena) return;
+  tc_split_params(e, e->theta, e->w_on_s);
+  tc_split_params(e, e->theta_t, e->w_tg_s);
+}
+void tc_init(dqn_engine* e) {
+  if (e->cfg.math_mode != DQN_MATH_3XTF32) return;
+  // one arena, two planes: every pre-split tensor lives at the same offset in both
+  const int B = e->B;
+  long long off = 0;
+  auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
+  std::vector<long long> o_conv_on, o_conv_tg, o_conv_d;
+  long long o_tow_on[2][MAXD], o_tow_tg[2][MAXD], o_tow_d[2][MAXD];
+  const long long o_xb = take((long long)e->rows_on * e->obs_elems);
+  for (auto& cl : e->convs) {
+    const long long per = (long long)cl.g.OH * cl.g.OW * cl.g.Cout;
+    o_conv_on.push_back(take(e->rows_on * per)); o_conv_tg.push_back(take(B * per)); o_conv_d.push_back(take(B * per));
+  }
+  for (int t = 0; t < e->ntow; ++t)
+    for (int l = 0; l < e->depth; ++l) {
+      o_tow_on[t][l] = take((long long)e->rows_on * e->tow[t][l].N); o_tow_tg[t][l] = take((long long)B * e->tow[t][l].N); o_tow_d[t][l] = take((long long)B * e->tow[t][l].N);
+    }
+  const long long o_won = take(e->nint), o_wtg = take(e->nint), o_ones = take(64);
+  e->lo_delta = off;
+  e->arena = dalloc<float>(2 * off);
+  float* a = e->arena;
+  e->xb_f = a + o_xb;
+  for (size_t l = 0; l < e->convs.size(); ++l) { e->on.conv_out_s.push_back(a + o_conv_on[l]); e->tg.conv_out_s.push_back(a + o_conv_tg[l]); e->conv_delta_s.push_back(a + o_conv_d[l]); }
+  for (int t = 0; t < e->ntow; ++t)
+    for (int l = 0; l < e->depth; ++l) { e->on.tow_out_s[t][l] = a + o_tow_on[t][l]; e->tg.tow_out_s[t][l] = a + o_tow_tg[t][l]; e->tow_delta_s[t][l] = a + o_tow_d[t][l]; }
+  e->w_on_s = a + o_won; e->w_tg_s = a + o_wtg; e->ones = a + o_ones;
+  const float one = 1.f;
+  CK(cudaMemcpy(e->ones, &one, sizeof(float), cudaMemcpyHostToDevice));       // hi plane {1,0,0,0}; lo plane stays zero
+  e->w_scale_lo = e->w_scale_hi = 0;
+  if (e->elem_bytes == 1 && !e->convs.empty()) { e->w_scale_lo = e->convs[0].w.off; e->w_scale_hi = e->convs[0].w.off + (long long)e->convs[0].w.K * e->convs[0].w.N; }
+  tc_params_changed(e);
+}
+void tc_destroy(dqn_engine* e) { if (e->arena) cudaFree(e->arena); e->arena = nullptr; }
 
 }  // namespace

@@ -15,11 +15,11 @@ import util                  # noqa: E402
 
 cp = lib.ControlPlane(2)
 rank, world = cp.rank, cp.world
-nccl_id = cp.broadcast_bytes(lib.nccl_unique_id() if rank == 0 else None, 128)
 ok = True
 for name, mode in (("testmdp", 0), ("conv_small", 0), ("conv_small", 1)):
     spec = util.SPECS[name]
     B = spec["B"]
+    nccl_id = cp.broadcast_bytes(lib.nccl_unique_id() if rank == 0 else None, 128)     # a ncclUniqueId is single-use: one per communicator
     net = util.make_oracle_net(spec, True, seed=21)
     tgt = util.perturbed_copy(net, seed=22)
     cfg = lib.make_config(util.layer_descs(spec), tuple(reversed(spec["obs"])), spec["nA"], obs_dtype="u8" if spec["u8"] else "f32",

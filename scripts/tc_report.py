@@ -29,8 +29,7 @@ print(f"oracle fp32+fp64 took {time.time() - t0:.1f}s")
 g32 = np.concatenate([x.ravel() for x in o32["grads"]])
 g64 = np.concatenate([x.ravel() for x in o64["grads"]])
 print(f"oracle32 vs fp64: q {util.relerr(o32['q'], o64['q']):.2e} td {util.relerr(o32['td'], o64['td']):.2e} grads {util.relerr(g32, g64):.2e}")
-for mode, label, variant in ((0, "fp32-simt", "0"), (1, "3xtf32-v0-single-acc", "0"), (1, "3xtf32-v1-4acc", "1"), (1, "3xtf32-v2-2acc+corr", "2")):
-    os.environ["DQN_TC_VARIANT"] = variant
+for mode, label in ((0, "fp32-simt"), (1, "3xtf32-tcgen05")):
     cfg = lib.make_config(util.layer_descs(spec), tuple(reversed(spec["obs"])), spec["nA"], obs_dtype="u8" if spec["u8"] else "f32",
                           batch_size=spec["B"], buffer_size=spec["N"], learning_rate=spec["lr"], discount=0.99, seed=2, math_mode=mode)
     eng = lib.Engine(cfg)
