@@ -315,12 +315,14 @@ void backward(E* e) {
     wg.M = c.w.K + 1; wg.N = c.g.Cout; wg.K = B * c.g.OH * c.g.OW; wg.vecA = (c.g.Cin % 4 == 0); wg.vecB = (c.g.Cout % 4 == 0);
     if (e->arena) {
       wg.Xs = l == 0 ? e->xb_f : e->on.conv_out_s[l - 1]; wg.Ds = e->conv_delta_s[l]; wg.ones = e->ones; wg.lo_delta = e->lo_delta;
-      wg.a_single = (l == 0 && e->elem_bytes == 1); wg.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
+      wg.a_single = (l == 0 && e->elem_bytes == 1);
     }
     snprintf(nm, sizeof nm, "conv%d_wgrad", l + 1);
     double fl = 2.0 * wg.M * wg.N * wg.K;
     double by = (double)B * c.g.IH * c.g.IW * c.g.Cin * (wg.x_u8 ? 1 : 4) + 4.0 * wg.K * wg.N + 4.0 * wg.M * wg.N;
-    if (!tc_conv_wgrad(e, nm, wg, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
+    ConvWgradOp wg_tc = wg;                    // the tensor-core operand holds raw byte values: fold the 1/255 into its epilogue only
+    wg_tc.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
+    if (!tc_conv_wgrad(e, nm, wg_tc, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
     if (l > 0) {
       ConvDgradOp dg{};
       dg.D = e->conv_delta[l]; dg.W = e->theta + c.w.off; dg.dX = e->conv_delta[l - 1]; dg.Yprev = e->on.conv_out[l - 1];

@@ -38,20 +38,23 @@ template <int ROWS> struct Tile<ROWS, false> {                // K-major: chunk 
   static constexpr int BYTES = (BK / 4) * LBO;
   static constexpr int KSTEP = 2 * LBO;                       // descriptor advance per 8-wide k step
 };
-template <int ROWS> struct Tile<ROWS, true> {                 // MN-major: chunk (k, row group g) at g*SBO + (k%8)*16 + (k/8)*LBO
-  static constexpr int SBO = 144;                             // 128 + 16: consecutive row groups land in different banks
-  static constexpr int LBO = (ROWS / 4) * SBO;
-  static constexpr int BYTES = (BK / 8) * LBO;
-  static constexpr int KSTEP = LBO;
+template <int ROWS> struct Tile<ROWS, true> {                 // MN-major TF32: the only layout the tensor core accepts is SWIZZLE_128B_BASE32B:
+  static_assert(ROWS % 32 == 0, "MN-major tiles come in atoms of 32 rows");
+  static constexpr int SBO = 512;                             //   atom = 4 k-rows x 128 bytes (32 consecutive rows of the operand);
+  static constexpr int LBO = (BK / 4) * SBO;                  //   atoms along k at SBO, along rows at LBO; inside an atom the 32-byte
+  static constexpr int BYTES = (ROWS / 32) * LBO;             //   units of a row are XORed with the row's index (Swizzle<2,5,2> on bytes)
+  static constexpr int KSTEP = 2 * SBO;
 };
 
 template <int BN, bool A_MN, bool B_MN> struct Lay {
   using TA = Tile<BM, A_MN>;
   using TB = Tile<BN, B_MN>;
-  static constexpr int STAGE_BYTES = 2 * TA::BYTES + 2 * TB::BYTES;   // A_hi, A_lo, B_hi, B_lo
-  static constexpr int STAGES = (2 * (2 * STAGE_BYTES + 128) <= 226 * 1024) ? 2 : 3;
+  static constexpr int A_BYTES = (TA::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
+  static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // A_hi, A_lo, B_hi, B_lo
+  static constexpr int STAGES = (2 * (2 * STAGE_BYTES + 1024 + 128) <= 226 * 1024) ? 2 : 3;
   static constexpr int CTAS = STAGES == 2 ? 2 : 1;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;              // + barriers / tmem address
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 128;       // + alignment slack + barriers / tmem address
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -106,8 +109,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// SWIZZLE_128B_BASE32B: word j of 16-byte chunk g is stored at word j ^ (g & 3)
+__device__ __forceinline__ float4 permute_chunk(float4 v, int c) {
+  if (c & 1) { float t = v.x; v.x = v.y; v.y = t; t = v.z; v.z = v.w; v.w = t; }
+  if (c & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -135,7 +148,9 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   using TA = typename L::TA;
   using TB = typename L::TB;
   constexpr int STAGES = L::STAGES;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + STAGES * L::STAGE_BYTES;        // full[STAGES], empty[STAGES], done : 8 bytes each
   const uint32_t bar_done = bars + 16 * STAGES;
@@ -169,17 +184,19 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    // ================= producers: address + cp.async only =================
+    // ================= producers: chunk addresses + cp.async only =================
     constexpr int A_PER = BM * (BK / 4) / PROD;                // 8 chunks of A per thread per stage
     constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/16 chunks of B
     const long long lo_delta = op.lo_delta;
-    // A: chunk -> (row / row group, k) assignment and its shared-memory offset
     ACtx actx[A_MN ? 1 : A_PER];
     uint32_t a_off[A_PER]; int a_kk[A_PER];
-    if (A_MN) {
+    if (A_MN) {                                                // lane = 16-byte chunk along the rows, k rows spread over warps / i
       actx[0] = op.prepA(m0 + lane * 4);
 #pragma unroll
-      for (int i = 0; i < A_PER; ++i) { a_kk[i] = (tid >> 5) + 4 * i; a_off[i] = lane * TA::SBO + (a_kk[i] & 7) * 16 + (a_kk[i] >> 3) * TA::LBO; }
+      for (int i = 0; i < A_PER; ++i) {
+        a_kk[i] = (tid >> 5) + 4 * i;
+        a_off[i] = (lane >> 3) * TA::LBO + a_kk[i] * 128 + (((lane & 7) ^ ((a_kk[i] & 3) << 1)) * 16);   // 32-byte units XOR k row (SWIZZLE_128B_BASE32B)
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
@@ -193,7 +210,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       const int e = tid + i * PROD;
-      if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = g * TB::SBO + (b_kk[i] & 7) * 16 + (b_kk[i] >> 3) * TB::LBO; }
+      if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
     for (int it = 0; it < nk; ++it) {
@@ -201,8 +218,8 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       const uint32_t ph = (it / STAGES) & 1;
       const int k0 = (kt0 + it) * BK;
       mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
-      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + TA::BYTES;
-      const uint32_t b_hi = a_lo_s + TA::BYTES, b_lo_s = b_hi + TB::BYTES;
+      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
+      const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
       KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
       if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                  // K-major: this thread's k chunk is the same for all its rows
 #pragma unroll
@@ -224,7 +241,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
         cp_async16(b_hi + b_off[i], q, nb);
         cp_async16(b_lo_s + b_off[i], q + (p ? lo_delta : 0), nb);
       }
-      cp_async_arrive(bars + 8 * s);
+      cp_async_arrive(bars + 8 * s);                           // arrives once this thread's copies have landed
       mbar_arrive(bars + 8 * s);
     }
     // ================= epilogue =================
@@ -280,14 +297,15 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       fence_proxy_async();                                      // cp.async wrote through the generic proxy; the MMA reads through the async proxy
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + TA::BYTES;
-        const uint32_t b_hi = a_lo_s + TA::BYTES, b_lo_s = b_hi + TB::BYTES;
+        const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
+        const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+        constexpr uint32_t LTA = A_MN ? 1u : 0u, LTB = B_MN ? 1u : 0u;      // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO);
-          const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO);
-          const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO);
-          const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO);
+          const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
+          const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
+          const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
+          const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
           const int ks = it * (BK / 8) + j;                     // global k-step index of this CTA
           const uint32_t dm = tmem + (uint32_t)((ks % R) * BN);
           if (SEP) {
@@ -315,6 +333,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 
 }  // namespace tc
 
+#ifndef TC_KERNEL_ONLY
 namespace {
 
 template <int BN, class Op>
@@ -426,3 +445,4 @@ void tc_init(dqn_engine* e) {
 void tc_destroy(dqn_engine* e) { if (e->arena) cudaFree(e->arena); e->arena = nullptr; }
 
 }  // namespace
+#endif  // TC_KERNEL_ONLY

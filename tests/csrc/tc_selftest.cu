@@ -1,0 +1,141 @@
+// GPU self-test of the tcgen05 kernel in isolation: every operand-layout combination against the CPU executor of the
+// same functor.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tc_selftest tests/csrc/tc_selftest.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../deepqlearning.jl_b200/csrc/igemm.cuh"
+using namespace dqn;
+#define TC_KERNEL_ONLY
+#include "../../deepqlearning.jl_b200/csrc/tc_gemm_impl.cuh"
+
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+static unsigned long long s_ = 88172645463325252ull;
+static float rnd() { s_ ^= s_ << 13; s_ ^= s_ >> 7; s_ ^= s_ << 17; return (float)((s_ >> 11) % 20001) / 10000.f - 1.f; }
+
+struct Arena {
+  float* d = nullptr; long long plane = 0; std::vector<float> h; long long used = 0;
+  void init(long long n) { plane = n; h.assign(2 * n, 0.f); CKC(cudaMalloc(&d, 2 * n * sizeof(float))); }
+  long long put(const std::vector<float>& v, bool single = false) {      // returns offset; writes hi/lo split planes
+    long long o = used; used += ((long long)v.size() + 63) / 64 * 64;
+    for (size_t i = 0; i < v.size(); ++i) { float hi, lo; split_tf32(v[i], hi, lo); if (single) { hi = v[i]; lo = 0; } h[o + i] = hi; h[plane + o + i] = lo; }
+    return o;
+  }
+  long long reserve(long long n) { long long o = used; used += (n + 63) / 64 * 64; return o; }
+  void upload() { CKC(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice)); }
+};
+
+template <int BN, class Op>
+static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
+  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+  Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
+  dim3 grid((o0.M + 127) / 128, (o0.N + BN - 1) / BN, nz * nsplit);
+  tc::tc_gemm_kernel<BN, 2, true, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero);
+  CKC(cudaGetLastError());
+  CKC(cudaDeviceSynchronize());
+}
+
+static int fails = 0;
+static void report(const char* name, const std::vector<float>& got, const std::vector<float>& ref) {
+  double mx = 0, mr = 0; size_t at = 0;
+  for (size_t i = 0; i < ref.size(); ++i) { double d = std::fabs((double)got[i] - ref[i]); if (d > mx) { mx = d; at = i; } mr = std::fmax(mr, std::fabs((double)ref[i])); }
+  const bool ok = mx <= 2e-5 * mr;
+  printf("%s %-28s maxdiff %.3e (ref max %.3e) at %zu: got %g ref %g\n", ok ? "ok  " : "FAIL", name, mx, mr, at, got[at], ref[at]);
+  if (!ok) ++fails;
+}
+
+template <int BN> static void test_dense(int M, int N, int K) {
+  Arena ar; ar.init(4 << 20);
+  std::vector<float> X(M * K), W((K + 1) * N), D(M * N), Y(M * N), C(M * N, 0.f);
+  for (auto& v : X) v = rnd(); for (auto& v : W) v = rnd() * 0.1f; for (auto& v : D) v = rnd(); for (auto& v : Y) v = rnd();
+  long long oX = ar.put(X), oW = ar.put(W), oD = ar.put(D), oOnes = ar.put(std::vector<float>{1.f, 0.f, 0.f, 0.f}, true);
+  ar.upload();
+  float *dX, *dW, *dD, *dY, *dC, *dG, *dDX;
+  CKC(cudaMalloc(&dX, X.size() * 4)); CKC(cudaMalloc(&dW, W.size() * 4)); CKC(cudaMalloc(&dD, D.size() * 4)); CKC(cudaMalloc(&dY, Y.size() * 4));
+  CKC(cudaMalloc(&dC, C.size() * 4)); CKC(cudaMalloc(&dG, W.size() * 4)); CKC(cudaMalloc(&dDX, X.size() * 4));
+  CKC(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice)); CKC(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice)); CKC(cudaMemcpy(dY, Y.data(), Y.size() * 4, cudaMemcpyHostToDevice));
+  {   // forward: A K-major, B MN-major
+    DenseFwdOp op{}; op.X = X.data(); op.ldx = K; op.W = W.data(); op.C = C.data(); op.ldc = N; op.act = ACT_RELU; op.M = M; op.N = N; op.K = K; op.vecA = op.vecB = 1;
+    std::vector<float> ref(M * N); op.C = ref.data(); igemm_host(op);
+    DenseFwdOp g = op; g.X = dX; g.W = dW; g.C = dC; g.Xs = ar.d + oX; g.Ws = ar.d + oW; g.Cs = nullptr; g.lo_delta = ar.plane;
+    run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
+    std::vector<float> got(M * N); CKC(cudaMemcpy(got.data(), dC, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("dense_fwd  (A:K  B:MN)", got, ref);
+  }
+  {   // dgrad: both K-major
+    DenseDgradOp op{}; op.D = D.data(); op.ldd = N; op.W = W.data(); op.ldx = K; op.Y = X.data(); op.ldy = K; op.act = ACT_TANH; op.accumulate = 0; op.apply_act = 1;
+    op.M = M; op.N = K; op.K = N; op.vecA = op.vecB = 1;
+    std::vector<float> ref(M * K); op.dX = ref.data(); igemm_host(op);
+    DenseDgradOp g = op; g.D = dD; g.W = dW; g.dX = dDX; g.Y = dX; g.Ds = ar.d + oD; g.Ws = ar.d + oW; g.dXs = nullptr; g.lo_delta = ar.plane;
+    run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
+    std::vector<float> got(M * K); CKC(cudaMemcpy(got.data(), dDX, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("dense_dgrad(A:K  B:K )", got, ref);
+  }
+  {   // wgrad: both MN-major, with the ones column
+    DenseWgradOp op{}; op.X = X.data(); op.ldx = K; op.D = D.data(); op.ldd = N; op.M = K + 1; op.N = N; op.K = M; op.vecA = op.vecB = 1;
+    std::vector<float> ref((K + 1) * N); op.dW = ref.data(); igemm_host(op);
+    DenseWgradOp g = op; g.X = dX; g.D = dD; g.dW = dG; g.Xs = ar.d + oX; g.Ds = ar.d + oD; g.ones = ar.d + oOnes; g.lo_delta = ar.plane;
+    run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
+    std::vector<float> got((K + 1) * N); CKC(cudaMemcpy(got.data(), dG, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("dense_wgrad(A:MN B:MN)", got, ref);
+  }
+  cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dC); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
+}
+
+template <int BN> static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int KW, int S) {
+  ConvGeom g{}; g.IH = IH; g.IW = IW; g.Cin = Cin; g.OH = (IH - KH) / S + 1; g.OW = (IW - KW) / S + 1; g.Cout = Cout; g.KH = KH; g.KW = KW; g.S = S; g.init();
+  const int K = KH * KW * Cin, P = nimg * g.OH * g.OW;
+  Arena ar; ar.init(8 << 20);
+  std::vector<float> X((size_t)nimg * IH * IW * Cin), W((K + 1) * Cout), D((size_t)P * Cout);
+  for (auto& v : X) v = rnd(); for (auto& v : W) v = rnd() * 0.1f; for (auto& v : D) v = rnd();
+  long long oX = ar.put(X), oW = ar.put(W), oD = ar.put(D), oOnes = ar.put(std::vector<float>{1.f, 0.f, 0.f, 0.f}, true);
+  ar.upload();
+  float *dX, *dW, *dD, *dY, *dG, *dDX;
+  CKC(cudaMalloc(&dX, X.size() * 4)); CKC(cudaMalloc(&dW, W.size() * 4)); CKC(cudaMalloc(&dD, D.size() * 4)); CKC(cudaMalloc(&dY, D.size() * 4));
+  CKC(cudaMalloc(&dG, W.size() * 4)); CKC(cudaMalloc(&dDX, X.size() * 4));
+  CKC(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice)); CKC(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice));
+  {
+    ConvFwdOp op{}; op.X = X.data(); op.W = W.data(); op.act = ACT_RELU; op.nimg = nimg; op.g = g; op.M = P; op.N = Cout; op.K = K; op.vecA = op.vecB = 1;
+    std::vector<float> ref((size_t)P * Cout); op.Y = ref.data(); igemm_host(op);
+    ConvFwdOp q = op; q.X = dX; q.W = dW; q.Y = dY; q.Xs = ar.d + oX; q.Ws = ar.d + oW; q.Ys = nullptr; q.lo_delta = ar.plane;
+    run_tc<BN>(q, 1, 1, nullptr, 0, ar.d);
+    std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dY, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("conv_fwd   (A:K  B:MN)", got, ref);
+  }
+  {
+    ConvWgradOp op{}; op.X = X.data(); op.D = D.data(); op.nimg = nimg; op.g = g; op.M = K + 1; op.N = Cout; op.K = P; op.vecA = op.vecB = 1;
+    std::vector<float> ref((K + 1) * Cout); op.dW = ref.data(); igemm_host(op);
+    ConvWgradOp q = op; q.X = dX; q.D = dD; q.dW = dG; q.Xs = ar.d + oX; q.Ds = ar.d + oD; q.ones = ar.d + oOnes; q.lo_delta = ar.plane;
+    run_tc<BN>(q, 1, 1, nullptr, 0, ar.d);
+    std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dG, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("conv_wgrad (A:MN B:MN)", got, ref);
+  }
+  {
+    std::vector<float> Yp(X.size()); for (auto& v : Yp) v = rnd();
+    float* dYp; CKC(cudaMalloc(&dYp, Yp.size() * 4)); CKC(cudaMemcpy(dYp, Yp.data(), Yp.size() * 4, cudaMemcpyHostToDevice));
+    ConvDgradOp op{}; op.D = D.data(); op.W = W.data(); op.Yprev = Yp.data(); op.act = ACT_RELU; op.apply_act = 1; op.nimg = nimg; op.g = g; op.vecA = op.vecB = 1;
+    std::vector<float> ref(X.size(), 0.f); op.dX = ref.data(); for (int z = 0; z < S * S; ++z) igemm_host(op, z);
+    ConvDgradOp q = op; q.D = dD; q.W = dW; q.dX = dDX; q.Yprev = dYp; q.Ds = ar.d + oD; q.Ws = ar.d + oW; q.dXs = nullptr; q.lo_delta = ar.plane;
+    CKC(cudaMemset(dDX, 0, X.size() * 4));
+    run_tc<BN>(q, S * S, 1, nullptr, 0, ar.d);
+    std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dDX, got.size() * 4, cudaMemcpyDeviceToHost));
+    report("conv_dgrad (A:K  B:K )", got, ref);
+    cudaFree(dYp);
+  }
+  cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
+}
+
+int main() {
+  printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
+  printf("-- dense M=200 N=128 K=160 (BN=128)\n"); test_dense<128>(200, 128, 160);
+  printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
+  printf("-- conv 4 img 20x20x8 -> 16, 4x4 s2 (BN=32)\n"); test_conv<32>(4, 20, 20, 8, 16, 4, 4, 2);
+  printf("-- conv 3 img 9x9x32 -> 64, 3x3 s1 (BN=64)\n");  test_conv<64>(3, 9, 9, 32, 64, 3, 3, 1);
+  printf(fails ? "SELFTEST FAILED %d\n" : "SELFTEST OK\n", fails);
+  return fails ? 1 : 0;
+}
