@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -160,6 +161,12 @@ def main():
     ms = cp.max_over_ranks(ms)
     launches = eng.launches_per_step() * args.steps
     value = world * args.steps / (ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms / args.steps, "n_gpus": world, "env": {k: v for k, v in os.environ.items() if k.startswith("DQN_")}, "loss": loss}))
+        eng.close()
+        cp.close()
+        return
 
     # ---- end to end through the public call with host buffers (e2e) -------------------------------
     #   per gradient step: add_exp! of train_freq=4 fresh transitions from pinned host memory (H2D), batch_train!, read (loss, grad_norm) (D2H)

@@ -90,6 +90,10 @@ struct dqn_engine {
   dqn_config_t cfg{};
   std::string err;
   cudaStream_t stream = nullptr;
+  // second lane: the target-network forward and the weight gradients run beside the online forward / the dgrad chain
+  cudaStream_t stream2 = nullptr; float* ws2 = nullptr;
+  cudaStream_t ls = nullptr; float* lws = nullptr;     // lane the contraction launchers currently target
+  std::vector<cudaEvent_t> evs; size_t ev_next = 0; int use_streams = 1;
   int nsm = 148;
   // topology
   std::vector<ConvL> convs;
@@ -134,6 +138,7 @@ struct dqn_engine {
   float* xb_f = nullptr; std::vector<float*> conv_delta_s; float* tow_delta_s[2][MAXD] = {};
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
+  int tc_deep = -1;
 };
 
 namespace {
@@ -155,11 +160,11 @@ struct Scope {
     if (on) {
       ProfRec r; r.name = name; r.flops = flops; r.bytes = bytes;
       CK(cudaEventCreate(&r.a)); CK(cudaEventCreate(&r.b));
-      CK(cudaEventRecord(r.a, e->stream));
+      CK(cudaEventRecord(r.a, e->ls));
       e->prof.push_back(r);
     }
   }
-  ~Scope() { if (on) cudaEventRecord(e->prof.back().b, e->stream); }
+  ~Scope() { if (on) cudaEventRecord(e->prof.back().b, e->ls); }
 };
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -179,7 +184,7 @@ void launch_igemm(E* e, const char* name, Op a, Op b, int nz, bool allow_split, 
   else cfgid = 1;
   const int bm = cfgid == 1 ? 64 : 128, bn = cfgid == 2 ? 32 : 64;
   int nsplit = 1;
-  if (allow_split) {
+  if (allow_split || (!Op::Z_IS_CLASS && 2 * ctas(bm, bn) <= e->nsm)) {     // also split tiny grids (the 512->1|6 heads): latency, not flops
     const int ktiles = (K + IGEMM_BK - 1) / IGEMM_BK;
     long long c = ctas(bm, bn);
     nsplit = (int)std::max<long long>(1, std::min<long long>({(2LL * e->nsm + c - 1) / c, (long long)ktiles / 4, 64LL}));
@@ -190,17 +195,33 @@ void launch_igemm(E* e, const char* name, Op a, Op b, int nz, bool allow_split, 
   const long long ws_stride = (long long)M * N;
   {
     Scope sc(e, name, flops, bytes);
-    if (cfgid == 0) igemm_kernel<128, 64, 8, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
-    else if (cfgid == 1) igemm_kernel<64, 64, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
-    else igemm_kernel<128, 32, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    if (cfgid == 0) igemm_kernel<128, 64, 8, 4, Op><<<grid, IGEMM_THREADS, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
+    else if (cfgid == 1) igemm_kernel<64, 64, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
+    else igemm_kernel<128, 32, 4, 4, Op><<<grid, IGEMM_THREADS, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
     CK(cudaGetLastError());
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
     dim3 g2((unsigned)std::min<long long>((ws_stride + 255) / 256, 4 * e->nsm), nz);
-    splitk_reduce_kernel<Op><<<g2, 256, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
     CK(cudaGetLastError());
   }
+}
+
+// lane switch + fork/join helpers (work identically in eager mode and under stream capture)
+struct Lane {
+  E* e; cudaStream_t s0; float* w0;
+  Lane(E* e_, bool second) : e(e_), s0(e_->ls), w0(e_->lws) { if (second) { e->ls = e->stream2; e->lws = e->ws2; } }
+  ~Lane() { e->ls = s0; e->lws = w0; }
+};
+cudaEvent_t next_event(E* e) {
+  if (e->ev_next == e->evs.size()) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->evs.push_back(ev); }
+  return e->evs[e->ev_next++];
+}
+void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everything enqueued on `later` from now on waits for `earlier` up to now
+  cudaEvent_t ev = next_event(e);
+  CK(cudaEventRecord(ev, earlier));
+  CK(cudaStreamWaitEvent(later, ev, 0));
 }
 
 // ---- network schedule ---------------------------------------------------------------------------
@@ -244,7 +265,7 @@ void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& b
   }
 }
 
-void backward(E* e) {
+void backward(E* e, bool conc) {
   const int B = e->B;
   char nm[64];
   const bool trunk = !e->convs.empty();
@@ -270,7 +291,11 @@ void backward(E* e) {
     snprintf(nm, sizeof nm, "dense%d_wgrad", l + 1);
     double fl = 0, by = 0;
     for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * wg[t].M * wg[t].N * B; by += 4.0 * ((double)B * wg[t].M + (double)B * wg[t].N + (double)wg[t].M * wg[t].N); }
-    if (!tc_dense_wgrad(e, nm, wg, e->ntow, fl, by)) launch_igemm(e, nm, wg[0], wg[1], e->ntow, true, fl, by);
+    {
+      if (conc) order_after(e, e->stream2, e->stream);          // delta of this layer is complete on the main lane
+      Lane lane(e, conc);
+      if (!tc_dense_wgrad(e, nm, wg, e->ntow, fl, by)) launch_igemm(e, nm, wg[0], wg[1], e->ntow, true, fl, by);
+    }
     // input gradients
     if (l > 0) {
       DenseDgradOp dg[2];
@@ -322,7 +347,11 @@ void backward(E* e) {
     double by = (double)B * c.g.IH * c.g.IW * c.g.Cin * (wg.x_u8 ? 1 : 4) + 4.0 * wg.K * wg.N + 4.0 * wg.M * wg.N;
     ConvWgradOp wg_tc = wg;                    // the tensor-core operand holds raw byte values: fold the 1/255 into its epilogue only
     wg_tc.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
-    if (!tc_conv_wgrad(e, nm, wg_tc, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
+    {
+      if (conc) order_after(e, e->stream2, e->stream);
+      Lane lane(e, conc);
+      if (!tc_conv_wgrad(e, nm, wg_tc, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
+    }
     if (l > 0) {
       ConvDgradOp dg{};
       dg.D = e->conv_delta[l]; dg.W = e->theta + c.w.off; dg.dX = e->conv_delta[l - 1]; dg.Yprev = e->on.conv_out[l - 1];
@@ -364,8 +393,15 @@ void enqueue_step(E* e, bool sample) {
   }
   enqueue_batch_prep(e);
   const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? e->xb_f : nullptr;
+  const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
+  e->ev_next = 0;
+  if (conc) order_after(e, e->stream2, e->stream);            // fork: the gathered batch is ready
+  {
+    Lane lane(e, conc);
+    forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s);
+  }
   forward(e, e->theta, e->xb, e->elem_bytes == 1, 2 * B, e->on, "online", xs, e->w_on_s);
-  forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s);
+  if (conc) order_after(e, e->stream, e->stream2);            // join before the head needs Q_target(s')
   {
     HeadArgs h{};
     const int L = e->depth - 1;
@@ -382,7 +418,8 @@ void enqueue_step(E* e, bool sample) {
     head_loss_kernel<<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
     CK(cudaGetLastError());
   }
-  backward(e);
+  backward(e, conc);
+  if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
     Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
     ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)e->nint, ncclFloat, ncclSum, e->comm, e->stream);
@@ -618,6 +655,8 @@ void allocate(E* e) {
   e->y = dalloc<float>(B); e->td = dalloc<float>(B); e->newp = dalloc<float>(B); e->best_a = dalloc<int>(B);
   e->ws_floats = 16LL << 20;      // 64 MB split-K workspace
   e->ws = dalloc<float>(e->ws_floats);
+  e->ws2 = dalloc<float>(e->ws_floats);
+  e->lws = e->ws;
   CK(cudaHostAlloc(&e->host_out, 16, cudaHostAllocMapped));
   memset(e->host_out, 0, 16);
   CK(cudaHostGetDevicePointer(&e->host_out_dev, e->host_out, 0));
@@ -634,7 +673,7 @@ void destroy(E* e) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   tc_destroy(e);
   void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
-                  e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws,
+                  e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws, e->ws2,
                   e->stage, e->flush_buf};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto p : e->on.conv_out) cudaFree(p);
@@ -646,6 +685,8 @@ void destroy(E* e) {
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (e->t0) cudaEventDestroy(e->t0);
   if (e->t1) cudaEventDestroy(e->t1);
+  for (auto ev : e->evs) cudaEventDestroy(ev);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -741,6 +782,9 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     if (prop.major < 10) fail(DQN_ERR_UNSUPPORTED, "compute capability %d.%d: this library is built for sm_100a only", prop.major, prop.minor);
     e->nsm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    e->ls = e->stream;
+    { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
     build_topology(e);
     allocate(e);
     tc_init(e);

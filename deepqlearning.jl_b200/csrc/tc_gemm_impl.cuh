@@ -46,14 +46,17 @@ template <int ROWS> struct Tile<ROWS, true> {                 // MN-major TF32: 
   static constexpr int KSTEP = 2 * SBO;
 };
 
-template <int BN, bool A_MN, bool B_MN> struct Lay {
+template <int BN, bool A_MN, bool B_MN, bool DEEP> struct Lay {
   using TA = Tile<BM, A_MN>;
   using TB = Tile<BN, B_MN>;
   static constexpr int A_BYTES = (TA::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
   static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // A_hi, A_lo, B_hi, B_lo
-  static constexpr int STAGES = (2 * (2 * STAGE_BYTES + 1024 + 128) <= 226 * 1024) ? 2 : 3;
-  static constexpr int CTAS = STAGES == 2 ? 2 : 1;
+  // DEEP: one CTA per SM with as many stages as fit (long-K contractions with few tiles: latency hiding comes from depth);
+  // otherwise two co-resident CTAs with two stages each when they fit (many short tiles: the neighbour hides prologue/epilogue)
+  static constexpr int FIT = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = DEEP ? (FIT > 6 ? 6 : FIT) : ((2 * (2 * STAGE_BYTES + 1024 + 128) <= 226 * 1024) ? 2 : 3);
+  static constexpr int CTAS = (!DEEP && STAGES == 2) ? 2 : 1;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 128;       // + alignment slack + barriers / tmem address
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -140,11 +143,11 @@ __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool
 }
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int BN, int R, bool SEP, class Op>
-__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>::CTAS == 2 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
+template <int BN, int R, bool SEP, bool DEEP, class Op>
+__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>::CTAS == 2 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
 tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
-  using L = Lay<BN, A_MN, B_MN>;
+  using L = Lay<BN, A_MN, B_MN, DEEP>;
   using TA = typename L::TA;
   using TB = typename L::TB;
   constexpr int STAGES = L::STAGES;
@@ -336,16 +339,21 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #ifndef TC_KERNEL_ONLY
 namespace {
 
-template <int BN, class Op>
-void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
-  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>;
+template <int BN, bool DEEP, class Op>
+void tc_launch_d(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
+  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, DEEP, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set = true;
   }
-  tc::tc_gemm_kernel<BN, 2, true, Op><<<grid, tc::THREADS, L::SMEM, e->stream>>>(a, b, nsplit, e->ws, ws_stride, e->arena);
+  tc::tc_gemm_kernel<BN, 2, true, DEEP, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena);
   CK(cudaGetLastError());
+}
+template <int BN, class Op>
+void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride, bool deep) {
+  if (deep) tc_launch_d<BN, true, Op>(e, grid, a, b, nsplit, ws_stride);
+  else tc_launch_d<BN, false, Op>(e, grid, a, b, nsplit, ws_stride);
 }
 
 template <class Op>
@@ -368,16 +376,19 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   }
   const long long ws_stride = (long long)M * N;
   dim3 grid((M + tc::BM - 1) / tc::BM, (N + bn - 1) / bn, nz * nsplit);
+  // deep single-CTA pipelines when the grid cannot put two CTAs on every SM anyway, or when each CTA runs a long k loop
+  const int kt_per_cta = (ktiles + nsplit - 1) / nsplit;
+  const bool deep = e->tc_deep == 1 || (e->tc_deep < 0 && ((long long)grid.x * grid.y * grid.z <= 2LL * e->nsm || kt_per_cta >= 24));
   {
     Scope sc(e, name, flops, bytes);
-    if (bn == 32) tc_launch_bn<32, Op>(e, grid, a, b, nsplit, ws_stride);
-    else if (bn == 64) tc_launch_bn<64, Op>(e, grid, a, b, nsplit, ws_stride);
-    else tc_launch_bn<128, Op>(e, grid, a, b, nsplit, ws_stride);
+    if (bn == 32) tc_launch_bn<32, Op>(e, grid, a, b, nsplit, ws_stride, deep);
+    else if (bn == 64) tc_launch_bn<64, Op>(e, grid, a, b, nsplit, ws_stride, deep);
+    else tc_launch_bn<128, Op>(e, grid, a, b, nsplit, ws_stride, deep);
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
     dim3 g2((unsigned)std::min<long long>((ws_stride / 4 + 255) / 256, 4 * e->nsm), nz);
-    splitk_reduce_kernel<Op><<<g2, 256, 0, e->stream>>>(a, b, nsplit, e->ws, ws_stride);
+    splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
     CK(cudaGetLastError());
   }
   return true;
@@ -412,6 +423,8 @@ void tc_params_changed(dqn_engine* e) {
 }
 void tc_init(dqn_engine* e) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32) return;
+  const char* dv = getenv("DQN_TC_DEEP");           // pipeline shape override: 0 = two CTAs x two stages, 1 = one CTA, deep; unset = per-launch heuristic
+  e->tc_deep = dv ? atoi(dv) : -1;
   // one arena, two planes: every pre-split tensor lives at the same offset in both
   const int B = e->B;
   long long off = 0;

@@ -27,13 +27,16 @@ struct Arena {
   void upload() { CKC(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice)); }
 };
 
+#ifndef DEEPT
+#define DEEPT true
+#endif
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
-  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG>;
-  CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEPT>;
+  CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, DEEPT, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
   Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
   dim3 grid((o0.M + 127) / 128, (o0.N + BN - 1) / BN, nz * nsplit);
-  tc::tc_gemm_kernel<BN, 2, true, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero);
+  tc::tc_gemm_kernel<BN, 2, true, DEEPT, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero);
   CKC(cudaGetLastError());
   CKC(cudaDeviceSynchronize());
 }
