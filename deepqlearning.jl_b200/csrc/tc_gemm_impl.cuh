@@ -8,13 +8,13 @@
 // batch and by the Adam pass for the weights; both planes of a tensor sit lo_delta floats apart in one arena).  The
 // producers therefore never touch data with the ALU:
 //
-//   warps 0-3 (128 threads)  cp.async 16-byte chunks global -> shared straight into the UMMA canonical no-swizzle layout,
+//   warps 0-7 (256 threads)  cp.async 16-byte chunks global -> shared straight into the UMMA canonical no-swizzle layout,
 //                            K-major (8-row x 16-byte core matrices, chunk = 4 consecutive k) or MN-major (chunk = 4
 //                            consecutive rows) depending on which way the source tensor is contiguous; im2col rows,
 //                            dgrad parity classes and the [x 1] bias column are just different chunk addresses
 //                            (op.ptrA / op.ptrB, nullptr = zero fill).  Completion is tracked by the stage's mbarrier
 //                            (cp.async.mbarrier.arrive).  After the main loop the same warps run the epilogue.
-//   warp 4                   one elected lane issues tcgen05.mma.kind::tf32, three per 8-wide k step:
+//   warp 8                   one elected lane issues tcgen05.mma.kind::tf32, three per 8-wide k step:
 //                            D += A_lo B_hi + A_hi B_lo + A_hi B_hi   (error-compensated "3xTF32"; the dropped
 //                            A_lo B_lo term is O(2^-22)); two when A is single-plane (raw byte values are TF32-exact).
 //   accumulators             fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
@@ -22,13 +22,17 @@
 //                            product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
 #pragma once
 #include <cstdlib>
+#ifndef TC_PRODUCER_CPASYNC
+#define TC_PRODUCER_CPASYNC 1      // 1: cp.async producers (faster in the full step on B200), 0: ld.global.nc -> st.shared
+#endif
+#define TC_CP_CA 1
 
 namespace tc {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-constexpr int PROD = 128;        // producer / epilogue threads
-constexpr int THREADS = 160;     // + 1 MMA warp
+constexpr int PROD = 256;        // producer / epilogue threads (8 warps: short per-thread address chains, more loads in flight)
+constexpr int THREADS = 288;     // + 1 MMA warp
 
 // shared-memory tile of one operand plane for one stage
 template <int ROWS, bool MN> struct Tile;
@@ -132,7 +136,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+#ifdef TC_CP_CA
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");   // L2 only: operands stream
+#endif
 }
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive when this thread's prior cp.async have landed
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -180,16 +188,16 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
+  if (warp == PROD / 32) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < PROD / 32) {
     // ================= producers: chunk addresses + cp.async only =================
-    constexpr int A_PER = BM * (BK / 4) / PROD;                // 8 chunks of A per thread per stage
-    constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/16 chunks of B
+    constexpr int A_PER = BM * (BK / 4) / PROD;                // 4 chunks of A per thread per stage
+    constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/32 chunks of B
     const long long lo_delta = op.lo_delta;
     ACtx actx[A_MN ? 1 : A_PER];
     uint32_t a_off[A_PER]; int a_kk[A_PER];
@@ -197,7 +205,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       actx[0] = op.prepA(m0 + lane * 4);
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
-        a_kk[i] = (tid >> 5) + 4 * i;
+        a_kk[i] = (tid >> 5) + (PROD / 32) * i;
         a_off[i] = (lane >> 3) * TA::LBO + a_kk[i] * 128 + (((lane & 7) ^ ((a_kk[i] & 3) << 1)) * 16);   // 32-byte units XOR k row (SWIZZLE_128B_BASE32B)
       }
     } else {
@@ -220,11 +228,13 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       const int k0 = (kt0 + it) * BK;
-      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
       const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
       const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
       KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
       if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                  // K-major: this thread's k chunk is the same for all its rows
+#if TC_PRODUCER_CPASYNC
+      // cp.async.ca 16-byte chunks straight into the UMMA layout; the stage's mbarrier tracks their completion
+      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
         const float* p;
@@ -238,28 +248,57 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) {
         const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
-                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
+                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);
         const uint32_t nb = p ? 16u : 0u;
         const float* q = p ? p : zero_src;
         cp_async16(b_hi + b_off[i], q, nb);
         cp_async16(b_lo_s + b_off[i], q + (p ? lo_delta : 0), nb);
       }
-      cp_async_arrive(bars + 8 * s);                           // arrives once this thread's copies have landed
+      cp_async_arrive(bars + 8 * s);
       mbar_arrive(bars + 8 * s);
+#else
+      // alternative kept for experiments: ld.global.nc 16 bytes -> registers -> st.shared 16 bytes, loads issued before the
+      // slot wait.  Same speed as cp.async on an isolated GEMM, ~10% slower inside the full step (register pressure, issue slots).
+      float4 vah[A_PER], val[A_PER], vbh[B_PER], vbl[B_PER];
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        const float* p;
+        if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
+        else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
+        vah[i] = p ? ldg_f4(p) : make4(0, 0, 0, 0);
+        val[i] = (p && a_lo) ? ldg_f4(p + lo_delta) : make4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
+                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
+        vbh[i] = p ? ldg_f4(p) : make4(0, 0, 0, 0);
+        vbl[i] = p ? ldg_f4(p + lo_delta) : make4(0, 0, 0, 0);
+      }
+      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) { sts128(a_hi + a_off[i], vah[i]); if (a_lo) sts128(a_lo_s + a_off[i], val[i]); }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) { sts128(b_hi + b_off[i], vbh[i]); sts128(b_lo_s + b_off[i], vbl[i]); }
+      fence_proxy_async();                                     // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(bars + 8 * s);
+#endif
     }
     // ================= epilogue =================
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
+    const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int m = m0 + q4 * 32 + lane;
+    constexpr int CPW = BN / (PROD / 128);                     // columns per warp: the two warps of a quarter split the tile's columns
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = (warp >> 2) * CPW; c0 < (warp >> 2) * CPW + CPW; c0 += 16) {
       uint32_t r[16];
       if (nk > 0) {
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + c0, r);
 #pragma unroll
         for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
           uint32_t q[16];
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, q);
+          tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + a * BN + c0, q);
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
         }
@@ -297,7 +336,6 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(bars + 8 * s, ph);
-      fence_proxy_async();                                      // cp.async wrote through the generic proxy; the MMA reads through the async proxy
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
@@ -331,7 +369,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc<TCOLS>(tmem); }
+  if (warp == PROD / 32) { tc_fence_after(); tmem_dealloc<TCOLS>(tmem); }
 }
 
 }  // namespace tc
@@ -424,7 +462,7 @@ void tc_params_changed(dqn_engine* e) {
 void tc_init(dqn_engine* e) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32) return;
   const char* dv = getenv("DQN_TC_DEEP");           // pipeline shape override: 0 = two CTAs x two stages, 1 = one CTA, deep; unset = per-launch heuristic
-  e->tc_deep = dv ? atoi(dv) : -1;
+  e->tc_deep = dv ? atoi(dv) : 0;      // measured on B200: two co-resident CTAs beat one deep pipeline on every layer of config 3
   // one arena, two planes: every pre-split tensor lives at the same offset in both
   const int B = e->B;
   long long off = 0;

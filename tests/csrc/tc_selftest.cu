@@ -133,7 +133,38 @@ template <int BN> static void test_conv(int nimg, int IH, int IW, int Cin, int C
   cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
 }
 
-int main() {
+// timing of one big dense forward (conv2-like and fc1-like shapes) - tuning aid
+template <int BN> static void bench_dense(int M, int N, int K, int iters) {
+  Arena ar; ar.init(64 << 20);
+  std::vector<float> X((size_t)M * K, 0.5f), W((size_t)(K + 1) * N, 0.25f);
+  long long oX = ar.put(X), oW = ar.put(W);
+  ar.upload();
+  float *dW, *dC; CKC(cudaMalloc(&dW, W.size() * 4)); CKC(cudaMalloc(&dC, (size_t)M * N * 4));
+  CKC(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  DenseFwdOp g{}; g.X = nullptr; g.ldx = K; g.W = dW; g.C = dC; g.ldc = N; g.act = ACT_RELU; g.M = M; g.N = N; g.K = K; g.vecA = g.vecB = 1;
+  g.Xs = ar.d + oX; g.Ws = ar.d + oW; g.Cs = nullptr; g.lo_delta = ar.plane;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
+  using L = tc::Lay<BN, false, true, DEEPT>;
+  dim3 grid((M + 127) / 128, (N + BN - 1) / BN, 1);
+  cudaEventRecord(a);
+  for (int i = 0; i < iters; ++i) tc::tc_gemm_kernel<BN, 2, true, DEEPT, DenseFwdOp><<<grid, tc::THREADS, L::SMEM>>>(g, g, 1, nullptr, 0, ar.d);
+  cudaEventRecord(b); CKC(cudaEventSynchronize(b));
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  const double us = 1e3 * ms / iters, tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
+  printf("bench dense M=%d N=%d K=%d BN=%d stages=%d ctas/SM=%d: %.1f us  %.1f TFLOP/s algorithmic (x3 = %.0f TF32)  grid %d\n", M, N, K, BN, L::STAGES, L::CTAS, us, tf, 3 * tf, grid.x * grid.y);
+  cudaFree(dW); cudaFree(dC); cudaFree(ar.d);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1) {
+    bench_dense<64>(41472, 64, 512, 20);       // conv2 forward shape
+    bench_dense<64>(37888, 64, 512, 20);       // same, exactly one wave of 296 CTAs
+    bench_dense<32>(204800, 32, 256, 20);      // conv1 forward shape (with a lo plane here)
+    bench_dense<128>(512, 1024, 3136, 20);     // fc1 forward, both towers
+    bench_dense<128>(18944, 128, 512, 20);     // one wave of BN=128 tiles
+    return 0;
+  }
   printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
   printf("-- dense M=200 N=128 K=160 (BN=128)\n"); test_dense<128>(200, 128, 160);
   printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
