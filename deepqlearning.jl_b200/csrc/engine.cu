@@ -92,6 +92,8 @@ struct dqn_engine {
   cudaStream_t stream = nullptr;
   // second lane: the target-network forward and the weight gradients run beside the online forward / the dgrad chain
   cudaStream_t stream2 = nullptr; float* ws2 = nullptr;
+  cudaStream_t stream3 = nullptr;                       // NCCL lane: the fc bucket is reduced while the conv backward still runs
+  long long tower_off = 0;                              // internal offset where the tower (Dense) parameters start
   cudaStream_t ls = nullptr; float* lws = nullptr;     // lane the contraction launchers currently target
   std::vector<cudaEvent_t> evs; size_t ev_next = 0; int use_streams = 1;
   int nsm = 148;
@@ -154,17 +156,18 @@ template <class T> T* dalloc(long long n) {
 
 // ---- launch bookkeeping -------------------------------------------------------------------------
 struct Scope {
-  E* e; bool on;
+  E* e; bool on; size_t slot = 0;
   Scope(E* e_, const char* name, double flops, double bytes) : e(e_), on(e_->profiling && !e_->capturing) {
     if (e->counting) e->launches++;
     if (on) {
       ProfRec r; r.name = name; r.flops = flops; r.bytes = bytes;
       CK(cudaEventCreate(&r.a)); CK(cudaEventCreate(&r.b));
       CK(cudaEventRecord(r.a, e->ls));
+      slot = e->prof.size();
       e->prof.push_back(r);
     }
   }
-  ~Scope() { if (on) cudaEventRecord(e->prof.back().b, e->ls); }
+  ~Scope() { if (on) cudaEventRecord(e->prof[slot].b, e->ls); }
 };
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -332,6 +335,11 @@ void backward(E* e, bool conc) {
       }
     }
   }
+  if (conc && e->cfg.world > 1 && trunk) {               // every Dense gradient is enqueued: reduce that bucket now, behind the conv backward
+    order_after(e, e->stream3, e->stream2);
+    ncclResult_t r = g_nccl.AllReduce(e->grad + e->tower_off, e->grad + e->tower_off, (size_t)(e->nint - e->tower_off), ncclFloat, ncclSum, e->comm, e->stream3);
+    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
   for (int l = (int)e->convs.size() - 1; l >= 0; --l) {
     const ConvL& c = e->convs[l];
     ConvWgradOp wg{};
@@ -366,32 +374,36 @@ void backward(E* e, bool conc) {
   }
 }
 
-void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for the indices in idx_d
+void enqueue_gather(E* e) {       // observation rows of the sampled transitions -> batch (and its tensor-core operand planes)
+  const long long rb = e->obs_row_bytes;
+  const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
+  dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
+  Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
+  gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0) ? e->xb_f : nullptr, e->lo_delta, e->elem_bytes == 1);
+  CK(cudaGetLastError());
+}
+void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for indices given by the caller
   {
     Scope sc(e, "batch_meta", 0, e->B * 40.0);
     batch_meta_kernel<<<(e->B + 255) / 256, 256, 0, e->stream>>>(e->idx_d, e->B, e->tree, e->P, e->act, e->rew, e->done, e->st,
                                                                 e->cfg.beta, e->a_b, e->r_b, e->d_b, e->w_b);
     CK(cudaGetLastError());
   }
-  {
-    const long long rb = e->obs_row_bytes;
-    const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
-    dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
-    Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
-    gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0) ? e->xb_f : nullptr, e->lo_delta, e->elem_bytes == 1);
-    CK(cudaGetLastError());
-  }
+  enqueue_gather(e);
 }
+size_t sample_smem(int B) { int HT = 1; while (HT < 4 * B) HT <<= 1; return 2 * HT * sizeof(int) + TREE_TOP * sizeof(float); }
 
 void enqueue_step(E* e, bool sample) {
   const int B = e->B;
   if (sample) {
-    int HT = 1; while (HT < 4 * B) HT <<= 1;
-    Scope sc(e, "sumtree_sample", 0, B * 8.0 * 22);
-    sample_kernel<<<1, (B + 31) / 32 * 32, 2 * HT * sizeof(int), e->stream>>>(e->tree, e->P, B, e->cfg.seed, e->st, 0, 0, e->idx_d);
-    CK(cudaGetLastError());
-  }
-  enqueue_batch_prep(e);
+    {
+      Scope sc(e, "sumtree_sample", 0, B * 8.0 * 22);
+      sample_kernel<<<1, (B + 31) / 32 * 32, sample_smem(B), e->stream>>>(e->tree, e->P, B, e->cfg.seed, e->st, 0, 0, e->idx_d,
+                                                                            e->act, e->rew, e->done, e->cfg.beta, e->a_b, e->r_b, e->d_b, e->w_b);
+      CK(cudaGetLastError());
+    }
+    enqueue_gather(e);
+  } else enqueue_batch_prep(e);
   const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? e->xb_f : nullptr;
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
   e->ev_next = 0;
@@ -421,9 +433,14 @@ void enqueue_step(E* e, bool sample) {
   backward(e, conc);
   if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
+    const bool split = conc && !e->convs.empty();          // the Dense bucket is already in flight on the NCCL lane
     Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
-    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)e->nint, ncclFloat, ncclSum, e->comm, e->stream);
+    const long long n = split ? e->tower_off : e->nint;
+    cudaStream_t cs = split ? e->stream3 : e->stream;
+    if (split) order_after(e, e->stream3, e->stream);
+    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)n, ncclFloat, ncclSum, e->comm, cs);
     if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    if (split) order_after(e, e->stream, e->stream3);
   }
   {
     Scope sc(e, "adam", 0, 7.0 * e->nint * 4);
@@ -435,12 +452,7 @@ void enqueue_step(E* e, bool sample) {
   {
     Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
     tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
-                                                                               1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0);
-    CK(cudaGetLastError());
-  }
-  {
-    Scope sc(e, "publish", 0, 12);
-    publish_kernel<<<1, 1, 0, e->stream>>>(e->st, e->host_out_dev);
+                                                                               1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
     CK(cudaGetLastError());
   }
 }
@@ -531,7 +543,7 @@ void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const u
     CK(cudaGetLastError());
   }
   if (n <= 4096) {
-    tree_update_kernel<<<1, 1024, 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0);
+    tree_update_kernel<<<1, 1024, 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0, nullptr);
     CK(cudaGetLastError());
   } else rebuild_tree(e);
   e->cursor = (e->cursor + n) % e->cap;
@@ -584,6 +596,7 @@ void build_topology(E* e) {
   long long off = 0;
   auto place = [&](Mat& m) { m.off = off; off += ((long long)(m.K + 1) * m.N + 3) / 4 * 4; };
   for (auto& cl : e->convs) place(cl.w);
+  e->tower_off = off;
   for (int t = 0; t < e->ntow; ++t)
     for (int l = 0; l < e->depth; ++l) {
       Mat m{0, dense[l].in, dense[l].out, dense[l].act};
@@ -686,6 +699,7 @@ void destroy(E* e) {
   if (e->t0) cudaEventDestroy(e->t0);
   if (e->t1) cudaEventDestroy(e->t1);
   for (auto ev : e->evs) cudaEventDestroy(ev);
+  if (e->stream3) cudaStreamDestroy(e->stream3);
   if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -783,6 +797,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     e->nsm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->stream3, cudaStreamNonBlocking));
     e->ls = e->stream;
     { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
     build_topology(e);
@@ -932,7 +947,7 @@ int dqn_update_priorities(dqn_engine_t* h, const int64_t* idx, const float* td, 
     CK(cudaMemcpyAsync(dp, td, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     td_to_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dp, n, h->cfg.alpha, h->cfg.eps);
     CK(cudaGetLastError());
-    tree_update_kernel<<<1, 1024, 0, h->stream>>>(h->tree, h->P, di, dp, (int)n, 1, h->st, 0, 1.0, 1.0, 0);
+    tree_update_kernel<<<1, 1024, 0, h->stream>>>(h->tree, h->P, di, dp, (int)n, 1, h->st, 0, 1.0, 1.0, 0, nullptr);
     CK(cudaGetLastError());
     check_dev_errors(h);
   });
@@ -963,8 +978,8 @@ int dqn_sample_indices(dqn_engine_t* h, uint64_t call, int64_t* idx_out) {
   return guard(h, [&] {
     if (h->curr_size < h->B) fail(DQN_ERR_STATE, "replay holds %lld transitions, batch_size is %d (PER:83)", h->curr_size, h->B);
     ensure_stage(h, h->B * 8);
-    int HT = 1; while (HT < 4 * h->B) HT <<= 1;
-    sample_kernel<<<1, (h->B + 31) / 32 * 32, 2 * HT * sizeof(int), h->stream>>>(h->tree, h->P, h->B, h->cfg.seed, h->st, 1, call, (long long*)h->stage);
+    sample_kernel<<<1, (h->B + 31) / 32 * 32, sample_smem(h->B), h->stream>>>(h->tree, h->P, h->B, h->cfg.seed, h->st, 1, call, (long long*)h->stage,
+                                                                               nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr);
     CK(cudaGetLastError());
     d2h(h, (long long*)idx_out, (const long long*)h->stage, h->B);
     check_dev_errors(h);

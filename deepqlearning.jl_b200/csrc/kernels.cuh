@@ -52,11 +52,13 @@ __device__ __forceinline__ float pow_f32(float x, float y) { return (float)pow((
 // ------------------------------------------------------------------------------------------------
 // Sum-tree.  tree[1] root, children of k at 2k, 2k+1, leaves at P + i.  Internal nodes are always
 // recomputed as fl(left + right) - the tree is a pure function of its leaves (bit-exact vs oracle/sumtree.py).
-__device__ __forceinline__ int tree_descend(const float* __restrict__ tree, int P, float u) {
-  float v = __fmul_rn(u, tree[1]);
+constexpr int TREE_TOP = 1024;            // nodes 1..1023 (the first 10 levels) are staged in shared memory by the sampler
+__device__ __forceinline__ int tree_descend(const float* __restrict__ tree, const float* __restrict__ top, int P, float u) {
+  float v = __fmul_rn(u, top ? top[1] : tree[1]);
   int node = 1;
   while (node < P) {
-    const float2 ch = *reinterpret_cast<const float2*>(tree + 2 * node);
+    const float2 ch = (top && 2 * node + 1 < TREE_TOP) ? *reinterpret_cast<const float2*>(top + 2 * node)
+                                                        : *reinterpret_cast<const float2*>(tree + 2 * node);
     const bool left = (v < ch.x) || (ch.y == 0.f);
     if (!left) v = __fsub_rn(v, ch.x);
     node = 2 * node + (left ? 0 : 1);
@@ -66,17 +68,24 @@ __device__ __forceinline__ int tree_descend(const float* __restrict__ tree, int 
 
 // B draws without replacement (StatsBase.sample(...; replace=false), PER:85): slot j redraws while a slot
 // i < j holds the same leaf; one check per round over a shared hash table.  One CTA, B <= 1024 threads.
+// The same CTA then gathers the per-sample metadata and importance weights (get_batch, PER:94-102).
 constexpr int SAMPLE_MAX_ROUNDS = 64;
 __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint64_t seed, DevState* st,
-                              int use_call, uint64_t call_in, long long* __restrict__ idx_out) {
+                              int use_call, uint64_t call_in, long long* __restrict__ idx_out,
+                              const int* __restrict__ act, const float* __restrict__ rew, const uint8_t* __restrict__ done, float beta,
+                              int* __restrict__ a_b, float* __restrict__ r_b, float* __restrict__ d_b, float* __restrict__ w_b) {
   extern __shared__ int sh[];
-  int HT = 1; while (HT < 4 * B) HT <<= 1;      // hash table: HT keys + HT owners (dynamic smem = 2*HT ints)
+  int HT = 1; while (HT < 4 * B) HT <<= 1;      // hash table: HT keys + HT owners, then the staged tree top
   int* keys = sh;
   int* owner = sh + HT;
+  float* top = reinterpret_cast<float*>(sh + 2 * HT);
+  const int ntop = min(TREE_TOP, 2 * P);
+  for (int t = threadIdx.x; t < ntop; t += blockDim.x) top[t] = tree[t];
+  __syncthreads();
   const int j = threadIdx.x;
   const uint64_t call = use_call ? call_in : st->sample_call;
   uint32_t attempt = 0;
-  int leaf = (j < B) ? tree_descend(tree, P, philox_uniform(seed, call, j, 0)) : -1;
+  int leaf = (j < B) ? tree_descend(tree, top, P, philox_uniform(seed, call, j, 0)) : -1;
   int round = 0;
   for (; round < SAMPLE_MAX_ROUNDS; ++round) {
     for (int t = threadIdx.x; t < HT; t += blockDim.x) { keys[t] = -1; owner[t] = 0x7fffffff; }
@@ -95,9 +104,16 @@ __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint
     const int rej = (j < B) && (owner[slot] < j);
     const int any = __syncthreads_or(rej);
     if (!any) break;
-    if (rej) { ++attempt; leaf = tree_descend(tree, P, philox_uniform(seed, call, j, attempt)); }
+    if (rej) { ++attempt; leaf = tree_descend(tree, top, P, philox_uniform(seed, call, j, attempt)); }
   }
-  if (j < B) idx_out[j] = leaf;
+  if (j < B) {
+    idx_out[j] = leaf;
+    if (a_b) {
+      a_b[j] = act[leaf]; r_b[j] = rew[leaf]; d_b[j] = done[leaf] ? 1.f : 0.f;
+      const float p = __fdiv_rn(tree[P + leaf], top[1]);
+      w_b[j] = pow_f32(__fmul_rn((float)st->curr_size, p), -beta);
+    }
+  }
   if (j == 0 && round >= SAMPLE_MAX_ROUNDS) atomicOr(&st->error, 1);
 }
 
@@ -177,7 +193,7 @@ __global__ void split_params_kernel(const float* __restrict__ w, float* __restri
 // sampling-call counter) so that a captured graph advances its own state.
 __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long long* __restrict__ idx, const float* __restrict__ newp,
                                    int n, int write_leaves, DevState* st, int end_of_step, double beta1, double beta2,
-                                   int advance_sampler) {
+                                   int advance_sampler, float* __restrict__ publish) {
   const int j = threadIdx.x;
   if (write_leaves) {
     for (int t = j; t < n; t += blockDim.x) {
@@ -199,6 +215,9 @@ __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long l
   if (end_of_step && j == 0) {
     st->b1p *= beta1; st->b2p *= beta2;
     if (advance_sampler) st->sample_call += 1;
+    if (publish) {      // scalars of the finished step -> mapped pinned host words (loss, grad_norm, error flags)
+      publish[0] = st->loss; publish[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(publish)[2] = st->error;
+    }
   }
 }
 
@@ -392,6 +411,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
                                                     float* __restrict__ w_hi, long long lo_delta, long long s0, long long s1, float scale) {
   const double c1 = 1.0 - st->b1p, c2 = 1.0 - st->b2p;
   const double omb1 = 1.0 - beta1, omb2 = 1.0 - beta2;
+  // m/c1 and v/c2 as multiplications by the reciprocals: <= 1 ulp(double) away from the reference's divisions, invisible once
+  // the update is rounded to Float32 (the parity test allows 2 ulp of the parameter); one fp64 division per element remains
+  const double rc1 = 1.0 / c1, rc2 = 1.0 / c2;
   float gmax = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 W = reinterpret_cast<float4*>(w)[i], Mv = reinterpret_cast<float4*>(m)[i], Vv = reinterpret_cast<float4*>(v)[i];
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
       // explicit _rn intrinsics: no FMA contraction, every Float64 op rounds separately as the reference's broadcast does
       const float mt = (float)__dadd_rn(__dmul_rn(beta1, (double)mp[k]), __dmul_rn(omb1, gd));
       const float vt = (float)__dadd_rn(__dmul_rn(beta2, (double)vp[k]), __dmul_rn(__dmul_rn(omb2, gd), gd));
-      const float d = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, c1), __dadd_rn(__dsqrt_rn(__ddiv_rn((double)vt, c2)), eps)), eta);
+      const float d = (float)__dmul_rn(__ddiv_rn(__dmul_rn((double)mt, rc1), __dadd_rn(__dsqrt_rn(__dmul_rn((double)vt, rc2)), eps)), eta);
       mp[k] = mt; vp[k] = vt; wp[k] = wp[k] - d;
     }
     reinterpret_cast<float4*>(w)[i] = W; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
