@@ -319,19 +319,35 @@ void backward(E* e, bool conc) {
       for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * B * dg[t].N * dg[t].K; by += 4.0 * ((double)B * dg[t].K + (double)dg[t].N * dg[t].K + 2.0 * B * dg[t].N); }
       if (!tc_dense_dgrad2(e, nm, dg, e->ntow, fl, by)) launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
     } else if (trunk) {
-      for (int t = 0; t < e->ntow; ++t) {       // towers accumulate into the trunk gradient in a fixed order
-        const Mat& w = e->tow[t][0];
-        DenseDgradOp op{};
-        op.D = e->tow_delta[t][0]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = dfeat; op.ldx = w.K;
-        op.Y = e->on.conv_out.back(); op.ldy = w.K; op.act = e->convs.back().w.act; op.accumulate = t > 0; op.apply_act = (t == e->ntow - 1);
-        op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
-        if (e->arena) {
-          op.Ds = (e->depth > 1 && w.N % 4 == 0) ? e->tow_delta_s[t][0] : nullptr; op.Ws = e->w_on_s + w.off;
-          op.dXs = (t == e->ntow - 1 && w.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
-        }
-        snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
-        const double fl = 2.0 * B * op.N * op.K, by = 4.0 * ((double)B * op.K + (double)op.N * op.K + 2.0 * B * op.N);
+      // gradient into the trunk: both towers in one contraction (K = N_val + N_adv) - no second launch, no read-modify-write
+      const Mat& w0 = e->tow[0][0]; const Mat& w1 = e->tow[e->ntow - 1][0];
+      DenseDgradOp op{};
+      op.D = e->tow_delta[0][0]; op.ldd = w0.N; op.W = e->theta + w0.off; op.dX = dfeat; op.ldx = w0.K;
+      op.Y = e->on.conv_out.back(); op.ldy = w0.K; op.act = e->convs.back().w.act; op.accumulate = 0; op.apply_act = 1;
+      op.M = B; op.N = w0.K; op.K = w0.N; op.K1 = 0;
+      if (e->ntow == 2) { op.K1 = w0.N; op.K = w0.N + w1.N; op.D2 = e->tow_delta[1][0]; op.ldd2 = w1.N; op.W2 = e->theta + w1.off; }
+      op.vecA = (w0.N % 4 == 0) && (w1.N % 4 == 0); op.vecB = op.vecA;
+      if (e->arena) {
+        const bool ok = e->depth > 1 && w0.N % 4 == 0 && w1.N % 4 == 0;
+        op.Ds = ok ? e->tow_delta_s[0][0] : nullptr; op.Ws = e->w_on_s + w0.off;
+        if (e->ntow == 2) { op.Ds2 = ok ? e->tow_delta_s[1][0] : nullptr; op.Ws2 = e->w_on_s + w1.off; }
+        op.dXs = (w0.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
+      }
+      snprintf(nm, sizeof nm, "dense1_dgrad");
+      const double fl = 2.0 * B * op.N * op.K, by = 4.0 * ((double)B * op.K + (double)op.N * op.K + 2.0 * B * op.N);
+      if (e->ntow == 1 || w0.N % 4 == 0) {
         if (!tc_dense_dgrad(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
+      } else {                                 // tower widths not 16-byte granular: one launch per tower, accumulating in a fixed order
+        for (int t = 0; t < e->ntow; ++t) {
+          const Mat& w = e->tow[t][0];
+          DenseDgradOp o2{};
+          o2.D = e->tow_delta[t][0]; o2.ldd = w.N; o2.W = e->theta + w.off; o2.dX = dfeat; o2.ldx = w.K;
+          o2.Y = e->on.conv_out.back(); o2.ldy = w.K; o2.act = e->convs.back().w.act; o2.accumulate = t > 0; o2.apply_act = (t == e->ntow - 1);
+          o2.M = B; o2.N = w.K; o2.K = w.N; o2.vecA = o2.vecB = 0;
+          if (e->arena) { o2.dXs = (t == e->ntow - 1 && w.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; o2.lo_delta = e->lo_delta; }
+          snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
+          launch_igemm(e, nm, o2, o2, 1, false, 2.0 * B * o2.N * o2.K, 4.0 * ((double)B * o2.K + (double)o2.N * o2.K + 2.0 * B * o2.N));
+        }
       }
     }
   }

@@ -212,19 +212,31 @@ struct DenseDgradOp {
   int M, N, K;
   int vecA, vecB;
   const float* Ds; const float* Ws; float* dXs; long long lo_delta; int a_single;
-  DQN_HD bool tc_ready() const { return Ds && Ws && (K % 4 == 0) && (ldd % 4 == 0); }
-  DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int, int k) const { return (c.valid && k < K) ? Ds + c.base + k : nullptr; }
-  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)n * K + k : nullptr; }
+  // optional second K segment (the other dueling tower): k in [K1, K) reads D2 / W2, so both towers' contributions to the
+  // trunk gradient are ONE contraction instead of two launches with a read-modify-write in between.  K1 == 0: single segment.
+  int K1; const float* D2; long long ldd2; const float* W2; const float* Ds2; const float* Ws2;
+  DQN_HD int seg0() const { return K1 > 0 ? K1 : K; }
+  DQN_HD bool tc_ready() const { return Ds && Ws && (K % 4 == 0) && (ldd % 4 == 0) && (K1 == 0 || (Ds2 && Ws2 && K1 % 4 == 0 && ldd2 % 4 == 0)); }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int m, int k) const {
+    if (!c.valid || k >= K) return nullptr;
+    return k < seg0() ? Ds + c.base + k : Ds2 + (long long)m * ldd2 + (k - K1);
+  }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const {
+    if (k >= K || n >= N) return nullptr;
+    return k < seg0() ? Ws + (long long)n * seg0() + k : Ws2 + (long long)n * (K - K1) + (k - K1);
+  }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
-  DQN_HD float4 loadA(const ACtx& c, const KCtx&, int, int k) const {
+  DQN_HD float4 loadA(const ACtx& c, const KCtx&, int m, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
-    return load4_f32(D + c.base + k, K - k, vecA);
+    if (k < seg0()) return load4_f32(D + c.base + k, seg0() - k, vecA);
+    return load4_f32(D2 + (long long)m * ldd2 + (k - K1), K - k, vecA);
   }
   DQN_HD float4 loadB(const KCtx&, int k, int n) const {      // 4 consecutive k at column n
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
-    return load4_f32(W + (long long)n * K + k, K - k, vecB);
+    if (k < seg0()) return load4_f32(W + (long long)n * seg0() + k, seg0() - k, vecB);
+    return load4_f32(W2 + (long long)n * (K - K1) + (k - K1), K - k, vecB);
   }
   DQN_HD void store(int m, int n, float v) const {
     long long o = (long long)m * ldx + n;

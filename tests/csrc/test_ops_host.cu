@@ -50,6 +50,19 @@ static void test_dense(int M, int K, int N, int act, bool u8) {
   cmp("dense_dgrad", dX, RX);
 }
 
+static void test_dgrad_two_towers(int M, int Kin, int N0, int N1) {
+  std::vector<float> D0(M * N0), D1(M * N1), W0((Kin + 1) * N0), W1((Kin + 1) * N1), Y(M * Kin), dX(M * Kin, 0.f), R(M * Kin);
+  for (auto& v : D0) v = rnd(); for (auto& v : D1) v = rnd(); for (auto& v : W0) v = rnd(); for (auto& v : W1) v = rnd(); for (auto& v : Y) v = rnd();
+  DenseDgradOp op{}; op.D = D0.data(); op.ldd = N0; op.W = W0.data(); op.dX = dX.data(); op.ldx = Kin; op.Y = Y.data(); op.ldy = Kin; op.act = ACT_RELU; op.apply_act = 1;
+  op.M = M; op.N = Kin; op.K = N0 + N1; op.K1 = N0; op.D2 = D1.data(); op.ldd2 = N1; op.W2 = W1.data(); op.vecA = op.vecB = (N0 % 4 == 0 && N1 % 4 == 0);
+  igemm_host(op);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < Kin; ++k) {
+    double s = 0; for (int n = 0; n < N0; ++n) s += (double)D0[m * N0 + n] * W0[k * N0 + n]; for (int n = 0; n < N1; ++n) s += (double)D1[m * N1 + n] * W1[k * N1 + n];
+    R[m * Kin + k] = (float)(s * act_deriv(Y[m * Kin + k], ACT_RELU));
+  }
+  cmp("dense_dgrad_2towers", dX, R);
+}
+
 static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int KW, int S, bool u8) {
   ConvGeom g{}; g.IH = IH; g.IW = IW; g.Cin = Cin; g.OH = (IH - KH) / S + 1; g.OW = (IW - KW) / S + 1; g.Cout = Cout; g.KH = KH; g.KW = KW; g.S = S; g.init();
   const int K = KH * KW * Cin, P = nimg * g.OH * g.OW;
@@ -118,6 +131,8 @@ static void test_fastdiv_and_u8() {
 
 int main() {
   test_fastdiv_and_u8();
+  test_dgrad_two_towers(9, 20, 8, 12);
+  test_dgrad_two_towers(5, 7, 4, 8);
   test_dense(7, 12, 8, ACT_RELU, false);
   test_dense(5, 2, 32, ACT_IDENTITY, false);     // README net first layer
   test_dense(9, 32, 1, ACT_IDENTITY, false);     // value head
