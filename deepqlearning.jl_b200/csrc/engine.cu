@@ -79,9 +79,6 @@ constexpr int MAXD = DQN_MAX_LAYERS;
 struct ActBufs {
   std::vector<float*> conv_out;
   float* tow_out[2][MAXD] = {};
-  // hi planes of the same tensors in the tensor-core operand arena (empty / null in DQN_MATH_FP32)
-  std::vector<float*> conv_out_s;
-  float* tow_out_s[2][MAXD] = {};
 };
 
 }  // namespace
@@ -135,9 +132,10 @@ struct dqn_engine {
   int profiling = 0; std::vector<ProfRec> prof; std::vector<cudaEvent_t> ev_pool;
   uint32_t* flush_buf = nullptr; long long flush_n = 0;
   bool capturing = false;
-  // tensor-core operand arena: hi planes at arena + offset, lo planes lo_delta floats later
+  // tensor-core side buffers: the sampled byte batch as fp32 (raw values k, exact in TF32), the first conv layer's weights
+  // pre-scaled by 1/255 for both networks, and the {1,0,0,0} chunk that realises the bias column of [x 1]
   float* arena = nullptr; long long lo_delta = 0;
-  float* xb_f = nullptr; std::vector<float*> conv_delta_s; float* tow_delta_s[2][MAXD] = {};
+  float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
   int tc_deep = -1;
@@ -228,11 +226,12 @@ void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everyt
 }
 
 // ---- network schedule ---------------------------------------------------------------------------
-// Xs / Wsplit: hi planes of the input batch and of this parameter vector (null => fp32 CUDA-core kernels only)
-void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag, const float* Xs, const float* Wsplit) {
+// Xs: the input batch as fp32 for the tensor-core path (null => fp32 CUDA-core kernels only); w1s: the first conv layer's
+// weights pre-scaled by 1/255 when Xs holds raw byte values
+void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag, const float* Xs, const float* w1s) {
   const void* cur = X; int cur_u8 = x_u8;
   const float* cur_s = Xs;
-  const bool tcm = Xs && Wsplit;
+  const bool tcm = Xs != nullptr;
   char nm[64];
   for (size_t l = 0; l < e->convs.size(); ++l) {
     const ConvL& c = e->convs[l];
@@ -240,12 +239,12 @@ void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& b
     op.X = cur; op.x_u8 = cur_u8; op.W = P + c.w.off; op.Y = bufs.conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
     op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
     op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
-    if (tcm) { op.Xs = cur_s; op.Ws = Wsplit + c.w.off; op.Ys = (c.g.Cout % 4 == 0) ? bufs.conv_out_s[l] : nullptr; op.lo_delta = e->lo_delta; op.a_single = (l == 0 && cur_u8); }
+    if (tcm) { op.Xs = cur_s; op.Ws = (l == 0 && cur_u8) ? w1s : P + c.w.off; op.a_single = (l == 0 && cur_u8); }
     snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, tag);
     const double fl = 2.0 * op.M * op.N * op.K;
     const double by = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8 ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
     if (!tc_conv_fwd(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
-    cur = bufs.conv_out[l]; cur_u8 = 0; cur_s = op.Ys;
+    cur = bufs.conv_out[l]; cur_u8 = 0; cur_s = bufs.conv_out[l];
   }
   for (int l = 0; l < e->depth; ++l) {
     DenseFwdOp ops[2];
@@ -255,10 +254,7 @@ void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& b
       op.X = l == 0 ? cur : (const void*)bufs.tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8 : 0;
       op.W = P + w.off; op.C = bufs.tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
       op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
-      if (tcm) {
-        op.Xs = l == 0 ? ((cur_u8 && e->convs.empty()) ? nullptr : cur_s) : ((e->tow[t][l - 1].N % 4 == 0) ? bufs.tow_out_s[t][l - 1] : nullptr);
-        op.Ws = Wsplit + w.off; op.Cs = (w.N % 4 == 0) ? bufs.tow_out_s[t][l] : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
-      }
+      if (tcm) { op.Xs = l == 0 ? (cur_u8 ? nullptr : cur_s) : bufs.tow_out[t][l - 1]; op.Ws = P + w.off; op.a_single = 0; }
     }
     if (e->ntow == 1) ops[1] = ops[0];
     snprintf(nm, sizeof nm, "dense%d_fwd_%s", l + 1, tag);
@@ -285,9 +281,8 @@ void backward(E* e, bool conc) {
       op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
       if (e->arena) {
         const bool raw_bytes = (l == 0 && !trunk && e->elem_bytes == 1);
-        op.Xs = l == 0 ? (trunk ? e->on.conv_out_s.back() : (raw_bytes ? nullptr : e->xb_f)) : ((e->tow[t][l - 1].N % 4 == 0) ? e->on.tow_out_s[t][l - 1] : nullptr);
-        op.Ds = (l < e->depth - 1 && w.N % 4 == 0) ? e->tow_delta_s[t][l] : nullptr;      // the head kernel writes the last layer's delta unsplit
-        op.ones = e->ones; op.lo_delta = e->lo_delta; op.a_single = 0; op.out_scale = 0.f;
+        op.Xs = l == 0 ? (trunk ? e->on.conv_out.back() : (raw_bytes ? nullptr : (const float*)e->xb)) : e->on.tow_out[t][l - 1];
+        op.Ds = e->tow_delta[t][l]; op.ones = e->ones; op.a_single = 0; op.out_scale = 0.f;
       }
     }
     if (e->ntow == 1) wg[1] = wg[0];
@@ -308,10 +303,7 @@ void backward(E* e, bool conc) {
         op.D = e->tow_delta[t][l]; op.ldd = w.N; op.W = e->theta + w.off; op.dX = e->tow_delta[t][l - 1]; op.ldx = w.K;
         op.Y = e->on.tow_out[t][l - 1]; op.ldy = w.K; op.act = wp.act; op.accumulate = 0; op.apply_act = 1;
         op.M = B; op.N = w.K; op.K = w.N; op.vecA = (w.N % 4 == 0); op.vecB = (w.N % 4 == 0);
-        if (e->arena) {
-          op.Ds = (l < e->depth - 1 && w.N % 4 == 0) ? e->tow_delta_s[t][l] : nullptr; op.Ws = e->w_on_s + w.off;
-          op.dXs = (w.K % 4 == 0) ? e->tow_delta_s[t][l - 1] : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
-        }
+        if (e->arena) { op.Ds = e->tow_delta[t][l]; op.Ws = e->theta + w.off; op.a_single = 0; }
       }
       if (e->ntow == 1) dg[1] = dg[0];
       snprintf(nm, sizeof nm, "dense%d_dgrad", l + 1);
@@ -328,10 +320,8 @@ void backward(E* e, bool conc) {
       if (e->ntow == 2) { op.K1 = w0.N; op.K = w0.N + w1.N; op.D2 = e->tow_delta[1][0]; op.ldd2 = w1.N; op.W2 = e->theta + w1.off; }
       op.vecA = (w0.N % 4 == 0) && (w1.N % 4 == 0); op.vecB = op.vecA;
       if (e->arena) {
-        const bool ok = e->depth > 1 && w0.N % 4 == 0 && w1.N % 4 == 0;
-        op.Ds = ok ? e->tow_delta_s[0][0] : nullptr; op.Ws = e->w_on_s + w0.off;
-        if (e->ntow == 2) { op.Ds2 = ok ? e->tow_delta_s[1][0] : nullptr; op.Ws2 = e->w_on_s + w1.off; }
-        op.dXs = (w0.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; op.lo_delta = e->lo_delta; op.a_single = 0;
+        op.Ds = e->tow_delta[0][0]; op.Ws = e->theta + w0.off; op.a_single = 0;
+        if (e->ntow == 2) { op.Ds2 = e->tow_delta[1][0]; op.Ws2 = e->theta + w1.off; }
       }
       snprintf(nm, sizeof nm, "dense1_dgrad");
       const double fl = 2.0 * B * op.N * op.K, by = 4.0 * ((double)B * op.K + (double)op.N * op.K + 2.0 * B * op.N);
@@ -344,7 +334,6 @@ void backward(E* e, bool conc) {
           o2.D = e->tow_delta[t][0]; o2.ldd = w.N; o2.W = e->theta + w.off; o2.dX = dfeat; o2.ldx = w.K;
           o2.Y = e->on.conv_out.back(); o2.ldy = w.K; o2.act = e->convs.back().w.act; o2.accumulate = t > 0; o2.apply_act = (t == e->ntow - 1);
           o2.M = B; o2.N = w.K; o2.K = w.N; o2.vecA = o2.vecB = 0;
-          if (e->arena) { o2.dXs = (t == e->ntow - 1 && w.K % 4 == 0) ? e->conv_delta_s.back() : nullptr; o2.lo_delta = e->lo_delta; }
           snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
           launch_igemm(e, nm, o2, o2, 1, false, 2.0 * B * o2.N * o2.K, 4.0 * ((double)B * o2.K + (double)o2.N * o2.K + 2.0 * B * o2.N));
         }
@@ -363,8 +352,8 @@ void backward(E* e, bool conc) {
     wg.D = e->conv_delta[l]; wg.dW = e->grad + c.w.off; wg.nimg = B; wg.g = c.g;
     wg.M = c.w.K + 1; wg.N = c.g.Cout; wg.K = B * c.g.OH * c.g.OW; wg.vecA = (c.g.Cin % 4 == 0); wg.vecB = (c.g.Cout % 4 == 0);
     if (e->arena) {
-      wg.Xs = l == 0 ? e->xb_f : e->on.conv_out_s[l - 1]; wg.Ds = e->conv_delta_s[l]; wg.ones = e->ones; wg.lo_delta = e->lo_delta;
       wg.a_single = (l == 0 && e->elem_bytes == 1);
+      wg.Xs = l == 0 ? (wg.a_single ? e->xb_f : (const float*)e->xb) : e->on.conv_out[l - 1]; wg.Ds = e->conv_delta[l]; wg.ones = e->ones;
     }
     snprintf(nm, sizeof nm, "conv%d_wgrad", l + 1);
     double fl = 2.0 * wg.M * wg.N * wg.K;
@@ -381,7 +370,7 @@ void backward(E* e, bool conc) {
       dg.D = e->conv_delta[l]; dg.W = e->theta + c.w.off; dg.dX = e->conv_delta[l - 1]; dg.Yprev = e->on.conv_out[l - 1];
       dg.act = e->convs[l - 1].w.act; dg.apply_act = 1; dg.nimg = B; dg.g = c.g;
       dg.vecA = (c.g.Cout % 4 == 0); dg.vecB = (c.g.Cout % 4 == 0);
-      if (e->arena) { dg.Ds = e->conv_delta_s[l]; dg.Ws = e->w_on_s + c.w.off; dg.dXs = (c.g.Cin % 4 == 0) ? e->conv_delta_s[l - 1] : nullptr; dg.lo_delta = e->lo_delta; dg.a_single = 0; }
+      if (e->arena) { dg.Ds = e->conv_delta[l]; dg.Ws = e->theta + c.w.off; dg.a_single = 0; }
       snprintf(nm, sizeof nm, "conv%d_dgrad", l + 1);
       fl = 2.0 * B * c.g.OH * c.g.OW * c.g.Cout * c.w.K;
       by = 4.0 * ((double)B * c.g.OH * c.g.OW * c.g.Cout + (double)c.w.K * c.g.Cout + 2.0 * B * c.g.IH * c.g.IW * c.g.Cin);
@@ -395,7 +384,7 @@ void enqueue_gather(E* e) {       // observation rows of the sampled transitions
   const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
   dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
   Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
-  gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0) ? e->xb_f : nullptr, e->lo_delta, e->elem_bytes == 1);
+  gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0 && e->elem_bytes == 1) ? e->xb_f : nullptr, 0, e->elem_bytes == 1);
   CK(cudaGetLastError());
 }
 void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for indices given by the caller
@@ -420,7 +409,7 @@ void enqueue_step(E* e, bool sample) {
     }
     enqueue_gather(e);
   } else enqueue_batch_prep(e);
-  const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? e->xb_f : nullptr;
+  const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? (e->elem_bytes == 1 ? e->xb_f : (const float*)e->xb) : nullptr;
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
   e->ev_next = 0;
   if (conc) order_after(e, e->stream2, e->stream);            // fork: the gathered batch is ready
@@ -462,7 +451,7 @@ void enqueue_step(E* e, bool sample) {
     Scope sc(e, "adam", 0, 7.0 * e->nint * 4);
     adam_kernel<<<2 * e->nsm * 2, 256, 0, e->stream>>>(e->theta, e->adam_m, e->adam_v, e->grad, e->nint / 4,
                                                        (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st,
-                                                       e->w_on_s, e->lo_delta, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
+                                                       e->w_on_s, 0, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
     CK(cudaGetLastError());
   }
   {

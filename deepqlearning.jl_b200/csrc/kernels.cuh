@@ -135,8 +135,8 @@ __global__ void batch_meta_kernel(const long long* __restrict__ idx, int B, cons
 
 // Observation gather: rows idx[j] of the s / s' stores -> contiguous batch (s rows 0..B-1, s' rows B..2B-1).
 // 16-byte loads, 4 in flight per thread; grid = (chunks, 2B).
-// Tensor-core path: the same pass also writes the batch as fp32 operand planes - raw byte values k as floats (exact in
-// TF32, single plane; the 1/255 is folded into the first layer's weight planes) or the hi/lo split of fp32 observations.
+// Tensor-core path with byte observations: the same pass also writes the batch as fp32 raw values k (exact in TF32, so this
+// operand needs no lo term; the 1/255 is folded into a scaled copy of the first layer's weights).
 __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ store_s, const uint8_t* __restrict__ store_sp,
                                                            const long long* __restrict__ idx, int B, long long row_bytes,
                                                            uint8_t* __restrict__ out, float* __restrict__ out_f, long long lo_delta, int obs_u8) {
@@ -164,9 +164,6 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<float4*>(o + 4 * q) = make4((float)(w[q] & 255u), (float)((w[q] >> 8) & 255u), (float)((w[q] >> 16) & 255u), (float)(w[q] >> 24));
-        } else {               // 4 floats -> hi/lo planes
-          float* o = out_f + (long long)row * (row_bytes >> 2) + v * 4;
-          store_split4(o, lo_delta, make4(__int_as_float(tmp[u].x), __int_as_float(tmp[u].y), __int_as_float(tmp[u].z), __int_as_float(tmp[u].w)));
         }
       }
     }
@@ -176,15 +173,12 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
   }
 }
 
-// theta -> operand planes (hi, lo) of the tensor-core path; [s0, s1) is the first layer's weight block when the
-// observations are raw bytes (scaled by 1/255 here instead of in the operand loader)
-__global__ void split_params_kernel(const float* __restrict__ w, float* __restrict__ hi, long long lo_delta, long long n4,
-                                    long long s0, long long s1, float scale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(w)[i];
-    const long long e = i * 4;
-    if (e >= s0 && e < s1) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
-    store_split4(hi + e, lo_delta, v);
+// [s0, s1) of theta is the first conv layer's weight block; when the observations are raw bytes the tensor-core path reads
+// a copy scaled by 1/255 (the byte values k are exact TF32 operands, Float32(k)/255f0 is not)
+__global__ void scale_block_kernel(const float* __restrict__ w, float* __restrict__ out, long long s0, long long s1, float scale) {
+  for (long long e = s0 + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; e < s1; e += (long long)gridDim.x * blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(w + e);
+    *reinterpret_cast<float4*>(out + (e - s0)) = make4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
   }
 }
 
@@ -431,11 +425,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
       mp[k] = mt; vp[k] = vt; wp[k] = wp[k] - d;
     }
     reinterpret_cast<float4*>(w)[i] = W; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
-    if (w_hi) {                                   // refresh the tensor-core operand planes of the online weights in the same pass
-      const long long e = i * 4;
-      if (e >= s0 && e < s1) { W.x *= scale; W.y *= scale; W.z *= scale; W.w *= scale; }
-      store_split4(w_hi + e, lo_delta, W);
-    }
+    const long long e = i * 4;
+    if (w_hi && e >= s0 && e < s1)                // first conv layer on raw bytes: refresh its 1/255-scaled copy in the same pass
+      *reinterpret_cast<float4*>(w_hi + (e - s0)) = make4(W.x * scale, W.y * scale, W.z * scale, W.w * scale);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));

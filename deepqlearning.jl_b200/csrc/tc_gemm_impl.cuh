@@ -3,20 +3,19 @@
 // Same operand functors as the fp32 path (igemm.cuh), different engine: a warp-specialised CTA computes one
 // 128 x BN output tile with the 5th-generation tensor cores.
 //
-// Operands arrive PRE-SPLIT: every fp32 tensor that feeds a contraction is kept in HBM as two TF32-exact planes
-// x = hi + lo (cvt.rna, written by the epilogue of the kernel that produced the tensor, by the gather for the sampled
-// batch and by the Adam pass for the weights; both planes of a tensor sit lo_delta floats apart in one arena).  The
-// producers therefore never touch data with the ALU:
+// 3xTF32: every fp32 operand value is used as two TF32-exact terms x = hi + lo (cvt.rna both, so the split is unbiased).
+// The split happens in SHARED memory: the producers cp.async the plain fp32 tensors (16-byte chunks; im2col rows, dgrad
+// parity classes and the [x 1] bias column are just different chunk addresses - op.ptrA / op.ptrB, nullptr = zero fill)
+// into the hi-plane slots of the UMMA canonical layout, then split their own chunks in place (hi back to the slot, lo to
+// the lo plane).  Global->shared traffic - the measured bottleneck of this kernel family on B200, ~3.6 TB/s chip-wide for
+// 16-byte cp.async - is therefore one pass over the fp32 data; an earlier version that kept hi/lo planes in HBM moved 2x.
 //
-//   warps 0-7 (256 threads)  cp.async 16-byte chunks global -> shared straight into the UMMA canonical no-swizzle layout,
-//                            K-major (8-row x 16-byte core matrices, chunk = 4 consecutive k) or MN-major (chunk = 4
-//                            consecutive rows) depending on which way the source tensor is contiguous; im2col rows,
-//                            dgrad parity classes and the [x 1] bias column are just different chunk addresses
-//                            (op.ptrA / op.ptrB, nullptr = zero fill).  Completion is tracked by the stage's mbarrier
-//                            (cp.async.mbarrier.arrive).  After the main loop the same warps run the epilogue.
-//   warp 8                   one elected lane issues tcgen05.mma.kind::tf32, three per 8-wide k step:
-//                            D += A_lo B_hi + A_hi B_lo + A_hi B_hi   (error-compensated "3xTF32"; the dropped
-//                            A_lo B_lo term is O(2^-22)); two when A is single-plane (raw byte values are TF32-exact).
+//   warps 0-7 (256 threads)  producers (cp.async + in-place split) and, after the main loop, the epilogue
+//                            (tcgen05.ld -> bias/activation or act' -> 16-byte stores); K-major operands use the no-swizzle
+//                            layout (8-row x 16-byte core matrices), MN-major operands SWIZZLE_128B_BASE32B.
+//   warps 8-10               one elected lane each issues tcgen05.mma.kind::tf32 for ONE of the three products per 8-wide k step
+//                            (A_hi B_hi | A_lo B_hi | A_hi B_lo; the dropped A_lo B_lo term is O(2^-22)); the A_lo stream idles
+//                            when A is single-plane (raw byte values are TF32-exact).
 //   accumulators             fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
 //                            1 ulp per MMA), so the correction products get their own accumulator (SEP) and the main
 //                            product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
@@ -29,10 +28,19 @@
 
 namespace tc {
 
+#ifdef TC_TRACE
+__device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (producer warp 0 and the MMA warp): tuning aid of the selftest
+#define TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) tc_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
 constexpr int PROD = 256;        // producer / epilogue threads (8 warps: short per-thread address chains, more loads in flight)
-constexpr int THREADS = 288;     // + 1 MMA warp
+constexpr int NMMA = 3;           // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
+                                  // a single thread issues ~70-cycle tcgen05.mma, three streams keep the tensor core fed
+constexpr int THREADS = PROD + 32 * NMMA;
 
 // shared-memory tile of one operand plane for one stage
 template <int ROWS, bool MN> struct Tile;
@@ -87,6 +95,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -126,8 +139,13 @@ __device__ __forceinline__ float4 permute_chunk(float4 v, int c) {
   if (c & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
   return v;
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -152,7 +170,7 @@ __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int BN, int R, bool SEP, bool DEEP, class Op>
-__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>::CTAS == 2 && BN * (R + (SEP ? 1 : 0)) <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>::CTAS == 2 && BN * (R + 2) <= 256) ? 2 : 1)
 tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
   using L = Lay<BN, A_MN, B_MN, DEEP>;
@@ -179,13 +197,14 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   const bool a_lo = !op.a_single;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NACC = R + (SEP ? 1 : 0);
+  constexpr int NACC = R + 2;                                  // R interleaved main accumulators + one per correction product
+  static_assert(SEP, "corrections always have their own accumulators");
   constexpr int TCOLS = pow2_cols(BN * NACC);
   static_assert(BN * NACC <= 512, "TMEM columns");
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, PROD); mbar_init(bars + 8 * (STAGES + s), 1); }
-    mbar_init(bar_done, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, PROD); mbar_init(bars + 8 * (STAGES + s), NMMA); }
+    mbar_init(bar_done, NMMA);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == PROD / 32) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
@@ -198,7 +217,6 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
     // ================= producers: chunk addresses + cp.async only =================
     constexpr int A_PER = BM * (BK / 4) / PROD;                // 4 chunks of A per thread per stage
     constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/32 chunks of B
-    const long long lo_delta = op.lo_delta;
     ACtx actx[A_MN ? 1 : A_PER];
     uint32_t a_off[A_PER]; int a_kk[A_PER];
     if (A_MN) {                                                // lane = 16-byte chunk along the rows, k rows spread over warps / i
@@ -224,66 +242,62 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
+    // Per stage: (1) cp.async the RAW fp32 chunks of stage `it` into the hi-plane slots, (2) while they fly, finish stage it-1:
+    // wait for this thread's own copies of it-1 (cp.async.wait_group), split every chunk in place - hi = rna_tf32(x) back to the
+    // same slot, lo = rna_tf32(x - hi) to the lo plane - and hand the stage to the MMA warp.  Each thread only ever touches the
+    // chunks it copied itself, so no cross-thread synchronisation is needed before the split.  Global->shared traffic is the
+    // plain fp32 tensor, once; the 2x of the two-plane format exists only in shared memory.
+    auto finish_stage = [&](int it) {
+      const int s = it % STAGES;
+      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
+      const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+      float4 va[A_PER], vb[B_PER];
+      if (a_lo) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) va[i] = lds128(a_hi + a_off[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+      if (a_lo) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) { float4 hi, lo; split4(va[i], hi, lo); sts128(a_hi + a_off[i], hi); sts128(a_lo_s + a_off[i], lo); }
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) { float4 hi, lo; split4(vb[i], hi, lo); sts128(b_hi + b_off[i], hi); sts128(b_lo_s + b_off[i], lo); }
+      fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(bars + 8 * s);
+    };
     for (int it = 0; it < nk; ++it) {
+      // hand stage it-1 to the tensor core FIRST (its copies were issued one iteration ago), then refill: the copies of
+      // stage `it` fly while the MMA warp works on it-1, and the split of it-1 never waits behind a busy slot
+      if (it > 0) { asm volatile("cp.async.wait_group 0;" ::: "memory"); if (warp == 0) TRACE(it * 8 + 3); finish_stage(it - 1); if (warp == 0) TRACE(it * 8 + 4); }
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       const int k0 = (kt0 + it) * BK;
-      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
-      const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+      const uint32_t a_hi = sbase + s * L::STAGE_BYTES;
+      const uint32_t b_hi = a_hi + 2 * L::A_BYTES;
       KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
       if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                  // K-major: this thread's k chunk is the same for all its rows
-#if TC_PRODUCER_CPASYNC
-      // cp.async.ca 16-byte chunks straight into the UMMA layout; the stage's mbarrier tracks their completion
-      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+      if (warp == 0) TRACE(it * 8 + 0);
+      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
+      if (warp == 0) TRACE(it * 8 + 1);
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
         const float* p;
         if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
         else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
-        const uint32_t nb = p ? 16u : 0u;
-        const float* q = p ? p : zero_src;
-        cp_async16(a_hi + a_off[i], q, nb);
-        if (a_lo) cp_async16(a_lo_s + a_off[i], q + (p ? lo_delta : 0), nb);
-      }
-#pragma unroll
-      for (int i = 0; i < B_PER; ++i) {
-        const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
-                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);
-        const uint32_t nb = p ? 16u : 0u;
-        const float* q = p ? p : zero_src;
-        cp_async16(b_hi + b_off[i], q, nb);
-        cp_async16(b_lo_s + b_off[i], q + (p ? lo_delta : 0), nb);
-      }
-      cp_async_arrive(bars + 8 * s);
-      mbar_arrive(bars + 8 * s);
-#else
-      // alternative kept for experiments: ld.global.nc 16 bytes -> registers -> st.shared 16 bytes, loads issued before the
-      // slot wait.  Same speed as cp.async on an isolated GEMM, ~10% slower inside the full step (register pressure, issue slots).
-      float4 vah[A_PER], val[A_PER], vbh[B_PER], vbl[B_PER];
-#pragma unroll
-      for (int i = 0; i < A_PER; ++i) {
-        const float* p;
-        if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
-        else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
-        vah[i] = p ? ldg_f4(p) : make4(0, 0, 0, 0);
-        val[i] = (p && a_lo) ? ldg_f4(p + lo_delta) : make4(0, 0, 0, 0);
+        cp_async16(a_hi + a_off[i], p ? p : zero_src, p ? 16u : 0u);
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) {
         const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
                               : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
-        vbh[i] = p ? ldg_f4(p) : make4(0, 0, 0, 0);
-        vbl[i] = p ? ldg_f4(p + lo_delta) : make4(0, 0, 0, 0);
+        cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
       }
-      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
-#pragma unroll
-      for (int i = 0; i < A_PER; ++i) { sts128(a_hi + a_off[i], vah[i]); if (a_lo) sts128(a_lo_s + a_off[i], val[i]); }
-#pragma unroll
-      for (int i = 0; i < B_PER; ++i) { sts128(b_hi + b_off[i], vbh[i]); sts128(b_lo_s + b_off[i], vbl[i]); }
-      fence_proxy_async();                                     // generic-proxy stores -> visible to the tensor core's async proxy
-      mbar_arrive(bars + 8 * s);
-#endif
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (warp == 0) TRACE(it * 8 + 2);
     }
+    if (nk > 0) { asm volatile("cp.async.wait_group 0;" ::: "memory"); finish_stage(nk - 1); }
     // ================= epilogue =================
     mbar_wait(bar_done, 0);
     tc_fence_after();
@@ -297,6 +311,7 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
         tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + c0, r);
 #pragma unroll
         for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
+          if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
           uint32_t q[16];
           tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + a * BN + c0, q);
 #pragma unroll
@@ -332,12 +347,15 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
   } else {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc2(BM, BN, A_MN, B_MN);
+    const int role = warp - PROD / 32;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
+      if (role == 0) TRACE(it * 8 + 5);
       mbar_wait(bars + 8 * s, ph);
+      if (role == 0) TRACE(it * 8 + 6);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {                                         // one elected lane, uniform control flow: no per-MMA election loop
         const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
         const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
         constexpr uint32_t LTA = A_MN ? 1u : 0u, LTB = B_MN ? 1u : 0u;      // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
@@ -348,24 +366,17 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
           const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
           const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
           const int ks = it * (BK / 8) + j;                     // global k-step index of this CTA
-          const uint32_t dm = tmem + (uint32_t)((ks % R) * BN);
-          if (SEP) {
-            const uint32_t dc = tmem + (uint32_t)(R * BN);
-            if (a_lo) umma_tf32(dc, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-            umma_tf32(dc, dah, dbl, idesc, (a_lo || ks > 0) ? 1u : 0u);
-            umma_tf32(dm, dah, dbh, idesc, ks >= R ? 1u : 0u);
-          } else {
-            if (a_lo) umma_tf32(dm, dal, dbh, idesc, ks >= R ? 1u : 0u);
-            umma_tf32(dm, dah, dbl, idesc, (a_lo || ks >= R) ? 1u : 0u);
-            umma_tf32(dm, dah, dbh, idesc, 1u);
-          }
+          if (role == 0) umma_tf32(tmem + (uint32_t)((ks % R) * BN), dah, dbh, idesc, ks >= R ? 1u : 0u);
+          else if (role == 1) { if (a_lo) umma_tf32(tmem + (uint32_t)(R * BN), dal, dbh, idesc, ks > 0 ? 1u : 0u); }
+          else umma_tf32(tmem + (uint32_t)((R + 1) * BN), dah, dbl, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(bars + 8 * (STAGES + s));                   // frees the smem slot when these MMAs retire
         if (it == nk - 1) umma_commit(bar_done);
       }
+      if (role == 0) TRACE(it * 8 + 7);
       __syncwarp();
     }
-    if (nk == 0 && lane == 0) mbar_arrive(bar_done);
+    if (nk == 0 && lane == 0) mbar_arrive(bar_done);               // one arrival per MMA warp
     tc_fence_before();
   }
   __syncthreads();
@@ -448,49 +459,31 @@ bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* op
 }
 bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, true, fl, by); }
 
-// (re)build the operand planes of both parameter vectors; the first conv layer's block is pre-scaled by 1/255 when it
-// consumes raw bytes
-void tc_split_params(dqn_engine* e, const float* theta, float* planes) {
-  split_params_kernel<<<2 * e->nsm, 256, 0, e->stream>>>(theta, planes, e->lo_delta, e->nint / 4, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
-  CK(cudaGetLastError());
-}
+// first conv layer on raw bytes: (re)build its 1/255-scaled weight copy for both networks
 void tc_params_changed(dqn_engine* e) {
-  if (!e->arena) return;
-  tc_split_params(e, e->theta, e->w_on_s);
-  tc_split_params(e, e->theta_t, e->w_tg_s);
+  if (!e->arena || e->w_scale_hi <= e->w_scale_lo) return;
+  scale_block_kernel<<<32, 256, 0, e->stream>>>(e->theta, e->w_on_s, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
+  scale_block_kernel<<<32, 256, 0, e->stream>>>(e->theta_t, e->w_tg_s, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
+  CK(cudaGetLastError());
 }
 void tc_init(dqn_engine* e) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32) return;
-  const char* dv = getenv("DQN_TC_DEEP");           // pipeline shape override: 0 = two CTAs x two stages, 1 = one CTA, deep; unset = per-launch heuristic
+  const char* dv = getenv("DQN_TC_DEEP");           // pipeline shape override: 0 = two CTAs x two stages, 1 = one CTA, deep
   e->tc_deep = dv ? atoi(dv) : 0;      // measured on B200: two co-resident CTAs beat one deep pipeline on every layer of config 3
-  // one arena, two planes: every pre-split tensor lives at the same offset in both
-  const int B = e->B;
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
-  std::vector<long long> o_conv_on, o_conv_tg, o_conv_d;
-  long long o_tow_on[2][MAXD], o_tow_tg[2][MAXD], o_tow_d[2][MAXD];
-  const long long o_xb = take((long long)e->rows_on * e->obs_elems);
-  for (auto& cl : e->convs) {
-    const long long per = (long long)cl.g.OH * cl.g.OW * cl.g.Cout;
-    o_conv_on.push_back(take(e->rows_on * per)); o_conv_tg.push_back(take(B * per)); o_conv_d.push_back(take(B * per));
-  }
-  for (int t = 0; t < e->ntow; ++t)
-    for (int l = 0; l < e->depth; ++l) {
-      o_tow_on[t][l] = take((long long)e->rows_on * e->tow[t][l].N); o_tow_tg[t][l] = take((long long)B * e->tow[t][l].N); o_tow_d[t][l] = take((long long)B * e->tow[t][l].N);
-    }
-  const long long o_won = take(e->nint), o_wtg = take(e->nint), o_ones = take(64);
-  e->lo_delta = off;
-  e->arena = dalloc<float>(2 * off);
-  float* a = e->arena;
-  e->xb_f = a + o_xb;
-  for (size_t l = 0; l < e->convs.size(); ++l) { e->on.conv_out_s.push_back(a + o_conv_on[l]); e->tg.conv_out_s.push_back(a + o_conv_tg[l]); e->conv_delta_s.push_back(a + o_conv_d[l]); }
-  for (int t = 0; t < e->ntow; ++t)
-    for (int l = 0; l < e->depth; ++l) { e->on.tow_out_s[t][l] = a + o_tow_on[t][l]; e->tg.tow_out_s[t][l] = a + o_tow_tg[t][l]; e->tow_delta_s[t][l] = a + o_tow_d[t][l]; }
-  e->w_on_s = a + o_won; e->w_tg_s = a + o_wtg; e->ones = a + o_ones;
-  const float one = 1.f;
-  CK(cudaMemcpy(e->ones, &one, sizeof(float), cudaMemcpyHostToDevice));       // hi plane {1,0,0,0}; lo plane stays zero
+  const bool bytes = e->elem_bytes == 1;
+  const long long o_xb = take(bytes ? (long long)e->rows_on * e->obs_elems : 0);
   e->w_scale_lo = e->w_scale_hi = 0;
-  if (e->elem_bytes == 1 && !e->convs.empty()) { e->w_scale_lo = e->convs[0].w.off; e->w_scale_hi = e->convs[0].w.off + (long long)e->convs[0].w.K * e->convs[0].w.N; }
+  if (bytes && !e->convs.empty()) { e->w_scale_lo = e->convs[0].w.off; e->w_scale_hi = e->convs[0].w.off + (long long)e->convs[0].w.K * e->convs[0].w.N; }
+  const long long wb = e->w_scale_hi - e->w_scale_lo;
+  const long long o_won = take(wb), o_wtg = take(wb), o_ones = take(64);
+  e->arena = dalloc<float>(off);
+  float* a = e->arena;
+  e->xb_f = bytes ? a + o_xb : nullptr;
+  e->w_on_s = wb ? a + o_won : nullptr; e->w_tg_s = wb ? a + o_wtg : nullptr; e->ones = a + o_ones;
+  const float one = 1.f;
+  CK(cudaMemcpy(e->ones, &one, sizeof(float), cudaMemcpyHostToDevice));       // {1,0,0,0}
   tc_params_changed(e);
 }
 void tc_destroy(dqn_engine* e) { if (e->arena) cudaFree(e->arena); e->arena = nullptr; }

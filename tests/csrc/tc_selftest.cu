@@ -20,7 +20,8 @@ struct Arena {
   void init(long long n) { plane = n; h.assign(2 * n, 0.f); CKC(cudaMalloc(&d, 2 * n * sizeof(float))); }
   long long put(const std::vector<float>& v, bool single = false) {      // returns offset; writes hi/lo split planes
     long long o = used; used += ((long long)v.size() + 63) / 64 * 64;
-    for (size_t i = 0; i < v.size(); ++i) { float hi, lo; split_tf32(v[i], hi, lo); if (single) { hi = v[i]; lo = 0; } h[o + i] = hi; h[plane + o + i] = lo; }
+    for (size_t i = 0; i < v.size(); ++i) h[o + i] = v[i];      // raw fp32: the kernel splits into TF32 hi/lo terms in shared memory
+    (void)single;
     return o;
   }
   long long reserve(long long n) { long long o = used; used += (n + 63) / 64 * 64; return o; }
@@ -152,6 +153,20 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   cudaEventRecord(b); CKC(cudaEventSynchronize(b));
   float ms; cudaEventElapsedTime(&ms, a, b);
   const double us = 1e3 * ms / iters, tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
+#ifdef TC_TRACE
+  {
+    std::vector<long long> tr(8192);
+    CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 8192));
+    const int nk = (K + 31) / 32;
+    printf("  trace CTA0 (cycles, relative to first event): stage: P.loop P.empty-ok P.issued P.landed(prev) P.split-done(prev) | M.wait M.full-ok M.issued\n");
+    const long long t0 = tr[0];
+    for (int it = 0; it < nk && it < 16; ++it) {
+      printf("  %2d:", it);
+      for (int j = 0; j < 8; ++j) printf(" %7lld", tr[it * 8 + j] ? tr[it * 8 + j] - t0 : -1);
+      printf("\n");
+    }
+  }
+#endif
   printf("bench dense M=%d N=%d K=%d BN=%d stages=%d ctas/SM=%d: %.1f us  %.1f TFLOP/s algorithmic (x3 = %.0f TF32)  grid %d\n", M, N, K, BN, L::STAGES, L::CTAS, us, tf, 3 * tf, grid.x * grid.y);
   cudaFree(dW); cudaFree(dC); cudaFree(ar.d);
 }
