@@ -25,6 +25,9 @@
 #define TC_PRODUCER_CPASYNC 1      // 1: cp.async producers (faster in the full step on B200), 0: ld.global.nc -> st.shared
 #endif
 #define TC_CP_CA 1
+#ifndef TC_HI_TRUNC
+#define TC_HI_TRUNC 1
+#endif
 
 namespace tc {
 
@@ -139,6 +142,8 @@ __device__ __forceinline__ float4 permute_chunk(float4 v, int c) {
   if (c & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
   return v;
 }
+__device__ __forceinline__ float lo_of_trunc(float x) { return tf32_rna(__fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u))); }
+__device__ __forceinline__ float4 lo_of_trunc4(const float4& v) { return make4(lo_of_trunc(v.x), lo_of_trunc(v.y), lo_of_trunc(v.z), lo_of_trunc(v.w)); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -258,12 +263,23 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+#if TC_HI_TRUNC
+      // the tensor core reads the top 19 bits of each fp32 word, so the raw tile already IS the hi plane (hi = trunc_tf32(x));
+      // only lo = rna_tf32(x - trunc_tf32(x)) has to be written - a third less shared-memory traffic in the staging pass
+      if (a_lo) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) sts128(a_lo_s + a_off[i], lo_of_trunc4(va[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+#else
       if (a_lo) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) { float4 hi, lo; split4(va[i], hi, lo); sts128(a_hi + a_off[i], hi); sts128(a_lo_s + a_off[i], lo); }
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) { float4 hi, lo; split4(vb[i], hi, lo); sts128(b_hi + b_off[i], hi); sts128(b_lo_s + b_off[i], lo); }
+#endif
       fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's async proxy
       mbar_arrive(bars + 8 * s);
     };

@@ -3,10 +3,13 @@
 Tolerances (stated once, used everywhere):
   * sampled leaf indices, ring contents, actions, best_a, sum-tree nodes: BIT-EXACT
   * Q-values, TD errors, targets, IS weights, loss: normwise relative error <= 1e-5  (north_star)
-  * gradients: normwise relative error <= 2e-4 per parameter array.  The typical distance is ~1e-6 (scripts/tc_report.py
-    prints it next to the oracle's own distance to fp64); the bound is set by ReLU units whose pre-activation lies within
-    rounding distance of zero - with 5.7M units per step a handful flip their sub-gradient between ANY two fp32
-    evaluations (different summation order is enough), which moves single gradient entries by ~1e-4 of the array maximum
+  * gradients, per parameter array: relative L2 error <= 2e-4 always; max-norm error <= 2e-4 x max|g| on smooth (tanh /
+    identity) networks and <= 5e-3 x max|g| on ReLU networks.  The typical distance is ~1e-6 on both (scripts/tc_report.py
+    prints it next to the oracle's own distance to fp64).  The looser max-norm bound on ReLU networks is not kernel error:
+    a ReLU unit whose pre-activation lies within rounding distance of zero flips its sub-gradient between ANY two fp32
+    evaluations (a different summation order is enough - Flux against itself under another BLAS threading would do it);
+    with 5.7M units per step a handful flip, and each moves a few gradient entries by up to ~1e-3 of the array maximum.
+    The tanh networks (mlp_tanh, conv_tanh) exercise the same kernels without that discontinuity
   * Adam: given the engine's own gradients, the updated parameters match the oracle's Flux-Adam to 1 ulp
 """
 import glob
@@ -123,6 +126,8 @@ def test_get_batch_matches_reference_get_batch(lib, name):
 
 
 def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, qtol=QTOL, gtol=GTOL):
+    relu_net = any(l[0] in ("dense", "conv") and l[-1] == 1 for l in spec["layers"])
+    gmax_tol = 5e-3 if relu_net else gtol
     B = spec["B"]
     theta_before = eng.get_params(0)
     m0, v0, bp0 = eng.get_adam_state()
@@ -157,10 +162,12 @@ def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, q
         for arr in out["grads"]:
             sl = slice(o, o + arr.size)
             den = max(np.abs(g64[sl]).max(), 1e-6 * np.abs(g64).max())
-            assert np.abs(g[sl] - gref[sl]).max() <= gtol * den, ("grad array at", o)
-            assert np.abs(g[sl] - g64[sl]).max() <= gtol * den
+            assert np.abs(g[sl] - gref[sl]).max() <= gmax_tol * den, ("grad array at", o)
+            assert np.abs(g[sl] - g64[sl]).max() <= gmax_tol * den
+            l2 = max(np.linalg.norm(g64[sl]), 1e-6 * np.linalg.norm(g64))
+            assert np.linalg.norm(g[sl] - g64[sl]) <= gtol * l2, ("grad array (L2) at", o)
             o += arr.size
-        assert abs(gn - out["grad_norm"]) <= gtol * out["grad_norm"]
+        assert abs(gn - out["grad_norm"]) <= gmax_tol * out["grad_norm"]
         assert gn == np.float32(np.abs(g).max())                             # globalnorm is max|g| (helpers.jl:38-46)
     # Adam in isolation: oracle Flux-Adam applied to the engine's own gradient
     g = eng.grads()
@@ -190,7 +197,7 @@ def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, q
     return loss, gn
 
 
-CASES = [("c1_gridworld", True, True, True), ("c1_gridworld", False, True, True), ("c1_gridworld", True, False, False),
+CASES = [("mlp_tanh", True, True, True), ("conv_tanh", True, True, True), ("c1_gridworld", True, True, True), ("c1_gridworld", False, True, True), ("c1_gridworld", True, False, False),
          ("testmdp", True, True, True), ("conv_small", True, True, True), ("conv_small", False, False, True), ("c2_mlp", True, True, True)]
 
 
@@ -217,7 +224,7 @@ def test_batch_train_step_parity_c3_full_batch(lib, math_mode):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["conv_small", "c2_mlp", "testmdp"])
+@pytest.mark.parametrize("name", ["conv_small", "c2_mlp", "testmdp", "mlp_tanh", "conv_tanh"])
 def test_batch_train_step_parity_tcgen05(lib, name):
     # the tensor-core (3xTF32) path takes every contraction it covers; the rest stays on the fp32 kernels
     spec, net, tgt, buf, eng = setup_pair(lib, name, math_mode=1)

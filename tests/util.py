@@ -17,6 +17,10 @@ SPECS = {
     # small conv trunk, u8 store, odd sizes
     "conv_small": dict(layers=[("conv", 4, 4, 8, 2, 1), ("conv", 3, 8, 12, 1, 1), ("flatten",), ("dense", 12 * 3 * 3, 20, 1), ("dense", 20, 5, 0)],
                        obs=(4, 12, 12), nA=5, B=24, N=300, u8=True, lr=1e-3),
+    # smooth (tanh) networks, every contraction large enough for the tensor-core path: gradient parity without ReLU sub-gradient flips
+    "mlp_tanh": dict(layers=[("dense", 128, 256, 2), ("dense", 256, 256, 2), ("dense", 256, 16, 0)], obs=(128,), nA=16, B=256, N=2048, u8=False, lr=1e-4),
+    "conv_tanh": dict(layers=[("conv", 4, 4, 32, 2, 2), ("conv", 3, 32, 32, 1, 2), ("flatten",), ("dense", 32 * 7 * 7, 64, 2), ("dense", 64, 5, 0)],
+                      obs=(4, 20, 20), nA=5, B=64, N=512, u8=True, lr=1e-3),
     # config 2 (BASELINE.json): 128 -> 3x256 -> 16
     "c2_mlp": dict(layers=[("dense", 128, 256, 1), ("dense", 256, 256, 1), ("dense", 256, 256, 1), ("dense", 256, 16, 0)],
                    obs=(128,), nA=16, B=256, N=4096, u8=False, lr=1e-4),
