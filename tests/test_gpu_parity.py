@@ -3,13 +3,13 @@
 Tolerances (stated once, used everywhere):
   * sampled leaf indices, ring contents, actions, best_a, sum-tree nodes: BIT-EXACT
   * Q-values, TD errors, targets, IS weights, loss: normwise relative error <= 1e-5  (north_star)
-  * gradients, per parameter array: relative L2 error <= 2e-4 always; max-norm error <= 2e-4 x max|g| on smooth (tanh /
-    identity) networks and <= 5e-3 x max|g| on ReLU networks.  The typical distance is ~1e-6 on both (scripts/tc_report.py
-    prints it next to the oracle's own distance to fp64).  The looser max-norm bound on ReLU networks is not kernel error:
-    a ReLU unit whose pre-activation lies within rounding distance of zero flips its sub-gradient between ANY two fp32
-    evaluations (a different summation order is enough - Flux against itself under another BLAS threading would do it);
-    with 5.7M units per step a handful flip, and each moves a few gradient entries by up to ~1e-3 of the array maximum.
-    The tanh networks (mlp_tanh, conv_tanh) exercise the same kernels without that discontinuity
+  * gradients, per parameter array, max-norm and L2: <= 5e-5 relative on smooth (tanh / identity) networks, <= 5e-3 on ReLU
+    networks.  The typical distance is ~1e-6 on both (scripts/tc_report.py prints it next to the oracle's own distance to
+    fp64).  The loose bound on ReLU networks is not kernel error: a ReLU unit whose pre-activation lies within rounding
+    distance of zero flips its sub-gradient between ANY two fp32 evaluations (a different summation order is enough - Flux
+    against itself under another BLAS threading would do it).  scripts/relu_flip_study.py shows it on the CPU alone: the
+    fp32 oracle against the fp64 oracle, config 3, 1 batch in 8 has 1e-3 relative error in the conv1/conv2 gradients while
+    all other arrays agree to 3e-7.  The tanh networks (mlp_tanh, conv_tanh) run the same kernels without that discontinuity
   * Adam: given the engine's own gradients, the updated parameters match the oracle's Flux-Adam to 1 ulp
 """
 import glob
@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 
 SEED = 2
 QTOL = 1e-5
-GTOL = 2e-4
+GTOL = 5e-5
 
 
 def make_engine(lib, spec, dueling=True, double_q=True, per=True, use_graph=True, math_mode=0, B=None, N=None, gamma=0.99):
@@ -165,7 +165,7 @@ def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, q
             assert np.abs(g[sl] - gref[sl]).max() <= gmax_tol * den, ("grad array at", o)
             assert np.abs(g[sl] - g64[sl]).max() <= gmax_tol * den
             l2 = max(np.linalg.norm(g64[sl]), 1e-6 * np.linalg.norm(g64))
-            assert np.linalg.norm(g[sl] - g64[sl]) <= gtol * l2, ("grad array (L2) at", o)
+            assert np.linalg.norm(g[sl] - g64[sl]) <= gmax_tol * l2, ("grad array (L2) at", o)
             o += arr.size
         assert abs(gn - out["grad_norm"]) <= gmax_tol * out["grad_norm"]
         assert gn == np.float32(np.abs(g).max())                             # globalnorm is max|g| (helpers.jl:38-46)
@@ -311,8 +311,9 @@ def test_engine_against_committed_golden_vectors(lib, path):
     assert np.array_equal(eng.targets()[1] - 1, g["best_a"])
     assert np.abs(eng.td() - g["td"]).max() <= 2 * QTOL * scale
     assert abs(loss - g["loss"]) <= 1e-5 * abs(g["loss"])
-    assert util.relerr(eng.grads(), g["grads64"]) <= GTOL
-    assert abs(gn - g["grad_norm"]) <= GTOL * g["grad_norm"]
+    gt = 5e-3 if name == "conv_small" else GTOL                  # ReLU network: flip-aware bound (module docstring)
+    assert util.relerr(eng.grads(), g["grads64"]) <= gt
+    assert abs(gn - g["grad_norm"]) <= gt * g["grad_norm"]
     assert np.abs(eng.get_priorities() - g["prio1"][:eng.replay_size()[0]]).max() <= 1e-5
     eng.close()
 
