@@ -138,7 +138,7 @@ struct dqn_engine {
   float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
-  int tc_deep = -1;
+  int tc_split = 0;
 };
 
 namespace {

@@ -10,15 +10,17 @@
 // the lo plane).  Global->shared traffic - the measured bottleneck of this kernel family on B200, ~3.6 TB/s chip-wide for
 // 16-byte cp.async - is therefore one pass over the fp32 data; an earlier version that kept hi/lo planes in HBM moved 2x.
 //
-//   warps 0-7 (256 threads)  producers (cp.async + in-place split) and, after the main loop, the epilogue
-//                            (tcgen05.ld -> bias/activation or act' -> 16-byte stores); K-major operands use the no-swizzle
-//                            layout (8-row x 16-byte core matrices), MN-major operands SWIZZLE_128B_BASE32B.
-//   warps 8-10               one elected lane each issues tcgen05.mma.kind::tf32 for ONE of the three products per 8-wide k step
-//                            (A_hi B_hi | A_lo B_hi | A_hi B_lo; the dropped A_lo B_lo term is O(2^-22)); the A_lo stream idles
-//                            when A is single-plane (raw byte values are TF32-exact).
-//   accumulators             fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
-//                            1 ulp per MMA), so the correction products get their own accumulator (SEP) and the main
-//                            product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
+//   one persistent CTA per SM (480 threads) walks output tiles blockIdx.x, +gridDim.x, ...; nothing drains between tiles:
+//   warps 0-7   producers: cp.async of 16-byte chunks into the ring (K-major operands in the no-swizzle layout of 8-row x 16-byte
+//               core matrices, MN-major operands in SWIZZLE_128B_BASE32B), DEPTH stages in flight behind the stage being split
+//   warps 8-11  epilogue: tcgen05.ld of one of the NBUF accumulator sets -> bias/activation or act' -> 16-byte stores, while the
+//               MMA warps already work on the next tile in the other set
+//   warps 12-14 one elected lane each issues tcgen05.mma.kind::tf32 for ONE of the three products per 8-wide k step
+//               (A_hi B_hi | A_lo B_hi | A_hi B_lo; the dropped A_lo B_lo term is O(2^-22)); the A_lo stream idles
+//               when A is single-plane (raw byte values are TF32-exact).
+//   accumulators  fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
+//               1 ulp per MMA), so the correction products get their own accumulators and the main
+//               product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
 #pragma once
 #include <cstdlib>
 #ifndef TC_PRODUCER_CPASYNC
@@ -33,17 +35,19 @@ namespace tc {
 
 #ifdef TC_TRACE
 __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (producer warp 0 and the MMA warp): tuning aid of the selftest
-#define TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) tc_trace[(slot)] = clock64(); } while (0)
+#define TRACE(slot) do { if (blockIdx.x == 0 && lane == 0 && (slot) < 8192) tc_trace[(slot)] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-constexpr int PROD = 256;        // producer / epilogue threads (8 warps: short per-thread address chains, more loads in flight)
-constexpr int NMMA = 3;           // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
-                                  // a single thread issues ~70-cycle tcgen05.mma, three streams keep the tensor core fed
-constexpr int THREADS = PROD + 32 * NMMA;
+constexpr int PROD_WARPS = 8;    // producer warps (cp.async + in-place split): short per-thread address chains, many loads in flight
+constexpr int PROD = 32 * PROD_WARPS;
+constexpr int EPI_WARPS = 4;     // epilogue warps: warp & 3 = the TMEM lane quarter it may read
+constexpr int NMMA = 3;          // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
+                                 // a single thread issues ~70-cycle tcgen05.mma, three streams keep the tensor core fed
+constexpr int THREADS = PROD + 32 * EPI_WARPS + 32 * NMMA;      // 480: warps 0-7 producers, 8-11 epilogue, 12-14 MMA
 
 // shared-memory tile of one operand plane for one stage
 template <int ROWS, bool MN> struct Tile;
@@ -61,18 +65,31 @@ template <int ROWS> struct Tile<ROWS, true> {                 // MN-major TF32: 
   static constexpr int KSTEP = 2 * SBO;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool DEEP> struct Lay {
+__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+// One persistent CTA per SM.  The shared-memory ring holds STAGES slots of {A raw, A lo, B raw, B lo}; DEPTH stages of
+// cp.async traffic stay in flight behind the stage being split, across tile boundaries (the ring never drains between tiles).
+// TMEM holds NBUF accumulator sets of NACC x BN columns, so the epilogue of tile i overlaps the main loop of tile i+1.
+template <int BN, int R, bool A_MN, bool B_MN> struct Lay {
   using TA = Tile<BM, A_MN>;
   using TB = Tile<BN, B_MN>;
   static constexpr int A_BYTES = (TA::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
   static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // A_hi, A_lo, B_hi, B_lo
-  // DEEP: one CTA per SM with as many stages as fit (long-K contractions with few tiles: latency hiding comes from depth);
-  // otherwise two co-resident CTAs with two stages each when they fit (many short tiles: the neighbour hides prologue/epilogue)
-  static constexpr int FIT = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = DEEP ? (FIT > 6 ? 6 : FIT) : ((2 * (2 * STAGE_BYTES + 1024 + 128) <= 226 * 1024) ? 2 : 3);
-  static constexpr int CTAS = (!DEEP && STAGES == 2) ? 2 : 1;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 128;       // + alignment slack + barriers / tmem address
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // A_hi(raw), A_lo, B_hi(raw), B_lo
+  static constexpr int TAIL = 1024 + 256;                              // alignment slack + barriers / tmem address
+  static constexpr int FIT = (227 * 1024 - TAIL) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+  static_assert(STAGES >= 3, "ring too shallow");
+#ifdef TC_EXP_DEPTH
+  static constexpr int DEPTH = TC_EXP_DEPTH;
+#else
+  static constexpr int DEPTH = STAGES - 2;
+#endif
+  static constexpr int NACC = R + 2;                                   // R interleaved main accumulators + one per correction product
+  static constexpr int NBUF = (2 * NACC * BN <= 512) ? 2 : 1;
+  static constexpr int TCOLS = pow2_cols(NBUF * NACC * BN);
+  static_assert(NACC * BN <= 512, "TMEM columns");
+  static constexpr int SMEM = STAGES * STAGE_BYTES + TAIL;
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -142,7 +159,11 @@ __device__ __forceinline__ float4 permute_chunk(float4 v, int c) {
   if (c & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
   return v;
 }
-__device__ __forceinline__ float lo_of_trunc(float x) { return tf32_rna(__fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u))); }
+// lo term of x = trunc_tf32(x) + lo.  The subtraction is exact; adding half a TF32 ulp to the bit pattern makes the tensor core's own
+// truncation of the operand a round-to-nearest (ties away) - the low 13 bits need no masking, the hardware ignores them.
+__device__ __forceinline__ float lo_of_trunc(float x) {
+  return __uint_as_float(__float_as_uint(__fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u))) + 0x1000u);
+}
 __device__ __forceinline__ float4 lo_of_trunc4(const float4& v) { return make4(lo_of_trunc(v.x), lo_of_trunc(v.y), lo_of_trunc(v.z), lo_of_trunc(v.w)); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -172,70 +193,71 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive w
 __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int BN, int R, bool SEP, bool DEEP, class Op>
-__global__ void __launch_bounds__(THREADS, (Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>::CTAS == 2 && BN * (R + 2) <= 256) ? 2 : 1)
-tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src) {
+template <int BN, int R, class Op>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, int nsplit, float* __restrict__ ws, long long ws_stride,
+               const float* __restrict__ zero_src, int MT, int NT, int ntiles) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
-  using L = Lay<BN, A_MN, B_MN, DEEP>;
+  using L = Lay<BN, R, A_MN, B_MN>;
   using TA = typename L::TA;
   using TB = typename L::TB;
-  constexpr int STAGES = L::STAGES;
+  constexpr int STAGES = L::STAGES, DEPTH = L::DEPTH, NACC = L::NACC, NBUF = L::NBUF;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + STAGES * L::STAGE_BYTES;        // full[STAGES], empty[STAGES], done : 8 bytes each
-  const uint32_t bar_done = bars + 16 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 16 * STAGES + 8);
-
-  const int zi = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
-  Op op = (Op::Z_IS_CLASS || zi == 0) ? opa : opb;
-  if (Op::Z_IS_CLASS) op.set_class(zi);
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  if (m0 >= op.M || n0 >= op.N) return;                        // uniform per CTA
-  const int ktiles = (op.K + BK - 1) / BK;
-  const int per = (ktiles + nsplit - 1) / nsplit;
-  const int kt0 = split * per, kt1 = min(ktiles, kt0 + per);
-  const int nk = max(kt1 - kt0, 0);
-  const bool a_lo = !op.a_single;
+  const uint32_t bar_full = sbase + STAGES * L::STAGE_BYTES;    // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]: 8 bytes each
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * STAGES;
+  const uint32_t bar_acce = bar_accf + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 16 * STAGES + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NACC = R + 2;                                  // R interleaved main accumulators + one per correction product
-  static_assert(SEP, "corrections always have their own accumulators");
-  constexpr int TCOLS = pow2_cols(BN * NACC);
-  static_assert(BN * NACC <= 512, "TMEM columns");
+  const bool a_lo = !opa.a_single;
+  constexpr int MMA_WARP0 = PROD_WARPS + EPI_WARPS;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, PROD); mbar_init(bars + 8 * (STAGES + s), NMMA); }
-    mbar_init(bar_done, NMMA);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, PROD_WARPS); mbar_init(bar_empty + 8 * s, NMMA); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == PROD / 32) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
+  if (warp == MMA_WARP0) tmem_alloc<L::TCOLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < PROD / 32) {
-    // ================= producers: chunk addresses + cp.async only =================
+  // tile t -> (m tile fastest, n tile, z = operand set x k split).  Every role walks the same list; a tile outside its
+  // operand's extent (parity classes differ in M) is skipped by all of them alike.
+  auto decode = [&](int t, Op& op, int& m0, int& n0, int& zs, int& kt0, int& nk) -> bool {
+    const int mt = t % MT, r = t / MT;
+    const int nt = r % NT;
+    zs = r / NT;
+    const int zi = zs / nsplit, split = zs - zi * nsplit;
+    op = (Op::Z_IS_CLASS || zi == 0) ? opa : opb;
+    if (Op::Z_IS_CLASS) op.set_class(zi);
+    m0 = mt * BM; n0 = nt * BN;
+    if (m0 >= op.M || n0 >= op.N) return false;
+    const int ktiles = (op.K + BK - 1) / BK;
+    const int per = (ktiles + nsplit - 1) / nsplit;
+    kt0 = split * per;
+    nk = max(min(ktiles, kt0 + per) - kt0, 0);
+    return true;
+  };
+
+  if (warp < PROD_WARPS) {
+    // ================= producers: chunk addresses + cp.async, then the in-place split =================
     constexpr int A_PER = BM * (BK / 4) / PROD;                // 4 chunks of A per thread per stage
     constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/32 chunks of B
-    ACtx actx[A_MN ? 1 : A_PER];
     uint32_t a_off[A_PER]; int a_kk[A_PER];
-    if (A_MN) {                                                // lane = 16-byte chunk along the rows, k rows spread over warps / i
-      actx[0] = op.prepA(m0 + lane * 4);
 #pragma unroll
-      for (int i = 0; i < A_PER; ++i) {
-        a_kk[i] = (tid >> 5) + (PROD / 32) * i;
+    for (int i = 0; i < A_PER; ++i) {
+      if (A_MN) {                                              // lane = 16-byte chunk along the rows, k rows spread over warps / i
+        a_kk[i] = (tid >> 5) + PROD_WARPS * i;
         a_off[i] = (lane >> 3) * TA::LBO + a_kk[i] * 128 + (((lane & 7) ^ ((a_kk[i] & 3) << 1)) * 16);   // 32-byte units XOR k row (SWIZZLE_128B_BASE32B)
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < A_PER; ++i) {
+      } else {
         const int r = (tid >> 3) + i * (PROD / 8);
-        actx[i] = op.prepA(m0 + r);
         a_kk[i] = (tid & 7) * 4;
         a_off[i] = (tid & 7) * TA::LBO + (r >> 3) * TA::SBO + (r & 7) * 16;
       }
@@ -247,156 +269,193 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
       if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
-    // Per stage: (1) cp.async the RAW fp32 chunks of stage `it` into the hi-plane slots, (2) while they fly, finish stage it-1:
-    // wait for this thread's own copies of it-1 (cp.async.wait_group), split every chunk in place - hi = rna_tf32(x) back to the
-    // same slot, lo = rna_tf32(x - hi) to the lo plane - and hand the stage to the MMA warp.  Each thread only ever touches the
-    // chunks it copied itself, so no cross-thread synchronisation is needed before the split.  Global->shared traffic is the
-    // plain fp32 tensor, once; the 2x of the two-plane format exists only in shared memory.
-    auto finish_stage = [&](int it) {
-      const int s = it % STAGES;
+    // Per stage: (1) cp.async the RAW fp32 chunks into the hi-plane slots of ring slot `is`; (2) once DEPTH younger stages are in
+    // flight, finish the oldest: wait for this thread's own copies of it (cp.async.wait_group DEPTH), write lo = rna_tf32(x - trunc_tf32(x))
+    // of every chunk to the lo plane and hand the slot to the MMA warps.  The tensor core reads the top 19 bits of each fp32 word, so the
+    // raw tile already IS the hi plane.  Each thread only ever touches the chunks it copied itself, so no cross-thread synchronisation
+    // is needed before the split.  Global->shared traffic is the plain fp32 tensor, once.
+    auto finish_stage = [&](int s) {
       const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
       const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
       float4 va[A_PER], vb[B_PER];
+#ifndef TC_EXP_NOSPLIT
       if (a_lo) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) va[i] = lds128(a_hi + a_off[i]);
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
-#if TC_HI_TRUNC
-      // the tensor core reads the top 19 bits of each fp32 word, so the raw tile already IS the hi plane (hi = trunc_tf32(x));
-      // only lo = rna_tf32(x - trunc_tf32(x)) has to be written - a third less shared-memory traffic in the staging pass
       if (a_lo) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) sts128(a_lo_s + a_off[i], lo_of_trunc4(va[i]));
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
-#else
-      if (a_lo) {
-#pragma unroll
-        for (int i = 0; i < A_PER; ++i) { float4 hi, lo; split4(va[i], hi, lo); sts128(a_hi + a_off[i], hi); sts128(a_lo_s + a_off[i], lo); }
-      }
-#pragma unroll
-      for (int i = 0; i < B_PER; ++i) { float4 hi, lo; split4(vb[i], hi, lo); sts128(b_hi + b_off[i], hi); sts128(b_lo_s + b_off[i], lo); }
-#endif
       fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(bars + 8 * s);
+#endif
+      __syncwarp();                                            // one arrival per warp: 256 single arrivals on one barrier word serialise (~1100 clk per stage)
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
     };
-    for (int it = 0; it < nk; ++it) {
-      // hand stage it-1 to the tensor core FIRST (its copies were issued one iteration ago), then refill: the copies of
-      // stage `it` fly while the MMA warp works on it-1, and the split of it-1 never waits behind a busy slot
-      if (it > 0) { asm volatile("cp.async.wait_group 0;" ::: "memory"); if (warp == 0) TRACE(it * 8 + 3); finish_stage(it - 1); if (warp == 0) TRACE(it * 8 + 4); }
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      const int k0 = (kt0 + it) * BK;
-      const uint32_t a_hi = sbase + s * L::STAGE_BYTES;
-      const uint32_t b_hi = a_hi + 2 * L::A_BYTES;
-      KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
-      if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                  // K-major: this thread's k chunk is the same for all its rows
-      if (warp == 0) TRACE(it * 8 + 0);
-      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);              // slot free (first pass returns immediately)
-      if (warp == 0) TRACE(it * 8 + 1);
+    int is = 0; uint32_t iph = 0;                              // ring slot / phase of the next stage to issue
+    int fs = 0, inflight = 0;                                  // oldest unfinished slot, committed-but-unfinished stages
+    int gtr = 0; (void)gtr;                                    // global stage counter (trace builds only)
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      Op op; int m0, n0, zs, kt0, nk;
+      if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+      ACtx actx[A_MN ? 1 : A_PER];
+      if (A_MN) actx[0] = op.prepA(m0 + lane * 4);
+      else {
 #pragma unroll
-      for (int i = 0; i < A_PER; ++i) {
-        const float* p;
-        if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
-        else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
-        cp_async16(a_hi + a_off[i], p ? p : zero_src, p ? 16u : 0u);
+        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (PROD / 8));
       }
+      for (int it = 0; it < nk; ++it) {
+        const int k0 = (kt0 + it) * BK;
+        const uint32_t a_hi = sbase + is * L::STAGE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * L::A_BYTES;
+        KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
+        if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                // K-major: this thread's k chunk is the same for all its rows
+        if (warp == 0) TRACE(gtr * 8 + 0);
+        mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
+        if (warp == 0) TRACE(gtr * 8 + 1);
 #pragma unroll
-      for (int i = 0; i < B_PER; ++i) {
-        const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
-                              : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
-        cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (warp == 0) TRACE(it * 8 + 2);
-    }
-    if (nk > 0) { asm volatile("cp.async.wait_group 0;" ::: "memory"); finish_stage(nk - 1); }
-    // ================= epilogue =================
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
-    const int m = m0 + q4 * 32 + lane;
-    constexpr int CPW = BN / (PROD / 128);                     // columns per warp: the two warps of a quarter split the tile's columns
-#pragma unroll 1
-    for (int c0 = (warp >> 2) * CPW; c0 < (warp >> 2) * CPW + CPW; c0 += 16) {
-      uint32_t r[16];
-      if (nk > 0) {
-        tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + c0, r);
-#pragma unroll
-        for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
-          if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
-          uint32_t q[16];
-          tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + a * BN + c0, q);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
+        for (int i = 0; i < A_PER; ++i) {
+          const float* p;
+          if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
+          else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
+#ifndef TC_EXP_NOLOAD
+          cp_async16(a_hi + a_off[i], p ? p : zero_src, p ? 16u : 0u);
+#else
+          if (p == (const float*)1) cp_async16(a_hi + a_off[i], p, 16u);
+#endif
         }
-      } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int i = 0; i < B_PER; ++i) {
+          const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
+                                : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
+#ifndef TC_EXP_NOLOAD
+          cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
+#else
+          if (p == (const float*)1) cp_async16(b_hi + b_off[i], p, 16u);
+#endif
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (warp == 0) TRACE(gtr * 8 + 2);
+        if (++is == STAGES) { is = 0; iph ^= 1; }
+        if (inflight == DEPTH) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
+          if (warp == 0) TRACE((gtr - DEPTH) * 8 + 3);
+          finish_stage(fs);
+          if (warp == 0) TRACE((gtr - DEPTH) * 8 + 4);
+          if (++fs == STAGES) fs = 0;
+        } else ++inflight;
+        ++gtr;
       }
-      if (m < op.M) {
-        if (nsplit == 1 && op.can_store4() && n0 + c0 + 15 < op.N) {
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (; inflight > 0; --inflight) { finish_stage(fs); if (++fs == STAGES) fs = 0; }
+  } else if (warp < MMA_WARP0) {
+    // ================= epilogue: TMEM -> registers -> bias/activation or act' -> 16-byte stores =================
+    const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
+    int buf = 0; uint32_t aph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      Op op; int m0, n0, zs, kt0, nk;
+      if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+      mbar_wait(bar_accf + 8 * buf, aph);
+      tc_fence_after();
+      const int m = m0 + q4 * 32 + lane;
+      const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NACC * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        if (nk > 0) {
+          tmem_ld16(tb + c0, r);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            op.store4(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-        } else if (nsplit > 1 && (op.N & 3) == 0 && n0 + c0 + 15 < op.N) {
-          float4* wp = reinterpret_cast<float4*>(ws + (long long)blockIdx.z * ws_stride + (long long)m * op.N + n0 + c0);
+          for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
+            if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
+            uint32_t q[16];
+            tmem_ld16(tb + a * BN + c0, q);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) wp[j >> 2] = make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < op.N) {
-              const float v = __uint_as_float(r[j]);
-              if (nsplit > 1) ws[(long long)blockIdx.z * ws_stride + (long long)m * op.N + n] = v;
-              else op.store(m, n, v);
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        if (m < op.M) {
+          if (nsplit == 1 && op.can_store4() && n0 + c0 + 15 < op.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              op.store4(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          } else if (nsplit > 1 && (op.N & 3) == 0 && n0 + c0 + 15 < op.N) {
+            float4* wp = reinterpret_cast<float4*>(ws + (long long)zs * ws_stride + (long long)m * op.N + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) wp[j >> 2] = make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < op.N) {
+                const float v = __uint_as_float(r[j]);
+                if (nsplit > 1) ws[(long long)zs * ws_stride + (long long)m * op.N + n] = v;
+                else op.store(m, n, v);
+              }
             }
           }
         }
       }
-    }
-    tc_fence_before();
-  } else {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc2(BM, BN, A_MN, B_MN);
-    const int role = warp - PROD / 32;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      if (role == 0) TRACE(it * 8 + 5);
-      mbar_wait(bars + 8 * s, ph);
-      if (role == 0) TRACE(it * 8 + 6);
-      tc_fence_after();
-      if (elect_one()) {                                         // one elected lane, uniform control flow: no per-MMA election loop
-        const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
-        const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
-        constexpr uint32_t LTA = A_MN ? 1u : 0u, LTB = B_MN ? 1u : 0u;      // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
-#pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
-          const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
-          const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
-          const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
-          const int ks = it * (BK / 8) + j;                     // global k-step index of this CTA
-          if (role == 0) umma_tf32(tmem + (uint32_t)((ks % R) * BN), dah, dbh, idesc, ks >= R ? 1u : 0u);
-          else if (role == 1) { if (a_lo) umma_tf32(tmem + (uint32_t)(R * BN), dal, dbh, idesc, ks > 0 ? 1u : 0u); }
-          else umma_tf32(tmem + (uint32_t)((R + 1) * BN), dah, dbl, idesc, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(bars + 8 * (STAGES + s));                   // frees the smem slot when these MMAs retire
-        if (it == nk - 1) umma_commit(bar_done);
-      }
-      if (role == 0) TRACE(it * 8 + 7);
+      tc_fence_before();                                       // this warp's tcgen05.ld are complete (wait::ld) and ordered before the arrive
       __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);          // accumulator set free for the tile after next
+      if (++buf == NBUF) { buf = 0; aph ^= 1; }
     }
-    if (nk == 0 && lane == 0) mbar_arrive(bar_done);               // one arrival per MMA warp
+  } else {
+    // ================= MMA issuers =================
+    constexpr uint32_t idesc = make_idesc2(BM, BN, A_MN, B_MN);
+    const int role = warp - MMA_WARP0;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
+    int s = 0; uint32_t ph = 0;
+    int buf = 0; uint32_t aph = 0;
+    int gtr = 0; (void)gtr;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      Op op; int m0, n0, zs, kt0, nk;
+      if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+      mbar_wait(bar_acce + 8 * buf, aph ^ 1);                  // the epilogue has drained this accumulator set (first NBUF tiles: immediate)
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
+      for (int it = 0; it < nk; ++it) {
+        if (role == 0) TRACE(gtr * 8 + 5);
+        mbar_wait(bar_full + 8 * s, ph);
+        if (role == 0) TRACE(gtr * 8 + 6);
+        tc_fence_after();
+        if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
+          const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
+          const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+          constexpr uint32_t LTA = A_MN ? 1u : 0u, LTB = B_MN ? 1u : 0u;      // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
+            const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
+            const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
+            const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
+            const int ks = it * (BK / 8) + j;                     // k-step index within this tile
+            if (role == 0) umma_tf32(acc + (uint32_t)((ks % R) * BN), dah, dbh, idesc, ks >= R ? 1u : 0u);
+            else if (role == 1) { if (a_lo) umma_tf32(acc + (uint32_t)(R * BN), dal, dbh, idesc, ks > 0 ? 1u : 0u); }
+            else umma_tf32(acc + (uint32_t)((R + 1) * BN), dah, dbl, idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);                         // frees the smem slot when these MMAs retire
+          if (it == nk - 1) umma_commit(bar_accf + 8 * buf);      // ... and publishes the accumulators after the tile's last stage
+        }
+        __syncwarp();
+        if (role == 0) TRACE(gtr * 8 + 7);
+        ++gtr;
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (nk == 0 && lane == 0) mbar_arrive(bar_accf + 8 * buf);   // one arrival per MMA warp
+      if (++buf == NBUF) { buf = 0; aph ^= 1; }
+    }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == PROD / 32) { tc_fence_after(); tmem_dealloc<TCOLS>(tmem); }
+  if (warp == MMA_WARP0) { tc_fence_after(); tmem_dealloc<L::TCOLS>(tmem); }
 }
 
 }  // namespace tc
@@ -404,21 +463,35 @@ tc_gemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_
 #ifndef TC_KERNEL_ONLY
 namespace {
 
-template <int BN, bool DEEP, class Op>
-void tc_launch_d(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride) {
-  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEP>;
+template <int BN, class Op>
+void tc_launch_bn(dqn_engine* e, const Op& a, const Op& b, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
+  using L = tc::Lay<BN, 2, Op::A_MCONTIG, !Op::B_KCONTIG>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, DEEP, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set = true;
   }
-  tc::tc_gemm_kernel<BN, 2, true, DEEP, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena);
+  const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
+  tc::tc_gemm_kernel<BN, 2, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
   CK(cudaGetLastError());
 }
-template <int BN, class Op>
-void tc_launch_bn(dqn_engine* e, dim3 grid, const Op& a, const Op& b, int nsplit, long long ws_stride, bool deep) {
-  if (deep) tc_launch_d<BN, true, Op>(e, grid, a, b, nsplit, ws_stride);
-  else tc_launch_d<BN, false, Op>(e, grid, a, b, nsplit, ws_stride);
+
+// k split of a contraction whose tile count does not fill the machine (or whose k extent dwarfs its output, the weight gradients):
+// minimise a rough time model - rounds of tiles over the SMs x stages per tile, plus the reduction pass over the partial outputs
+int tc_pick_split(dqn_engine* e, long long tiles0, int ktiles, int bn, long long out_elems, int nz) {
+  const double stage_us = bn == 128 ? 0.70 : (bn == 64 ? 0.45 : 0.32), tile_us = 1.5;
+  int best = 1; double best_t = 1e30;
+  const int max_ns = std::max(1, std::min(64, ktiles / 4));
+  for (int ns = 1; ns <= max_ns; ++ns) {
+    if (ns > 1 && (long long)nz * ns * out_elems > e->ws_floats) break;
+    const int per = (ktiles + ns - 1) / ns;
+    if (ns > 1 && (long long)per * (ns - 1) >= ktiles) continue;             // a split with an empty last range
+    const long long rounds = (tiles0 * ns + e->nsm - 1) / e->nsm;
+    double t = rounds * (per * stage_us + tile_us);
+    if (ns > 1) t += 5.0 + (double)(ns + 1) * out_elems * nz * 4.0 / 2.5e6;  // reduce kernel: launch + bytes at ~2.5 TB/s
+    if (t < best_t) { best_t = t; best = ns; }
+  }
+  return best;
 }
 
 template <class Op>
@@ -431,24 +504,19 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   if (!Op::Z_IS_CLASS && nz == 2) { M = std::max(M, b.M); N = std::max(N, b.N); K = std::max(K, b.K); }
   if (M < 64 || N < 24 || K < 32) return false;                 // small / odd layers stay on the fp32 CUDA-core kernel
   const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-  const long long ctas = (long long)((M + tc::BM - 1) / tc::BM) * ((N + bn - 1) / bn) * nz;
-  int nsplit = 1;
+  const int MT = (M + tc::BM - 1) / tc::BM, NT = (N + bn - 1) / bn;
+  const long long tiles0 = (long long)MT * NT * nz;
   const int ktiles = (K + tc::BK - 1) / tc::BK;
-  if (!Op::Z_IS_CLASS && (allow_split || ctas < e->nsm)) {     // splitk_reduce has no notion of dgrad parity classes
-    nsplit = (int)std::max<long long>(1, std::min<long long>({(2LL * e->nsm + ctas - 1) / ctas, (long long)ktiles / 8, 64LL}));
-    const long long stride = (long long)M * N;
-    if (nsplit > 1 && (long long)nz * nsplit * stride > e->ws_floats) nsplit = (int)std::max<long long>(1, e->ws_floats / (nz * stride));
-  }
+  int nsplit = 1;
+  if (!Op::Z_IS_CLASS && (allow_split || tiles0 < e->nsm))      // splitk_reduce has no notion of dgrad parity classes
+    nsplit = e->tc_split > 0 ? std::min(e->tc_split, std::max(1, ktiles / 4)) : tc_pick_split(e, tiles0, ktiles, bn, (long long)M * N, nz);
   const long long ws_stride = (long long)M * N;
-  dim3 grid((M + tc::BM - 1) / tc::BM, (N + bn - 1) / bn, nz * nsplit);
-  // deep single-CTA pipelines when the grid cannot put two CTAs on every SM anyway, or when each CTA runs a long k loop
-  const int kt_per_cta = (ktiles + nsplit - 1) / nsplit;
-  const bool deep = e->tc_deep == 1 || (e->tc_deep < 0 && ((long long)grid.x * grid.y * grid.z <= 2LL * e->nsm || kt_per_cta >= 24));
+  const int ntiles = (int)(tiles0 * nsplit);
   {
     Scope sc(e, name, flops, bytes);
-    if (bn == 32) tc_launch_bn<32, Op>(e, grid, a, b, nsplit, ws_stride, deep);
-    else if (bn == 64) tc_launch_bn<64, Op>(e, grid, a, b, nsplit, ws_stride, deep);
-    else tc_launch_bn<128, Op>(e, grid, a, b, nsplit, ws_stride, deep);
+    if (bn == 32) tc_launch_bn<32, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
+    else if (bn == 64) tc_launch_bn<64, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
+    else tc_launch_bn<128, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
@@ -484,8 +552,8 @@ void tc_params_changed(dqn_engine* e) {
 }
 void tc_init(dqn_engine* e) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32) return;
-  const char* dv = getenv("DQN_TC_DEEP");           // pipeline shape override: 0 = two CTAs x two stages, 1 = one CTA, deep
-  e->tc_deep = dv ? atoi(dv) : 0;      // measured on B200: two co-resident CTAs beat one deep pipeline on every layer of config 3
+  const char* dv = getenv("DQN_TC_SPLIT");          // tuning override: force this k split wherever a split is allowed
+  e->tc_split = dv ? atoi(dv) : 0;
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
   const bool bytes = e->elem_bytes == 1;

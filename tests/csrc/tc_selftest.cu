@@ -28,16 +28,20 @@ struct Arena {
   void upload() { CKC(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice)); }
 };
 
-#ifndef DEEPT
-#define DEEPT true
-#endif
+static int g_nsm = 148;
+template <int BN, class Op>
+static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
+  using L = tc::Lay<BN, 2, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  static bool attr = false;
+  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
+  Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
+  const int MT = (o0.M + 127) / 128, NT = (o0.N + BN - 1) / BN, ntiles = MT * NT * nz * nsplit;
+  const int grid = ntiles < g_nsm ? ntiles : g_nsm;
+  tc::tc_gemm_kernel<BN, 2, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
+}
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
-  using L = tc::Lay<BN, Op::A_MCONTIG, !Op::B_KCONTIG, DEEPT>;
-  CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, true, DEEPT, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
-  Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
-  dim3 grid((o0.M + 127) / 128, (o0.N + BN - 1) / BN, nz * nsplit);
-  tc::tc_gemm_kernel<BN, 2, true, DEEPT, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero);
+  launch_tc_raw<BN>(op, nz, nsplit, ws, ws_stride, zero);
   CKC(cudaGetLastError());
   CKC(cudaDeviceSynchronize());
 }
@@ -146,10 +150,10 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   g.Xs = ar.d + oX; g.Ws = ar.d + oW; g.Cs = nullptr; g.lo_delta = ar.plane;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
-  using L = tc::Lay<BN, false, true, DEEPT>;
+  using L = tc::Lay<BN, 2, false, true>;
   dim3 grid((M + 127) / 128, (N + BN - 1) / BN, 1);
   cudaEventRecord(a);
-  for (int i = 0; i < iters; ++i) tc::tc_gemm_kernel<BN, 2, true, DEEPT, DenseFwdOp><<<grid, tc::THREADS, L::SMEM>>>(g, g, 1, nullptr, 0, ar.d);
+  for (int i = 0; i < iters; ++i) launch_tc_raw<BN>(g, 1, 1, nullptr, 0, ar.d);
   cudaEventRecord(b); CKC(cudaEventSynchronize(b));
   float ms; cudaEventElapsedTime(&ms, a, b);
   const double us = 1e3 * ms / iters, tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
@@ -157,27 +161,29 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   {
     std::vector<long long> tr(8192);
     CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 8192));
-    const int nk = (K + 31) / 32;
-    printf("  trace CTA0 (cycles, relative to first event): stage: P.loop P.empty-ok P.issued P.landed(prev) P.split-done(prev) | M.wait M.full-ok M.issued\n");
+    printf("  trace CTA0 (cycles rel. to first event): stage: P.loop P.empty-ok P.issued P.landed P.split-done | M.wait M.full-ok M.issued\n");
     const long long t0 = tr[0];
-    for (int it = 0; it < nk && it < 16; ++it) {
+    for (int it = 0; it < 40; ++it) {
       printf("  %2d:", it);
       for (int j = 0; j < 8; ++j) printf(" %7lld", tr[it * 8 + j] ? tr[it * 8 + j] - t0 : -1);
       printf("\n");
     }
+    std::vector<long long> z(8192, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 8192));
   }
 #endif
-  printf("bench dense M=%d N=%d K=%d BN=%d stages=%d ctas/SM=%d: %.1f us  %.1f TFLOP/s algorithmic (x3 = %.0f TF32)  grid %d\n", M, N, K, BN, L::STAGES, L::CTAS, us, tf, 3 * tf, grid.x * grid.y);
+  printf("bench dense M=%d N=%d K=%d BN=%d stages=%d depth=%d: %.1f us  %.1f TFLOP/s algorithmic (x3 = %.0f TF32)  grid %d\n", M, N, K, BN, L::STAGES, L::DEPTH, us, tf, 3 * tf, grid.x * grid.y);
   cudaFree(dW); cudaFree(dC); cudaFree(ar.d);
 }
 
 int main(int argc, char** argv) {
+  { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
-    bench_dense<64>(41472, 64, 512, 20);       // conv2 forward shape
-    bench_dense<64>(37888, 64, 512, 20);       // same, exactly one wave of 296 CTAs
-    bench_dense<32>(204800, 32, 256, 20);      // conv1 forward shape (with a lo plane here)
-    bench_dense<128>(512, 1024, 3136, 20);     // fc1 forward, both towers
-    bench_dense<128>(18944, 128, 512, 20);     // one wave of BN=128 tiles
+    const int it = argc > 2 ? atoi(argv[2]) : 20;
+    bench_dense<64>(41472, 64, 512, it);       // conv2 forward shape
+    bench_dense<64>(37888, 64, 512, it);       // same, exactly one wave of 296 CTAs
+    bench_dense<32>(204800, 32, 256, it);      // conv1 forward shape (with a lo plane here)
+    bench_dense<128>(512, 1024, 3136, it);     // fc1 forward, both towers
+    bench_dense<128>(18944, 128, 512, it);     // one wave of BN=128 tiles
     return 0;
   }
   printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
@@ -185,6 +191,7 @@ int main(int argc, char** argv) {
   printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
   printf("-- conv 4 img 20x20x8 -> 16, 4x4 s2 (BN=32)\n"); test_conv<32>(4, 20, 20, 8, 16, 4, 4, 2);
   printf("-- conv 3 img 9x9x32 -> 64, 3x3 s1 (BN=64)\n");  test_conv<64>(3, 9, 9, 32, 64, 3, 3, 1);
+  printf("-- dense M=39685 N=64 K=96 (BN=64, 311 tiles: several tiles per persistent CTA)\n"); test_dense<64>(39685, 64, 96);
   printf(fails ? "SELFTEST FAILED %d\n" : "SELFTEST OK\n", fails);
   return fails ? 1 : 0;
 }
