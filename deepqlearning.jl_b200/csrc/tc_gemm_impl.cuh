@@ -35,15 +35,16 @@ namespace tc {
 
 #ifdef TC_TRACE
 __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (producer warp 0 and the MMA warp): tuning aid of the selftest
-#define TRACE(slot) do { if (blockIdx.x == 0 && lane == 0 && (slot) < 8192) tc_trace[(slot)] = clock64(); } while (0)
+#define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 512) tc_trace[(st) * 16 + (ev)] = clock64(); } while (0)
 #else
-#define TRACE(slot) do { } while (0)
+#define TRACE(st, ev) do { } while (0)
 #endif
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
 constexpr int PROD_WARPS = 8;    // producer warps (cp.async + in-place split): short per-thread address chains, many loads in flight
 constexpr int PROD = 32 * PROD_WARPS;
+constexpr int NGRP = 2;          // producer groups (4 warps each) that take alternate stages
 constexpr int EPI_WARPS = 4;     // epilogue warps: warp & 3 = the TMEM lane quarter it may read
 constexpr int NMMA = 3;          // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
                                  // a single thread issues ~70-cycle tcgen05.mma, three streams keep the tensor core fed
@@ -67,28 +68,41 @@ template <int ROWS> struct Tile<ROWS, true> {                 // MN-major TF32: 
 
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-// One persistent CTA per SM.  The shared-memory ring holds STAGES slots of {A raw, A lo, B raw, B lo}; DEPTH stages of
-// cp.async traffic stay in flight behind the stage being split, across tile boundaries (the ring never drains between tiles).
-// TMEM holds NBUF accumulator sets of NACC x BN columns, so the epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int R, bool A_MN, bool B_MN> struct Lay {
-  using TA = Tile<BM, A_MN>;
+// A staging tile in shared memory (read back by the producers only, never by the tensor core): free-form, conflict-free both ways
+template <bool MN> struct AStage;
+template <> struct AStage<false> {                            // K-major source: row r (128 of them) = 32 floats + 16 bytes of padding
+  static constexpr int PITCH = BK * 4 + 16;
+  static constexpr int BYTES = BM * PITCH;
+};
+template <> struct AStage<true> {                             // MN-major source: k row kk (32 of them) = 128 floats + 16 bytes of padding
+  static constexpr int PITCH = BM * 4 + 16;
+  static constexpr int BYTES = BK * PITCH;
+};
+
+// One persistent CTA per SM.  Shared-memory ring: STAGES slots of {A staging, B raw(=hi), B lo}; DEPTH stages of cp.async traffic stay
+// in flight behind the stage being finished, across tile boundaries (the ring never drains between tiles).
+// TMEM (all 512 columns): NBUF accumulator sets of NACC x BN columns (the epilogue of tile i overlaps the main loop of tile i+1 when
+// NBUF = 2), then a ring of AST A-operand stages of 64 columns each (32 k-columns of the hi plane, 32 of the lo plane).
+template <int BN, int R, int NBUF, bool A_MN, bool B_MN> struct Lay {
   using TB = Tile<BN, B_MN>;
-  static constexpr int A_BYTES = (TA::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
-  static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // A_hi(raw), A_lo, B_hi(raw), B_lo
+  using SA = AStage<A_MN>;
+  static constexpr int A_BYTES = (SA::BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;            // A staging, B_hi(raw), B_lo
   static constexpr int TAIL = 1024 + 256;                              // alignment slack + barriers / tmem address
   static constexpr int FIT = (227 * 1024 - TAIL) / STAGE_BYTES;
-  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
-  static_assert(STAGES >= 3, "ring too shallow");
+  static constexpr int STAGES = (FIT > 8 ? 8 : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
+  static_assert(STAGES >= 6, "ring too shallow");
 #ifdef TC_EXP_DEPTH
   static constexpr int DEPTH = TC_EXP_DEPTH;
 #else
-  static constexpr int DEPTH = STAGES - 2;
+  static constexpr int DEPTH = STAGES >= 8 ? 2 : 1;                   // stages in flight per producer group behind the one it finishes
 #endif
   static constexpr int NACC = R + 2;                                   // R interleaved main accumulators + one per correction product
-  static constexpr int NBUF = (2 * NACC * BN <= 512) ? 2 : 1;
-  static constexpr int TCOLS = pow2_cols(NBUF * NACC * BN);
-  static_assert(NACC * BN <= 512, "TMEM columns");
+  static constexpr int ACC_COLS = NBUF * NACC * BN;
+  static constexpr int AST_FIT = (512 - ACC_COLS) / 64;
+  static constexpr int AST = 4;                                        // A-operand stages resident in TMEM
+  static_assert(AST_FIT >= AST && AST % NGRP == 0, "TMEM columns");
   static constexpr int SMEM = STAGES * STAGE_BYTES + TAIL;
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -108,12 +122,30 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   return ok;
 }
 // bounded wait: a protocol bug traps (context error, reported through the C-ABI) instead of hanging the GPU
+#ifndef TC_WAIT_IMPL
+#define TC_WAIT_IMPL 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if TC_WAIT_IMPL == 0
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   for (uint32_t spins = 1; !mbar_try(bar, parity); ++spins) {
     if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+#elif TC_WAIT_IMPL == 1
+  // tight loop: the try_wait itself suspends the warp for a hardware-defined interval, nothing else is issued between polls
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n"
+      "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D_%=;\n"
+      " add.u32 n, n, 1;\n setp.lt.u32 p, n, 0x4000000;\n @p bra W_%=;\n trap;\n"
+      "D_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+#else
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n"
+      "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n @p bra D_%=;\n"
+      " add.u32 n, n, 1;\n setp.lt.u32 p, n, 0x4000000;\n @p bra W_%=;\n trap;\n"
+      "D_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
@@ -139,6 +171,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
       " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from TMEM (lanes = rows, one fp32 k element per column), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -194,35 +244,38 @@ __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN, int R, class Op>
+template <int BN, int R, int NBUF, class Op>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, int nsplit, float* __restrict__ ws, long long ws_stride,
                const float* __restrict__ zero_src, int MT, int NT, int ntiles) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
-  using L = Lay<BN, R, A_MN, B_MN>;
-  using TA = typename L::TA;
+  using L = Lay<BN, R, NBUF, A_MN, B_MN>;
   using TB = typename L::TB;
-  constexpr int STAGES = L::STAGES, DEPTH = L::DEPTH, NACC = L::NACC, NBUF = L::NBUF;
+  using SA = typename L::SA;
+  constexpr int STAGES = L::STAGES, DEPTH = L::DEPTH, NACC = L::NACC, AST = L::AST;
+  constexpr uint32_t ACOL0 = L::ACC_COLS;                        // first TMEM column of the A-operand ring
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + STAGES * L::STAGE_BYTES;    // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]: 8 bytes each
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_accf = bar_empty + 8 * STAGES;
+  const uint32_t bar_full = sbase + STAGES * L::STAGE_BYTES;    // full[8], empty[8], aempty[4], acc_full[2], acc_empty[2]: 8 bytes each
+  const uint32_t bar_empty = bar_full + 64;
+  const uint32_t bar_aempty = bar_empty + 64;
+  const uint32_t bar_accf = bar_aempty + 32;
   const uint32_t bar_acce = bar_accf + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 16 * STAGES + 32);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 200);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool a_lo = !opa.a_single;
   constexpr int MMA_WARP0 = PROD_WARPS + EPI_WARPS;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, PROD_WARPS); mbar_init(bar_empty + 8 * s, NMMA); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, PROD_WARPS / NGRP); mbar_init(bar_empty + 8 * s, NMMA); }
+    for (int s = 0; s < AST; ++s) mbar_init(bar_aempty + 8 * s, NMMA);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP0) tmem_alloc<L::TCOLS>(smem_u32(tmem_slot));
+  if (warp == MMA_WARP0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,58 +300,88 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
   };
 
   if (warp < PROD_WARPS) {
-    // ================= producers: chunk addresses + cp.async, then the in-place split =================
-    constexpr int A_PER = BM * (BK / 4) / PROD;                // 4 chunks of A per thread per stage
-    constexpr int B_PER = BN * (BK / 4) / PROD;                // BN/32 chunks of B
-    uint32_t a_off[A_PER]; int a_kk[A_PER];
+    // ================= producers: NGRP groups of 4 warps, group g owns the stages with (stage index % NGRP) == g =================
+    // One stage costs a producer warp a serial chain of ~1000 cycles (addresses, cp.async, landing, shared -> registers -> TMEM);
+    // alternating groups overlap two such chains, which is what keeps the tensor core fed.
+    constexpr int GT = PROD / NGRP;                            // threads per group (128: one per row of the tile)
+    constexpr int A_PER = BM * (BK / 4) / GT;                  // 8 chunks of A per thread per stage
+    constexpr int B_PER = BN * (BK / 4) / GT;                  // BN/16 chunks of B
+    const int grp = warp >> 2, gtid = tid & (GT - 1);
+    uint32_t a_off[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-      if (A_MN) {                                              // lane = 16-byte chunk along the rows, k rows spread over warps / i
-        a_kk[i] = (tid >> 5) + PROD_WARPS * i;
-        a_off[i] = (lane >> 3) * TA::LBO + a_kk[i] * 128 + (((lane & 7) ^ ((a_kk[i] & 3) << 1)) * 16);   // 32-byte units XOR k row (SWIZZLE_128B_BASE32B)
-      } else {
-        const int r = (tid >> 3) + i * (PROD / 8);
-        a_kk[i] = (tid & 7) * 4;
-        a_off[i] = (tid & 7) * TA::LBO + (r >> 3) * TA::SBO + (r & 7) * 16;
-      }
+      if (A_MN) a_off[i] = ((gtid >> 5) + 4 * i) * SA::PITCH + lane * 16;       // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
+      else      a_off[i] = ((gtid >> 3) + i * (GT / 8)) * SA::PITCH + (gtid & 7) * 16;   // 8 lanes = the 128 contiguous bytes of one row
     }
     uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
-      const int e = tid + i * PROD;
+      const int e = gtid + i * GT;
       if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
-    // Per stage: (1) cp.async the RAW fp32 chunks into the hi-plane slots of ring slot `is`; (2) once DEPTH younger stages are in
-    // flight, finish the oldest: wait for this thread's own copies of it (cp.async.wait_group DEPTH), write lo = rna_tf32(x - trunc_tf32(x))
-    // of every chunk to the lo plane and hand the slot to the MMA warps.  The tensor core reads the top 19 bits of each fp32 word, so the
-    // raw tile already IS the hi plane.  Each thread only ever touches the chunks it copied itself, so no cross-thread synchronisation
-    // is needed before the split.  Global->shared traffic is the plain fp32 tensor, once.
+    // A reaches the tensor core through TMEM: row (q*32 + lane) of the tile is TMEM lane (q*32 + lane)
+    const int q4 = warp & 3;
+    const uint32_t a_rd = A_MN ? (uint32_t)((q4 * 32 + lane) * 4) : (uint32_t)((q4 * 32 + lane) * SA::PITCH);
+    const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0;
+    int as = grp % AST; uint32_t aph = 0;                       // TMEM A-ring slot / phase of this group's next stage to finish
+    int gtr = 0, ftr = 0; (void)gtr; (void)ftr;               // stage counters of trace builds
+    // finish the stage in ring slot s (the group's copies of it have landed and are visible - see the bar.sync before the call):
+    //   A: read this thread's row from the staging tile, write it as it is to the hi columns of the TMEM slot (the tensor core reads
+    //      the top 19 bits: hi = trunc_tf32(x)) and lo = rna_tf32(x - hi) to the lo columns;
+    //   B: write lo of the chunks this thread copied to the B lo plane (the raw plane is the hi plane);
+    //   then hand the stage to the MMA warps.
     auto finish_stage = [&](int s) {
-      const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
-      const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
-      float4 va[A_PER], vb[B_PER];
-#ifndef TC_EXP_NOSPLIT
-      if (a_lo) {
+      const uint32_t a_st = sbase + s * L::STAGE_BYTES;
+      const uint32_t b_hi = a_st + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+      uint32_t v[32];
+#ifdef TC_EXP_NOFIN
+      mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      as += NGRP; if (as >= AST) { as -= AST; aph ^= 1; }
+      return;
+#endif
+      if (A_MN) {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) va[i] = lds128(a_hi + a_off[i]);
+        for (int i = 0; i < 32; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 f = lds128(a_st + a_rd + i * 16);
+          v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
+        }
       }
+      float4 vb[B_PER];
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+      if (warp == 0) TRACE(ftr, 5);
+      mbar_wait(bar_aempty + 8 * as, aph ^ 1);                 // the MMAs that read this TMEM slot AST stages ago have retired
+      tc_fence_after();
+      if (warp == 0) TRACE(ftr, 6);
+      const uint32_t ta = a_tm + (uint32_t)(as * 64);
+      tmem_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
+      tmem_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
       if (a_lo) {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) sts128(a_lo_s + a_off[i], lo_of_trunc4(va[i]));
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
+        tmem_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
+        tmem_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
       }
 #pragma unroll
       for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+      tmem_st_wait();
+      if (warp == 0) TRACE(ftr, 7);
       fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's async proxy
-#endif
-      __syncwarp();                                            // one arrival per warp: 256 single arrivals on one barrier word serialise (~1100 clk per stage)
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (warp == 0) TRACE(ftr, 8);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);            // one arrival per warp of the group
+      as += NGRP; if (as >= AST) { as -= AST; aph ^= 1; }
     };
-    int is = 0; uint32_t iph = 0;                              // ring slot / phase of the next stage to issue
-    int fs = 0, inflight = 0;                                  // oldest unfinished slot, committed-but-unfinished stages
-    int gtr = 0; (void)gtr;                                    // global stage counter (trace builds only)
+    int is = grp; uint32_t iph = 0;                            // ring slot / phase of this group's next stage to issue
+    int fs = grp, inflight = 0;                                // its oldest unfinished slot, its committed-but-unfinished stages
+    int gg = 0;                                                // global stage counter (all tiles)
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
@@ -306,53 +389,51 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       if (A_MN) actx[0] = op.prepA(m0 + lane * 4);
       else {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (PROD / 8));
+        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (gtid >> 3) + i * (GT / 8));
       }
-      for (int it = 0; it < nk; ++it) {
+      for (int it = 0; it < nk; ++it, ++gg) {
+        if ((gg % NGRP) != grp) continue;
         const int k0 = (kt0 + it) * BK;
-        const uint32_t a_hi = sbase + is * L::STAGE_BYTES;
-        const uint32_t b_hi = a_hi + 2 * L::A_BYTES;
+        const uint32_t a_st = sbase + is * L::STAGE_BYTES;
+        const uint32_t b_hi = a_st + L::A_BYTES;
         KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
-        if (!A_MN) kc = op.prepK(k0 + a_kk[0]);                // K-major: this thread's k chunk is the same for all its rows
-        if (warp == 0) TRACE(gtr * 8 + 0);
+        if (!A_MN) kc = op.prepK(k0 + (gtid & 7) * 4);         // K-major: this thread's k chunk is the same for all its rows
+        if (warp == 0) TRACE(gg, 0);
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
-        if (warp == 0) TRACE(gtr * 8 + 1);
+        if (warp == 0) TRACE(gg, 1);
+#ifndef TC_EXP_NOLOAD
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
           const float* p;
-          if (A_MN) { const KCtx kq = op.prepK(k0 + a_kk[i]); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + a_kk[i]); }
-          else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (PROD / 8), k0 + a_kk[i]);
-#ifndef TC_EXP_NOLOAD
-          cp_async16(a_hi + a_off[i], p ? p : zero_src, p ? 16u : 0u);
-#else
-          if (p == (const float*)1) cp_async16(a_hi + a_off[i], p, 16u);
-#endif
+          if (A_MN) { const int kk = (gtid >> 5) + 4 * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
+          else p = op.ptrA(actx[i], kc, m0 + (gtid >> 3) + i * (GT / 8), k0 + (gtid & 7) * 4);
+          cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
         }
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) {
           const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
                                 : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
-#ifndef TC_EXP_NOLOAD
           cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
-#else
-          if (p == (const float*)1) cp_async16(b_hi + b_off[i], p, 16u);
-#endif
         }
+#endif
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (warp == 0) TRACE(gtr * 8 + 2);
-        if (++is == STAGES) { is = 0; iph ^= 1; }
+        if (warp == 0) TRACE(gg, 2);
+        is += NGRP; if (is >= STAGES) { is -= STAGES; iph ^= 1; }
         if (inflight == DEPTH) {
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
-          if (warp == 0) TRACE((gtr - DEPTH) * 8 + 3);
+          ftr = gg - DEPTH * NGRP;
+          if (warp == 0) TRACE(ftr, 3);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");    // every copy of the group's oldest stage has landed
+          if (warp == 0) TRACE(ftr, 4);
           finish_stage(fs);
-          if (warp == 0) TRACE((gtr - DEPTH) * 8 + 4);
-          if (++fs == STAGES) fs = 0;
+          if (warp == 0) TRACE(ftr, 9);
+          fs += NGRP; if (fs >= STAGES) fs -= STAGES;
         } else ++inflight;
-        ++gtr;
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    for (; inflight > 0; --inflight) { finish_stage(fs); if (++fs == STAGES) fs = 0; }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");
+    for (; inflight > 0; --inflight) { finish_stage(fs); fs += NGRP; if (fs >= STAGES) fs -= STAGES; }
   } else if (warp < MMA_WARP0) {
     // ================= epilogue: TMEM -> registers -> bias/activation or act' -> 16-byte stores =================
     const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
@@ -364,6 +445,9 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       tc_fence_after();
       const int m = m0 + q4 * 32 + lane;
       const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NACC * BN);
+#ifdef TC_EXP_NOEPI
+      if (m0 < 0)
+#endif
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
@@ -405,16 +489,17 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       }
       tc_fence_before();                                       // this warp's tcgen05.ld are complete (wait::ld) and ordered before the arrive
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);          // accumulator set free for the tile after next
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);          // accumulator set free again
       if (++buf == NBUF) { buf = 0; aph ^= 1; }
     }
   } else {
     // ================= MMA issuers =================
-    constexpr uint32_t idesc = make_idesc2(BM, BN, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc2(BM, BN, false, B_MN);   // A comes from TMEM: K-major by construction
     const int role = warp - MMA_WARP0;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
     int s = 0; uint32_t ph = 0;
-    int buf = 0; uint32_t aph = 0;
+    int as = 0;
     int gtr = 0; (void)gtr;
+    int buf = 0; uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
@@ -422,32 +507,35 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       tc_fence_after();
       const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
       for (int it = 0; it < nk; ++it) {
-        if (role == 0) TRACE(gtr * 8 + 5);
+        if (role == 0) TRACE(gtr, 11);
         mbar_wait(bar_full + 8 * s, ph);
-        if (role == 0) TRACE(gtr * 8 + 6);
+        if (role == 0) TRACE(gtr, 12);
         tc_fence_after();
         if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
-          const uint32_t a_hi = sbase + s * L::STAGE_BYTES, a_lo_s = a_hi + L::A_BYTES;
-          const uint32_t b_hi = a_lo_s + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
-          constexpr uint32_t LTA = A_MN ? 1u : 0u, LTB = B_MN ? 1u : 0u;      // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
+          const uint32_t b_hi = sbase + s * L::STAGE_BYTES + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+          const uint32_t a_hi_t = tmem + ACOL0 + (uint32_t)(as * 64), a_lo_t = a_hi_t + 32;
+          constexpr uint32_t LTB = B_MN ? 1u : 0u;               // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dah = make_desc(a_hi + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
-            const uint64_t dal = make_desc(a_lo_s + j * TA::KSTEP, TA::LBO, TA::SBO, LTA);
             const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
             const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
             const int ks = it * (BK / 8) + j;                     // k-step index within this tile
-            if (role == 0) umma_tf32(acc + (uint32_t)((ks % R) * BN), dah, dbh, idesc, ks >= R ? 1u : 0u);
-            else if (role == 1) { if (a_lo) umma_tf32(acc + (uint32_t)(R * BN), dal, dbh, idesc, ks > 0 ? 1u : 0u); }
-            else umma_tf32(acc + (uint32_t)((R + 1) * BN), dah, dbl, idesc, ks > 0 ? 1u : 0u);
+#ifdef TC_EXP_NOMMA
+            if (ks < 0)
+#endif
+            if (role == 0) umma_tf32_ts(acc + (uint32_t)((ks % R) * BN), a_hi_t + j * 8, dbh, idesc, ks >= R ? 1u : 0u);
+            else if (role == 1) { if (a_lo) umma_tf32_ts(acc + (uint32_t)(R * BN), a_lo_t + j * 8, dbh, idesc, ks > 0 ? 1u : 0u); }
+            else umma_tf32_ts(acc + (uint32_t)((R + 1) * BN), a_hi_t + j * 8, dbl, idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * s);                         // frees the smem slot when these MMAs retire
+          umma_commit(bar_empty + 8 * s);                         // frees the smem slot when these MMAs retire ...
+          umma_commit(bar_aempty + 8 * as);                       // ... and the TMEM A slot
           if (it == nk - 1) umma_commit(bar_accf + 8 * buf);      // ... and publishes the accumulators after the tile's last stage
         }
         __syncwarp();
-        if (role == 0) TRACE(gtr * 8 + 7);
+        if (role == 0) TRACE(gtr, 13);
         ++gtr;
         if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++as == AST) as = 0;
       }
       if (nk == 0 && lane == 0) mbar_arrive(bar_accf + 8 * buf);   // one arrival per MMA warp
       if (++buf == NBUF) { buf = 0; aph ^= 1; }
@@ -455,7 +543,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == MMA_WARP0) { tc_fence_after(); tmem_dealloc<L::TCOLS>(tmem); }
+  if (warp == MMA_WARP0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
 }
 
 }  // namespace tc
@@ -463,23 +551,23 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
 #ifndef TC_KERNEL_ONLY
 namespace {
 
-template <int BN, class Op>
-void tc_launch_bn(dqn_engine* e, const Op& a, const Op& b, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
-  using L = tc::Lay<BN, 2, Op::A_MCONTIG, !Op::B_KCONTIG>;
+template <int BN, int R, int NBUF, class Op>
+void tc_launch_v(dqn_engine* e, const Op& a, const Op& b, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
+  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set = true;
   }
   const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
-  tc::tc_gemm_kernel<BN, 2, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
+  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
   CK(cudaGetLastError());
 }
 
 // k split of a contraction whose tile count does not fill the machine (or whose k extent dwarfs its output, the weight gradients):
 // minimise a rough time model - rounds of tiles over the SMs x stages per tile, plus the reduction pass over the partial outputs
 int tc_pick_split(dqn_engine* e, long long tiles0, int ktiles, int bn, long long out_elems, int nz) {
-  const double stage_us = bn == 128 ? 0.70 : (bn == 64 ? 0.45 : 0.32), tile_us = 1.5;
+  const double stage_us = bn == 64 ? 0.33 : 0.22, tile_us = 1.0;
   int best = 1; double best_t = 1e30;
   const int max_ns = std::max(1, std::min(64, ktiles / 4));
   for (int ns = 1; ns <= max_ns; ++ns) {
@@ -503,7 +591,7 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   int M = a0.M, N = a0.N, K = a0.K;
   if (!Op::Z_IS_CLASS && nz == 2) { M = std::max(M, b.M); N = std::max(N, b.N); K = std::max(K, b.K); }
   if (M < 64 || N < 24 || K < 32) return false;                 // small / odd layers stay on the fp32 CUDA-core kernel
-  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  const int bn = N <= 32 ? 32 : 64;
   const int MT = (M + tc::BM - 1) / tc::BM, NT = (N + bn - 1) / bn;
   const long long tiles0 = (long long)MT * NT * nz;
   const int ktiles = (K + tc::BK - 1) / tc::BK;
@@ -514,9 +602,12 @@ bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_s
   const int ntiles = (int)(tiles0 * nsplit);
   {
     Scope sc(e, name, flops, bytes);
-    if (bn == 32) tc_launch_bn<32, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
-    else if (bn == 64) tc_launch_bn<64, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
-    else tc_launch_bn<128, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
+    // short k loops: two accumulator sets (overlapped epilogue) and a single main accumulator - at most ~150 truncating adds per
+    // output; long k loops: the main product interleaved over two accumulators, one set (the epilogue is a small fraction there)
+    const int ksteps = ((ktiles + nsplit - 1) / nsplit) * (tc::BK / 8);
+    (void)ksteps;
+    if (bn == 32) tc_launch_v<32, 2, 2, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
+    else tc_launch_v<64, 2, 1, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);

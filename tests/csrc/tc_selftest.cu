@@ -28,16 +28,20 @@ struct Arena {
   void upload() { CKC(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice)); }
 };
 
+#ifndef TEST_R
+#define TEST_R 2
+#endif
 static int g_nsm = 148;
 template <int BN, class Op>
 static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
-  using L = tc::Lay<BN, 2, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  constexpr int R = BN == 32 ? 2 : TEST_R, NBUF = BN == 32 ? 2 : (TEST_R == 1 ? 2 : 1);
+  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
   static bool attr = false;
-  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, 2, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
+  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
   Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
   const int MT = (o0.M + 127) / 128, NT = (o0.N + BN - 1) / BN, ntiles = MT * NT * nz * nsplit;
   const int grid = ntiles < g_nsm ? ntiles : g_nsm;
-  tc::tc_gemm_kernel<BN, 2, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
+  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
 }
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
@@ -150,7 +154,7 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   g.Xs = ar.d + oX; g.Ws = ar.d + oW; g.Cs = nullptr; g.lo_delta = ar.plane;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
-  using L = tc::Lay<BN, 2, false, true>;
+  using L = tc::Lay<BN, BN == 32 ? 2 : TEST_R, BN == 32 ? 2 : (TEST_R == 1 ? 2 : 1), false, true>;
   dim3 grid((M + 127) / 128, (N + BN - 1) / BN, 1);
   cudaEventRecord(a);
   for (int i = 0; i < iters; ++i) launch_tc_raw<BN>(g, 1, 1, nullptr, 0, ar.d);
@@ -161,11 +165,11 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   {
     std::vector<long long> tr(8192);
     CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 8192));
-    printf("  trace CTA0 (cycles rel. to first event): stage: P.loop P.empty-ok P.issued P.landed P.split-done | M.wait M.full-ok M.issued\n");
+    printf("  trace CTA0: stage: P.top empty-ok issued | landed bar-ok | fin:lds'd aempty-ok st-waited fenced done | gap | M.wait full-ok issued\n");
     const long long t0 = tr[0];
-    for (int it = 0; it < 40; ++it) {
+    for (int it = 8; it < 36; ++it) {
       printf("  %2d:", it);
-      for (int j = 0; j < 8; ++j) printf(" %7lld", tr[it * 8 + j] ? tr[it * 8 + j] - t0 : -1);
+      for (int j = 0; j < 14; ++j) { if (j == 10) continue; printf(" %7lld", tr[it * 16 + j] ? tr[it * 16 + j] - t0 : -1); }
       printf("\n");
     }
     std::vector<long long> z(8192, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 8192));
@@ -182,16 +186,17 @@ int main(int argc, char** argv) {
     bench_dense<64>(41472, 64, 512, it);       // conv2 forward shape
     bench_dense<64>(37888, 64, 512, it);       // same, exactly one wave of 296 CTAs
     bench_dense<32>(204800, 32, 256, it);      // conv1 forward shape (with a lo plane here)
-    bench_dense<128>(512, 1024, 3136, it);     // fc1 forward, both towers
-    bench_dense<128>(18944, 128, 512, it);     // one wave of BN=128 tiles
+    bench_dense<64>(512, 1024, 3136, it);      // fc1 forward, both towers (64 tiles, no k split here)
+    bench_dense<64>(18944, 128, 512, it);      // two waves of BN=64 tiles
     return 0;
   }
   printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
-  printf("-- dense M=200 N=128 K=160 (BN=128)\n"); test_dense<128>(200, 128, 160);
+  printf("-- dense M=200 N=128 K=160 (BN=64, two n tiles)\n"); test_dense<64>(200, 128, 160);
   printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
   printf("-- conv 4 img 20x20x8 -> 16, 4x4 s2 (BN=32)\n"); test_conv<32>(4, 20, 20, 8, 16, 4, 4, 2);
   printf("-- conv 3 img 9x9x32 -> 64, 3x3 s1 (BN=64)\n");  test_conv<64>(3, 9, 9, 32, 64, 3, 3, 1);
   printf("-- dense M=39685 N=64 K=96 (BN=64, 311 tiles: several tiles per persistent CTA)\n"); test_dense<64>(39685, 64, 96);
+  printf("-- conv 2 img 84x84x4 -> 32, 8x8 s4 (BN=32, conv1 geometry)\n"); test_conv<32>(2, 84, 84, 4, 32, 8, 8, 4);
   printf(fails ? "SELFTEST FAILED %d\n" : "SELFTEST OK\n", fails);
   return fails ? 1 : 0;
 }
