@@ -42,13 +42,15 @@ __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (produ
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-constexpr int PROD_WARPS = 8;    // producer warps (cp.async + in-place split): short per-thread address chains, many loads in flight
-constexpr int PROD = 32 * PROD_WARPS;
-constexpr int NGRP = 2;          // producer groups (4 warps each) that take alternate stages
+constexpr int LOAD_WARPS = 4;    // loader warps: chunk addresses + cp.async only (an LDGSTS that waits for a queue slot blocks nothing else)
+constexpr int LOADERS = 32 * LOAD_WARPS;
+constexpr int NGRP = 2;          // converter groups (4 warps each: one per TMEM lane quarter) that take alternate stages
+constexpr int CONV_WARPS = 4 * NGRP;
 constexpr int EPI_WARPS = 4;     // epilogue warps: warp & 3 = the TMEM lane quarter it may read
 constexpr int NMMA = 3;          // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
-                                 // a single thread issues ~70-cycle tcgen05.mma, three streams keep the tensor core fed
-constexpr int THREADS = PROD + 32 * EPI_WARPS + 32 * NMMA;      // 480: warps 0-7 producers, 8-11 epilogue, 12-14 MMA
+                                 // one thread can issue a tcgen05 instruction every ~75 cycles, three streams keep the tensor core fed
+constexpr int CONV_WARP0 = LOAD_WARPS, EPI_WARP0 = CONV_WARP0 + CONV_WARPS, MMA_WARP0 = EPI_WARP0 + EPI_WARPS;
+constexpr int THREADS = 32 * (MMA_WARP0 + NMMA);              // 608: warps 0-3 loaders, 4-11 converters, 12-15 epilogue, 16-18 MMA
 
 // shared-memory tile of one operand plane for one stage
 template <int ROWS, bool MN> struct Tile;
@@ -93,11 +95,6 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN> struct Lay {
   static constexpr int FIT = (227 * 1024 - TAIL) / STAGE_BYTES;
   static constexpr int STAGES = (FIT > 8 ? 8 : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
   static_assert(STAGES >= 6, "ring too shallow");
-#ifdef TC_EXP_DEPTH
-  static constexpr int DEPTH = TC_EXP_DEPTH;
-#else
-  static constexpr int DEPTH = STAGES >= 8 ? 2 : 1;                   // stages in flight per producer group behind the one it finishes
-#endif
   static constexpr int NACC = R + 2;                                   // R interleaved main accumulators + one per correction product
   static constexpr int ACC_COLS = NBUF * NACC * BN;
   static constexpr int AST_FIT = (512 - ACC_COLS) / 64;
@@ -122,6 +119,9 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   return ok;
 }
 // bounded wait: a protocol bug traps (context error, reported through the C-ABI) instead of hanging the GPU
+#ifndef TC_EPI_UNROLL
+#define TC_EPI_UNROLL 1
+#endif
 #ifndef TC_WAIT_IMPL
 #define TC_WAIT_IMPL 1
 #endif
@@ -138,6 +138,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n"
       "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D_%=;\n"
       " add.u32 n, n, 1;\n setp.lt.u32 p, n, 0x4000000;\n @p bra W_%=;\n trap;\n"
+      "D_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+#elif TC_WAIT_IMPL == 3
+  // non-suspending poll
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n"
+      "W_%=:\n mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D_%=;\n"
+      " add.u32 n, n, 1;\n setp.lt.u32 p, n, 0x10000000;\n @p bra W_%=;\n trap;\n"
       "D_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
 #else
   asm volatile(
@@ -189,6 +196,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -252,26 +265,24 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
   using L = Lay<BN, R, NBUF, A_MN, B_MN>;
   using TB = typename L::TB;
   using SA = typename L::SA;
-  constexpr int STAGES = L::STAGES, DEPTH = L::DEPTH, NACC = L::NACC, AST = L::AST;
+  constexpr int STAGES = L::STAGES, NACC = L::NACC, AST = L::AST;
   constexpr uint32_t ACOL0 = L::ACC_COLS;                        // first TMEM column of the A-operand ring
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + STAGES * L::STAGE_BYTES;    // full[8], empty[8], aempty[4], acc_full[2], acc_empty[2]: 8 bytes each
+  const uint32_t bar_landed = sbase + STAGES * L::STAGE_BYTES;  // landed[8], full[8], empty[8], acc_full[2], acc_empty[2]: 8 bytes each
+  const uint32_t bar_full = bar_landed + 64;
   const uint32_t bar_empty = bar_full + 64;
-  const uint32_t bar_aempty = bar_empty + 64;
-  const uint32_t bar_accf = bar_aempty + 32;
+  const uint32_t bar_accf = bar_empty + 64;
   const uint32_t bar_acce = bar_accf + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 200);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 232);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool a_lo = !opa.a_single;
-  constexpr int MMA_WARP0 = PROD_WARPS + EPI_WARPS;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, PROD_WARPS / NGRP); mbar_init(bar_empty + 8 * s, NMMA); }
-    for (int s = 0; s < AST; ++s) mbar_init(bar_aempty + 8 * s, NMMA);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, LOADERS); mbar_init(bar_full + 8 * s, 4); mbar_init(bar_empty + 8 * s, NMMA); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -298,90 +309,31 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     nk = max(min(ktiles, kt0 + per) - kt0, 0);
     return true;
   };
+  // light version for the roles that only need the k extent
+  auto decode_nk = [&](int t, int& nk) -> bool {
+    Op op; int m0, n0, zs, kt0;
+    return decode(t, op, m0, n0, zs, kt0, nk);
+  };
 
-  if (warp < PROD_WARPS) {
-    // ================= producers: NGRP groups of 4 warps, group g owns the stages with (stage index % NGRP) == g =================
-    // One stage costs a producer warp a serial chain of ~1000 cycles (addresses, cp.async, landing, shared -> registers -> TMEM);
-    // alternating groups overlap two such chains, which is what keeps the tensor core fed.
-    constexpr int GT = PROD / NGRP;                            // threads per group (128: one per row of the tile)
-    constexpr int A_PER = BM * (BK / 4) / GT;                  // 8 chunks of A per thread per stage
-    constexpr int B_PER = BN * (BK / 4) / GT;                  // BN/16 chunks of B
-    const int grp = warp >> 2, gtid = tid & (GT - 1);
+  constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
+  if (warp < LOAD_WARPS) {
+    // ================= loaders: chunk addresses + cp.async into ring slot, completion signalled on landed[slot] =================
+    constexpr int A_PER = BM * (BK / 4) / LOADERS;             // 8 chunks of A per thread per stage
+    constexpr int B_PER = B_CH / LOADERS;                      // BN/16 chunks of B
     uint32_t a_off[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-      if (A_MN) a_off[i] = ((gtid >> 5) + 4 * i) * SA::PITCH + lane * 16;       // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
-      else      a_off[i] = ((gtid >> 3) + i * (GT / 8)) * SA::PITCH + (gtid & 7) * 16;   // 8 lanes = the 128 contiguous bytes of one row
+      if (A_MN) a_off[i] = ((tid >> 5) + 4 * i) * SA::PITCH + lane * 16;        // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
+      else      a_off[i] = ((tid >> 3) + i * (LOADERS / 8)) * SA::PITCH + (tid & 7) * 16;   // 8 lanes = the 128 contiguous bytes of one row
     }
     uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
-      const int e = gtid + i * GT;
+      const int e = tid + i * LOADERS;
       if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
-    // A reaches the tensor core through TMEM: row (q*32 + lane) of the tile is TMEM lane (q*32 + lane)
-    const int q4 = warp & 3;
-    const uint32_t a_rd = A_MN ? (uint32_t)((q4 * 32 + lane) * 4) : (uint32_t)((q4 * 32 + lane) * SA::PITCH);
-    const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0;
-    int as = grp % AST; uint32_t aph = 0;                       // TMEM A-ring slot / phase of this group's next stage to finish
-    int gtr = 0, ftr = 0; (void)gtr; (void)ftr;               // stage counters of trace builds
-    // finish the stage in ring slot s (the group's copies of it have landed and are visible - see the bar.sync before the call):
-    //   A: read this thread's row from the staging tile, write it as it is to the hi columns of the TMEM slot (the tensor core reads
-    //      the top 19 bits: hi = trunc_tf32(x)) and lo = rna_tf32(x - hi) to the lo columns;
-    //   B: write lo of the chunks this thread copied to the B lo plane (the raw plane is the hi plane);
-    //   then hand the stage to the MMA warps.
-    auto finish_stage = [&](int s) {
-      const uint32_t a_st = sbase + s * L::STAGE_BYTES;
-      const uint32_t b_hi = a_st + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
-      uint32_t v[32];
-#ifdef TC_EXP_NOFIN
-      mbar_wait(bar_aempty + 8 * as, aph ^ 1);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      as += NGRP; if (as >= AST) { as -= AST; aph ^= 1; }
-      return;
-#endif
-      if (A_MN) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 f = lds128(a_st + a_rd + i * 16);
-          v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
-        }
-      }
-      float4 vb[B_PER];
-#pragma unroll
-      for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
-      if (warp == 0) TRACE(ftr, 5);
-      mbar_wait(bar_aempty + 8 * as, aph ^ 1);                 // the MMAs that read this TMEM slot AST stages ago have retired
-      tc_fence_after();
-      if (warp == 0) TRACE(ftr, 6);
-      const uint32_t ta = a_tm + (uint32_t)(as * 64);
-      tmem_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-      tmem_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
-      if (a_lo) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
-        tmem_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-        tmem_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
-      }
-#pragma unroll
-      for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
-      tmem_st_wait();
-      if (warp == 0) TRACE(ftr, 7);
-      fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's async proxy
-      if (warp == 0) TRACE(ftr, 8);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);            // one arrival per warp of the group
-      as += NGRP; if (as >= AST) { as -= AST; aph ^= 1; }
-    };
-    int is = grp; uint32_t iph = 0;                            // ring slot / phase of this group's next stage to issue
-    int fs = grp, inflight = 0;                                // its oldest unfinished slot, its committed-but-unfinished stages
-    int gg = 0;                                                // global stage counter (all tiles)
+    int is = 0; uint32_t iph = 0;                              // ring slot / phase of the next stage
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
@@ -389,24 +341,21 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       if (A_MN) actx[0] = op.prepA(m0 + lane * 4);
       else {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (gtid >> 3) + i * (GT / 8));
+        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (LOADERS / 8));
       }
-      for (int it = 0; it < nk; ++it, ++gg) {
-        if ((gg % NGRP) != grp) continue;
+      for (int it = 0; it < nk; ++it) {
         const int k0 = (kt0 + it) * BK;
         const uint32_t a_st = sbase + is * L::STAGE_BYTES;
         const uint32_t b_hi = a_st + L::A_BYTES;
         KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
-        if (!A_MN) kc = op.prepK(k0 + (gtid & 7) * 4);         // K-major: this thread's k chunk is the same for all its rows
-        if (warp == 0) TRACE(gg, 0);
+        if (!A_MN) kc = op.prepK(k0 + (tid & 7) * 4);          // K-major: this thread's k chunk is the same for all its rows
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
-        if (warp == 0) TRACE(gg, 1);
 #ifndef TC_EXP_NOLOAD
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
           const float* p;
-          if (A_MN) { const int kk = (gtid >> 5) + 4 * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
-          else p = op.ptrA(actx[i], kc, m0 + (gtid >> 3) + i * (GT / 8), k0 + (gtid & 7) * 4);
+          if (A_MN) { const int kk = (tid >> 5) + 4 * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
+          else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
           cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
         }
 #pragma unroll
@@ -416,27 +365,92 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
           cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
         }
 #endif
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (warp == 0) TRACE(gg, 2);
-        is += NGRP; if (is >= STAGES) { is -= STAGES; iph ^= 1; }
-        if (inflight == DEPTH) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
-          ftr = gg - DEPTH * NGRP;
-          if (warp == 0) TRACE(ftr, 3);
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");    // every copy of the group's oldest stage has landed
-          if (warp == 0) TRACE(ftr, 4);
-          finish_stage(fs);
-          if (warp == 0) TRACE(ftr, 9);
-          fs += NGRP; if (fs >= STAGES) fs -= STAGES;
-        } else ++inflight;
+        // the barrier receives this thread's arrival once all of its copies above have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_landed + 8 * is) : "memory");
+        if (++is == STAGES) { is = 0; iph ^= 1; }
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");
-    for (; inflight > 0; --inflight) { finish_stage(fs); fs += NGRP; if (fs >= STAGES) fs -= STAGES; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < EPI_WARP0) {
+    // ================= converters: group g owns the stages with (stage index % NGRP) == g =================
+    //   A: shared-memory staging tile -> registers (one row per thread) -> TMEM: the raw words are the hi plane (the tensor core reads
+    //      the top 19 bits: hi = trunc_tf32(x)), lo = rna_tf32(x - hi) goes to the lo columns;
+    //   B: lo of the raw plane -> B lo plane; then the stage is handed to the MMA warps.
+    // One stage is a serial chain of several hundred cycles for a warp (wait, LDS, split, tcgen05.st, wait::st, fences); two groups
+    // working on alternate stages overlap two such chains.
+    constexpr int GT = 128;                                    // threads per group: one per row of the tile
+    constexpr int B_PER = B_CH / GT;
+    const int cw = warp - CONV_WARP0, grp = cw >> 2, gtid = tid - 32 * CONV_WARP0 - grp * GT;
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    uint32_t b_off[B_PER];
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = gtid + i * GT;
+      if (B_MN) { const int g = e % (BN / 4), kk = e / (BN / 4); b_off[i] = (g >> 3) * TB::LBO + kk * 128 + (((g & 7) ^ ((kk & 3) << 1)) * 16); }
+      else      { const int r = e >> 3; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
+    }
+    const uint32_t a_rd = A_MN ? (uint32_t)(row * 4) : (uint32_t)(row * SA::PITCH);
+    const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0;
+    int gg = 0;                                                // global stage counter (all tiles)
+    int s = grp; uint32_t ph = 0;                              // ring slot / phase of this group's next stage
+    int as = grp % AST;                                        // its TMEM A-ring slot
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int nk;
+      if (!decode_nk(t, nk)) continue;
+      for (int it = 0; it < nk; ++it, ++gg) {
+        if ((gg % NGRP) != grp) continue;
+        const uint32_t a_st = sbase + s * L::STAGE_BYTES;
+        const uint32_t b_hi = a_st + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
+        mbar_wait(bar_landed + 8 * s, ph);                     // every loader's copies of this stage have landed
+#ifndef TC_EXP_NOFIN
+        uint32_t v[32];
+        if (A_MN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = lds128(a_st + a_rd + i * 16);
+            v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
+          }
+        }
+        float4 vb[B_PER];
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+#endif
+        // TMEM slot `as` was read by the MMAs of stage gg - AST: their retirement is a completed phase of that stage's empty barrier
+        if (gg >= AST) {
+          const int g0 = gg - AST;
+          mbar_wait(bar_empty + 8 * (g0 % STAGES), (uint32_t)((g0 / STAGES) & 1));
+        }
+        tc_fence_after();
+#ifndef TC_EXP_NOFIN
+        const uint32_t ta = a_tm + (uint32_t)(as * 64);
+        tmem_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
+        tmem_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+        if (a_lo) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
+          tmem_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
+          tmem_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+        tmem_st_wait();
+        fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core's async proxy
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);          // one arrival per warp of the group
+        s += NGRP; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+        as += NGRP; if (as >= AST) as -= AST;
+      }
+    }
   } else if (warp < MMA_WARP0) {
     // ================= epilogue: TMEM -> registers -> bias/activation or act' -> 16-byte stores =================
     const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
+    constexpr int EPI_UNROLL = TC_EPI_UNROLL;                  // column chunks in flight: their bias / act' loads overlap
     int buf = 0; uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
@@ -448,18 +462,23 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
 #ifdef TC_EXP_NOEPI
       if (m0 < 0)
 #endif
-#pragma unroll 1
+#pragma unroll EPI_UNROLL
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
         if (nk > 0) {
-          tmem_ld16(tb + c0, r);
+          uint32_t q[NACC - 1][16];
+          tmem_ld16_nowait(tb + c0, r);
+#pragma unroll
+          for (int a = 1; a < NACC; ++a) {
+            if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
+            tmem_ld16_nowait(tb + a * BN + c0, q[a - 1]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
-            if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
-            uint32_t q[16];
-            tmem_ld16(tb + a * BN + c0, q);
+            if (a == R && !a_lo) continue;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[a - 1][j])));
           }
         } else {
 #pragma unroll
@@ -498,7 +517,6 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     const int role = warp - MMA_WARP0;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
     int s = 0; uint32_t ph = 0;
     int as = 0;
-    int gtr = 0; (void)gtr;
     int buf = 0; uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
@@ -507,9 +525,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
       tc_fence_after();
       const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
       for (int it = 0; it < nk; ++it) {
-        if (role == 0) TRACE(gtr, 11);
         mbar_wait(bar_full + 8 * s, ph);
-        if (role == 0) TRACE(gtr, 12);
         tc_fence_after();
         if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
           const uint32_t b_hi = sbase + s * L::STAGE_BYTES + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
@@ -527,13 +543,10 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
             else if (role == 1) { if (a_lo) umma_tf32_ts(acc + (uint32_t)(R * BN), a_lo_t + j * 8, dbh, idesc, ks > 0 ? 1u : 0u); }
             else umma_tf32_ts(acc + (uint32_t)((R + 1) * BN), a_hi_t + j * 8, dbl, idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * s);                         // frees the smem slot when these MMAs retire ...
-          umma_commit(bar_aempty + 8 * as);                       // ... and the TMEM A slot
+          umma_commit(bar_empty + 8 * s);                         // frees the smem slot and the TMEM A slot when these MMAs retire ...
           if (it == nk - 1) umma_commit(bar_accf + 8 * buf);      // ... and publishes the accumulators after the tile's last stage
         }
         __syncwarp();
-        if (role == 0) TRACE(gtr, 13);
-        ++gtr;
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++as == AST) as = 0;
       }

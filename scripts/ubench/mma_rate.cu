@@ -10,13 +10,6 @@ using namespace dqn;
 using namespace tc;
 
 // mode 0: K-major no-swizzle (LBO padded), 1: K-major no-swizzle (LBO unpadded), 2: K-major SWIZZLE_128B, 3: A from TMEM
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 template <int N>
 __global__ void mma_rate(int iters, int issuers, int mode, int nacc, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -63,19 +56,20 @@ __global__ void mma_rate(int iters, int issuers, int mode, int nacc, long long* 
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
 }
 
-template <int N> void run(int issuers, int mode, int nacc, int ctas) {
+template <int N> void run(int issuers, int mode, int nacc, int ctas, int iters = 2000) {
   long long* d; cudaMalloc(&d, 64); cudaMemset(d, 0, 64);
-  const int iters = 2000;
   cudaFuncSetAttribute(mma_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   mma_rate<N><<<ctas, 128, 200 * 1024>>>(iters, issuers, mode, nacc, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+  if (iters < 100) { printf("N=%3d issuers=%d mode=%d iters=%d: issue %lld clk, issue+commit->barrier complete %lld clk\n", N, issuers, mode, iters, h[0], h[1]); cudaFree(d); return; }
   printf("N=%3d issuers=%d mode=%d nacc=%d ctas=%3d: %s  per-MMA (all issuers): %.1f clk  [issue-only %.1f clk]\n", N, issuers, mode, nacc, ctas,
          cudaGetErrorString(e), (double)h[1] / (iters * 4.0 * issuers), (double)h[0] / (iters * 4.0));
   cudaFree(d);
 }
 
 int main() {
+  for (int it = 0; it < 5; ++it) { run<64>(1, 3, 1, 1, it); run<64>(3, 3, 1, 1, it); }
   for (int mode = 0; mode < 4; mode += 3) {
     run<32>(1, mode, 1, 1); run<32>(2, mode, 1, 1); run<32>(3, mode, 1, 1); run<32>(3, mode, 1, 148);
     run<64>(1, mode, 1, 1); run<64>(2, mode, 1, 1); run<64>(3, mode, 1, 1); run<64>(3, mode, 2, 1);
