@@ -75,6 +75,7 @@ struct ConvL { ConvGeom g; Mat w; };
 struct ProfRec { cudaEvent_t a, b; std::string name; double flops, bytes; };
 
 constexpr int MAXD = DQN_MAX_LAYERS;
+constexpr int COLSUM_CTAS = 296;
 
 struct ActBufs {
   std::vector<float*> conv_out;
@@ -139,6 +140,7 @@ struct dqn_engine {
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
   int tc_split = 0;
+  float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
 };
 
 namespace {
@@ -360,10 +362,20 @@ void backward(E* e, bool conc) {
     double by = (double)B * c.g.IH * c.g.IW * c.g.Cin * (wg.x_u8 ? 1 : 4) + 4.0 * wg.K * wg.N + 4.0 * wg.M * wg.N;
     ConvWgradOp wg_tc = wg;                    // the tensor-core operand holds raw byte values: fold the 1/255 into its epilogue only
     wg_tc.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
+    // a bias row that would open a 128-row tile of its own (257 = 2 x 128 + 1 rows in the first layer) is summed by colsum_kernel instead
+    const bool split_bias = e->arena && (c.w.K % 128 == 0) && c.w.K <= 256 && (c.g.Cout % 4 == 0) && c.g.Cout <= 1024;   // worth a launch only when it saves >= 1/3 of the tiles
+    if (split_bias) { wg_tc.M = c.w.K; wg_tc.no_bias = 1; }
     {
       if (conc) order_after(e, e->stream2, e->stream);
       Lane lane(e, conc);
       if (!tc_conv_wgrad(e, nm, wg_tc, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
+      else if (split_bias) {
+        snprintf(nm, sizeof nm, "conv%d_bgrad", l + 1);
+        Scope sc(e, nm, 0, 4.0 * wg.K * wg.N);
+        colsum_kernel<<<COLSUM_CTAS, 256, 0, e->ls>>>(e->conv_delta[l], (long long)wg.K, wg.N, e->grad + c.w.off + (long long)c.w.K * c.g.Cout,
+                                                     e->colsum_part + (e->ls == e->stream ? 0 : COLSUM_CTAS * 1024), e->colsum_ticket + (e->ls == e->stream ? 0 : 1));
+        CK(cudaGetLastError());
+      }
     }
     if (l > 0) {
       ConvDgradOp dg{};
@@ -671,6 +683,8 @@ void allocate(E* e) {
   const int nA = c.n_actions;
   e->q_s = dalloc<float>((long long)B * nA); e->q_sp_on = dalloc<float>((long long)B * nA); e->q_sp_tg = dalloc<float>((long long)B * nA);
   e->y = dalloc<float>(B); e->td = dalloc<float>(B); e->newp = dalloc<float>(B); e->best_a = dalloc<int>(B);
+  e->colsum_part = dalloc<float>(2LL * COLSUM_CTAS * 1024);
+  e->colsum_ticket = dalloc<unsigned int>(2);
   e->ws_floats = 16LL << 20;      // 64 MB split-K workspace
   e->ws = dalloc<float>(e->ws_floats);
   e->ws2 = dalloc<float>(e->ws_floats);
@@ -692,7 +706,7 @@ void destroy(E* e) {
   tc_destroy(e);
   void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
                   e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws, e->ws2,
-                  e->stage, e->flush_buf};
+                  e->stage, e->flush_buf, e->colsum_part, e->colsum_ticket};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto p : e->on.conv_out) cudaFree(p);
   for (auto p : e->tg.conv_out) cudaFree(p);

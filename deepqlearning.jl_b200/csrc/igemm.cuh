@@ -373,13 +373,15 @@ struct ConvWgradOp {
   static constexpr bool A_MCONTIG = true, B_KCONTIG = false, Z_IS_CLASS = false;
   const void* X; int x_u8;
   const float* D; float* dW; int nimg; ConvGeom g;
-  int M, N, K;               // M = KH*KW*Cin + 1, N = Cout, K = nimg*OH*OW
+  int M, N, K;               // M = KH*KW*Cin + 1 (or without the + 1, see no_bias), N = Cout, K = nimg*OH*OW
   int vecA, vecB;
   const float* Xs; const float* Ds; const float* ones; long long lo_delta; int a_single; float out_scale;
+  int no_bias;               // 1: M = KH*KW*Cin, the bias gradient (column sums of D) is produced by colsum_kernel instead of a ones row
+  DQN_HD int kin() const { return no_bias ? M : M - 1; }
   DQN_HD bool tc_ready() const { return Xs && Ds && ones && (g.Cin % 4 == 0) && (N % 4 == 0); }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int m, int k) const {     // 4 consecutive m (channels of one tap) at pixel k
     if (!c.valid || k >= K) return nullptr;
-    const int cnt = (M - 1) - m;
+    const int cnt = kin() - m;
     return cnt >= 4 ? Xs + kc.off + c.base : (cnt == 0 ? ones : nullptr);
   }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * N + n : nullptr; }
@@ -389,7 +391,7 @@ struct ConvWgradOp {
     g.fCin.divmod((uint32_t)m, t, ci); g.fKW.divmod(t, kh, kw);
     return ((long long)kh * g.IW + kw) * g.Cin + ci;
   }
-  DQN_HD ACtx prepA(int m) const { ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = (c.valid && m < M - 1) ? moff(m) : 0; return c; }
+  DQN_HD ACtx prepA(int m) const { ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = (c.valid && m < kin()) ? moff(m) : 0; return c; }
   DQN_HD KCtx prepK(int k) const {          // pixel -> offset of its receptive field origin
     KCtx c; c.t0 = c.t1 = c.t2 = 0; c.off = 0;
     if (k < K) {
@@ -402,7 +404,7 @@ struct ConvWgradOp {
   DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(ldg1u((const uint8_t*)X + o)) : ldg1((const float*)X + o); }
   DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int m, int k) const {   // 4 consecutive m at pixel k
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
-    const int cnt = (M - 1) - m;
+    const int cnt = kin() - m;
     float4 v = make4(0, 0, 0, 0);
     if (cnt >= 4 && vecA) {
       v = x_u8 ? load4_u8((const uint8_t*)X + kc.off + c.base, 4, true) : ldg4((const float*)X + kc.off + c.base);
@@ -416,7 +418,7 @@ struct ConvWgradOp {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * N + n, N - n, vecB);
   }
-  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < M - 1) ? out_scale : 1.f; }
+  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < kin()) ? out_scale : 1.f; }
   DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v * oscale(m); }
   DQN_HD bool can_store4() const { return N % 4 == 0; }
   DQN_HD void store4(int m, int n, float4 v) const {

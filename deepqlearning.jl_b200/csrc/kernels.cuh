@@ -469,6 +469,64 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, long long n, uint32_t 
 __global__ void publish_kernel(const DevState* __restrict__ st, float* __restrict__ out) {
   out[0] = st->loss; out[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(out)[2] = st->error;
 }
+
+// Column sums of a row-major matrix D[P][N] (N % 4 == 0): the bias gradient of a conv layer, db[n] = sum_pixels delta[pix][n].
+// Deterministic: every CTA sums a fixed slab of rows in a fixed order into part[cta][N]; the last CTA to finish (ticket) adds the
+// partials in CTA order.  grid = G CTAs of 256 threads, part holds G*N floats, ticket is a zeroed counter that the kernel resets.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ D, long long P, int N, float* __restrict__ out,
+                                                     float* __restrict__ part, unsigned int* __restrict__ ticket) {
+  __shared__ float4 sh[256];
+  __shared__ int last;
+  const int nc = N >> 2;                                      // float4 columns
+  const int tx = threadIdx.x % nc, ty = threadIdx.x / nc, rows_per = 256 / nc;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(P, r0 + per);
+  float4 acc = make4(0.f, 0.f, 0.f, 0.f);
+  if (ty < rows_per) {
+    long long r = r0 + ty;
+    for (; r + 7LL * rows_per < r1; r += 8LL * rows_per) {   // eight independent loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(D + (r + (long long)j * rows_per) * N) + tx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+    }
+    for (; r < r1; r += rows_per) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(D + r * N) + tx);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    float4 s4 = make4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < rows_per; ++j) { const float4 v = sh[j * nc + threadIdx.x]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+    reinterpret_cast<float4*>(part + (long long)blockIdx.x * N)[threadIdx.x] = s4;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // final pass, same fixed shape: thread (tx, ty) adds the partials of CTAs ty, ty + rows_per, ... in order, then the ty sums are added in order
+  acc = make4(0.f, 0.f, 0.f, 0.f);
+  if (ty < rows_per) {
+    for (unsigned c = ty; c < gridDim.x; c += rows_per) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (long long)c * N) + tx);   // L2: written by other CTAs
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  __syncthreads();
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    float4 s4 = make4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < rows_per; ++j) { const float4 v = sh[j * nc + threadIdx.x]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+    reinterpret_cast<float4*>(out)[threadIdx.x] = s4;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
 #endif  // __CUDACC__
 
 }  // namespace dqn

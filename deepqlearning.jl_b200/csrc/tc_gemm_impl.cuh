@@ -42,9 +42,15 @@ __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (produ
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-constexpr int LOAD_WARPS = 4;    // loader warps: chunk addresses + cp.async only (an LDGSTS that waits for a queue slot blocks nothing else)
+#ifndef TC_LOAD_WARPS
+#define TC_LOAD_WARPS 4
+#endif
+#ifndef TC_NGRP
+#define TC_NGRP 2
+#endif
+constexpr int LOAD_WARPS = TC_LOAD_WARPS;    // loader warps: chunk addresses + cp.async only (an LDGSTS that waits for a queue slot blocks nothing else)
 constexpr int LOADERS = 32 * LOAD_WARPS;
-constexpr int NGRP = 2;          // converter groups (4 warps each: one per TMEM lane quarter) that take alternate stages
+constexpr int NGRP = TC_NGRP;    // converter groups (4 warps each: one per TMEM lane quarter) that take alternate stages
 constexpr int CONV_WARPS = 4 * NGRP;
 constexpr int EPI_WARPS = 4;     // epilogue warps: warp & 3 = the TMEM lane quarter it may read
 constexpr int NMMA = 3;          // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
@@ -323,7 +329,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     uint32_t a_off[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-      if (A_MN) a_off[i] = ((tid >> 5) + 4 * i) * SA::PITCH + lane * 16;        // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
+      if (A_MN) a_off[i] = ((tid >> 5) + LOAD_WARPS * i) * SA::PITCH + lane * 16;        // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
       else      a_off[i] = ((tid >> 3) + i * (LOADERS / 8)) * SA::PITCH + (tid & 7) * 16;   // 8 lanes = the 128 contiguous bytes of one row
     }
     uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
@@ -354,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
           const float* p;
-          if (A_MN) { const int kk = (tid >> 5) + 4 * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
+          if (A_MN) { const int kk = (tid >> 5) + LOAD_WARPS * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
           else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
           cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
         }
