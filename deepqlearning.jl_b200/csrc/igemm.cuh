@@ -162,7 +162,7 @@ DQN_HD void store_split4(float* hi_ptr, long long lo_delta, const float4& v) {
 
 // Per-row (m) and per-column-of-A (k) decode contexts, hoisted out of the inner loops by the kernels.
 struct ACtx { long long base; int i0, i1; int valid; };
-struct KCtx { long long off; int t0, t1, t2; };
+struct KCtx { long long off; int t0, t1, t2; long long offb; };
 
 // ------------------------------------------------------------------------------------------------
 // Dense forward:  C[m][n] = act( sum_k X[m][k] W[k][n] + W[K][n] )
@@ -180,7 +180,7 @@ struct DenseFwdOp {
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldx; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
   DQN_HD float4 loadA(const ACtx& c, const KCtx&, int, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     if (x_u8) return load4_u8((const uint8_t*)X + c.base + k, K - k, vecA);
@@ -216,18 +216,25 @@ struct DenseDgradOp {
   // trunk gradient are ONE contraction instead of two launches with a read-modify-write in between.  K1 == 0: single segment.
   int K1; const float* D2; long long ldd2; const float* W2; const float* Ds2; const float* Ws2;
   DQN_HD int seg0() const { return K1 > 0 ? K1 : K; }
-  DQN_HD bool tc_ready() const { return Ds && Ws && (K % 4 == 0) && (ldd % 4 == 0) && (K1 == 0 || (Ds2 && Ws2 && K1 % 4 == 0 && ldd2 % 4 == 0)); }
-  DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int m, int k) const {
-    if (!c.valid || k >= K) return nullptr;
-    return k < seg0() ? Ds + c.base + k : Ds2 + (long long)m * ldd2 + (k - K1);
+  DQN_HD bool tc_ready() const {
+    return Ds && Ws && (K % 4 == 0) && (ldd % 4 == 0) && (K1 == 0 || (Ds2 && Ws2 && K1 % 4 == 0 && ldd2 % 4 == 0 && (long long)M * ldd2 < (1LL << 31))) && (long long)N * K < (1LL << 31);
   }
-  DQN_HD const float* ptrB(const KCtx&, int k, int n) const {
+  // k context: kc.t0 = segment (0: D/W, 1: D2/W2), kc.off = k inside the segment, kc.t1 = the segment's width; row context: c.i0 = m * ldd2
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const {
+    if (!c.valid || k >= K) return nullptr;
+    return (kc.t0 ? Ds2 + c.i0 : Ds + c.base) + kc.off;
+  }
+  DQN_HD const float* ptrB(const KCtx& kc, int k, int n) const {
     if (k >= K || n >= N) return nullptr;
-    return k < seg0() ? Ws + (long long)n * seg0() + k : Ws2 + (long long)n * (K - K1) + (k - K1);
+    return (kc.t0 ? Ws2 : Ws) + (n * kc.t1 + (int)kc.off);
   }
   DQN_HD void set_class(int) {}
-  DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = (int)((long long)m * ldd2); c.i1 = 0; return c; }
+  DQN_HD KCtx prepK(int k) const {
+    KCtx c; c.t2 = 0; c.offb = 0;
+    c.t0 = k < seg0() ? 0 : 1; c.off = c.t0 ? k - K1 : k; c.t1 = c.t0 ? K - K1 : seg0();
+    return c;
+  }
   DQN_HD float4 loadA(const ACtx& c, const KCtx&, int m, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     if (k < seg0()) return load4_f32(D + c.base + k, seg0() - k, vecA);
@@ -275,7 +282,7 @@ struct DenseWgradOp {
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * ldd + n : nullptr; }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = m; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
-  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
   DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int m, int k) const {   // 4 consecutive m at batch row k
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     const int kin = M - 1;
@@ -340,7 +347,7 @@ struct ConvFwdOp {
     g.fCin.divmod((uint32_t)k, t, ci); g.fKW.divmod(t, kh, kw);
     return ((long long)kh * g.IW + kw) * g.Cin + ci;
   }
-  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k < K ? koff(k) : 0; c.t0 = c.t1 = c.t2 = 0; return c; }
+  DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k < K ? koff(k) : 0; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
   DQN_HD float ld1(long long o) const { return x_u8 ? u8_to_f32(ldg1u((const uint8_t*)X + o)) : ldg1((const float*)X + o); }
   DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int, int k) const {
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
@@ -393,7 +400,7 @@ struct ConvWgradOp {
   }
   DQN_HD ACtx prepA(int m) const { ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = (c.valid && m < kin()) ? moff(m) : 0; return c; }
   DQN_HD KCtx prepK(int k) const {          // pixel -> offset of its receptive field origin
-    KCtx c; c.t0 = c.t1 = c.t2 = 0; c.off = 0;
+    KCtx c; c.t0 = c.t1 = c.t2 = 0; c.off = 0; c.offb = 0;
     if (k < K) {
       uint32_t t, ow, n, oh;
       g.fOW.divmod((uint32_t)k, t, ow); g.fOH.divmod(t, n, oh);
@@ -438,16 +445,18 @@ struct ConvDgradOp {
   int vecA, vecB;
   const float* Ds; const float* Ws; float* dXs; long long lo_delta; int a_single;
   DQN_HD bool tc_ready() const { return Ds && Ws && (g.Cout % 4 == 0); }
+  // row context: c.base = offset of D[img][i0][i1][0] (the tap (0,0) source pixel, possibly outside the image), i0/i1 for the bounds;
+  // k context: kc.off = co - (th*OW + tw)*Cout moves from there to tap (th,tw), kc.offb = offset of W[kh][kw][0][co]
+  DQN_HD bool tap_ok(const ACtx& c, const KCtx& kc) const {
+    return (unsigned)(c.i0 - kc.t0) < (unsigned)g.OH && (unsigned)(c.i1 - kc.t1) < (unsigned)g.OW;
+  }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const {
-    if (!c.valid || k >= K) return nullptr;
-    const int oh = c.i0 - kc.t0, ow = c.i1 - kc.t1;
-    if (oh < 0 || oh >= g.OH || ow < 0 || ow >= g.OW) return nullptr;
-    return Ds + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + kc.t2;
+    if (!c.valid || k >= K || !tap_ok(c, kc)) return nullptr;
+    return Ds + c.base + kc.off;
   }
   DQN_HD const float* ptrB(const KCtx& kc, int k, int n) const {
     if (k >= K || n >= N) return nullptr;
-    const int kh = ph + kc.t0 * g.S, kw = pw + kc.t1 * g.S;
-    return Ws + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + kc.t2;
+    return Ws + kc.offb + (long long)(n * g.Cout);
   }
   DQN_HD void set_class(int z) {
     ph = z / g.S; pw = z - ph * g.S;
@@ -461,40 +470,42 @@ struct ConvDgradOp {
   }
   DQN_HD ACtx prepA(int m) const {
     ACtx c; c.valid = m < M; c.base = 0; c.i0 = c.i1 = 0;
-    if (c.valid) { uint32_t t, b, n, a; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, n, a); c.i0 = (int)a; c.i1 = (int)b; c.base = n; }
+    if (c.valid) {
+      uint32_t t, b, n, a; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, n, a); c.i0 = (int)a; c.i1 = (int)b;
+      c.base = (((long long)n * g.OH + (int)a) * g.OW + (int)b) * g.Cout;
+    }
     return c;
   }
   DQN_HD KCtx prepK(int k) const {      // k -> (th, tw, co)
-    KCtx c; c.off = 0; c.t0 = c.t1 = c.t2 = 0;
-    if (k < K) { uint32_t t, co, th, tw; g.fCout.divmod((uint32_t)k, t, co); ftw.divmod(t, th, tw); c.t0 = (int)th; c.t1 = (int)tw; c.t2 = (int)co; }
+    KCtx c; c.off = 0; c.offb = 0; c.t0 = c.t1 = c.t2 = 0;
+    if (k < K) {
+      uint32_t t, co, th, tw; g.fCout.divmod((uint32_t)k, t, co); ftw.divmod(t, th, tw); c.t0 = (int)th; c.t1 = (int)tw; c.t2 = (int)co;
+      c.off = (long long)(int)co - (long long)((int)th * g.OW + (int)tw) * g.Cout;
+      const int kh = ph + (int)th * g.S, kw = pw + (int)tw * g.S;
+      c.offb = ((long long)kh * g.KW + kw) * g.Cin * g.Cout + (int)co;
+    }
     return c;
   }
   DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int, int k) const {     // 4 consecutive co of one tap
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
     if (vecA) {
-      const int oh = c.i0 - kc.t0, ow = c.i1 - kc.t1;
-      if (oh < 0 || oh >= g.OH || ow < 0 || ow >= g.OW) return make4(0, 0, 0, 0);
-      return ldg4(D + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + kc.t2);
+      if (!tap_ok(c, kc)) return make4(0, 0, 0, 0);
+      return ldg4(D + c.base + kc.off);
     }
     float4 v = make4(0, 0, 0, 0);
     for (int j = 0; j < 4 && k + j < K; ++j) {
       const KCtx q = prepK(k + j);
-      const int oh = c.i0 - q.t0, ow = c.i1 - q.t1;
-      if (oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW) set4(v, j, ldg1(D + (((long long)c.base * g.OH + oh) * g.OW + ow) * g.Cout + q.t2));
+      if (tap_ok(c, q)) set4(v, j, ldg1(D + c.base + q.off));
     }
     return v;
   }
   DQN_HD float4 loadB(const KCtx& kc, int k, int n) const {                  // 4 consecutive k (= co) at ci = n
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
-    if (vecB) {
-      const int kh = ph + kc.t0 * g.S, kw = pw + kc.t1 * g.S;
-      return ldg4(W + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + kc.t2);
-    }
+    if (vecB) return ldg4(W + kc.offb + (long long)(n * g.Cout));
     float4 v = make4(0, 0, 0, 0);
     for (int j = 0; j < 4 && k + j < K; ++j) {
       const KCtx q = prepK(k + j);
-      const int kh = ph + q.t0 * g.S, kw = pw + q.t1 * g.S;
-      set4(v, j, ldg1(W + (((long long)kh * g.KW + kw) * g.Cin + n) * g.Cout + q.t2));
+      set4(v, j, ldg1(W + q.offb + (long long)(n * g.Cout)));
     }
     return v;
   }
@@ -580,7 +591,7 @@ igemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_st
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) { const KCtx kc = op.prepK(k0 + a_k[i]); ra[i] = op.loadA(actx[i], kc, m0 + a_m[i], k0 + a_k[i]); }
     }
-    KCtx kb; kb.off = 0; kb.t0 = kb.t1 = kb.t2 = 0;
+    KCtx kb; kb.off = 0; kb.offb = 0; kb.t0 = kb.t1 = kb.t2 = 0;
     if (Op::B_KCONTIG) kb = op.prepK(k0 + b_k[0]);
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {

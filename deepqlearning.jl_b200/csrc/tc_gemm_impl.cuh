@@ -82,8 +82,8 @@ template <> struct AStage<false> {                            // K-major source:
   static constexpr int PITCH = BK * 4 + 16;
   static constexpr int BYTES = BM * PITCH;
 };
-template <> struct AStage<true> {                             // MN-major source: k row kk (32 of them) = 128 floats + 16 bytes of padding
-  static constexpr int PITCH = BM * 4 + 16;
+template <> struct AStage<true> {                             // MN-major source: k row kk (32 of them) = 128 floats + 64 bytes of padding
+  static constexpr int PITCH = BM * 4 + 64;                   //   (pitch/16 = 4 mod 8: the loaders' 8 k rows x 4 chunks per warp spread evenly over the banks)
   static constexpr int BYTES = BK * PITCH;
 };
 
@@ -326,10 +326,11 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     // ================= loaders: chunk addresses + cp.async into ring slot, completion signalled on landed[slot] =================
     constexpr int A_PER = BM * (BK / 4) / LOADERS;             // 8 chunks of A per thread per stage
     constexpr int B_PER = B_CH / LOADERS;                      // BN/16 chunks of B
+    constexpr int MPT = LOADERS / BK;                          // MN-major A: threads that share a k row
     uint32_t a_off[A_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-      if (A_MN) a_off[i] = ((tid >> 5) + LOAD_WARPS * i) * SA::PITCH + lane * 16;        // lane = 16-byte chunk along the rows (4 m), k rows over warps / i
+      if (A_MN) a_off[i] = (tid / MPT) * SA::PITCH + ((tid % MPT) + MPT * i) * 16;   // one k row per thread (one k decode per stage), its m chunks over i
       else      a_off[i] = ((tid >> 3) + i * (LOADERS / 8)) * SA::PITCH + (tid & 7) * 16;   // 8 lanes = the 128 contiguous bytes of one row
     }
     uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
@@ -343,24 +344,21 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
-      ACtx actx[A_MN ? 1 : A_PER];
-      if (A_MN) actx[0] = op.prepA(m0 + lane * 4);
-      else {
+      ACtx actx[A_PER];
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(m0 + (tid >> 3) + i * (LOADERS / 8));
-      }
+      for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(A_MN ? m0 + ((tid % MPT) + MPT * i) * 4 : m0 + (tid >> 3) + i * (LOADERS / 8));
       for (int it = 0; it < nk; ++it) {
         const int k0 = (kt0 + it) * BK;
         const uint32_t a_st = sbase + is * L::STAGE_BYTES;
         const uint32_t b_hi = a_st + L::A_BYTES;
-        KCtx kc; kc.off = 0; kc.t0 = kc.t1 = kc.t2 = 0;
-        if (!A_MN) kc = op.prepK(k0 + (tid & 7) * 4);          // K-major: this thread's k chunk is the same for all its rows
+        KCtx kc; kc.off = 0; kc.offb = 0; kc.t0 = kc.t1 = kc.t2 = 0;
+        kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 7) * 4);   // one k decode per thread and stage: its k row (MN-major) or k chunk (K-major)
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
 #ifndef TC_EXP_NOLOAD
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
           const float* p;
-          if (A_MN) { const int kk = (tid >> 5) + LOAD_WARPS * i; const KCtx kq = op.prepK(k0 + kk); p = op.ptrA(actx[0], kq, m0 + lane * 4, k0 + kk); }
+          if (A_MN) p = op.ptrA(actx[i], kc, m0 + ((tid % MPT) + MPT * i) * 4, k0 + tid / MPT);
           else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
           cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
         }
