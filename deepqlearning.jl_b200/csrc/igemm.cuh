@@ -178,6 +178,11 @@ struct DenseFwdOp {
   DQN_HD bool tc_ready() const { return Xs && Ws && (K % 4 == 0) && (N % 4 == 0) && (ldx % 4 == 0); }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx&, int, int k) const { return (c.valid && k < K) ? Xs + c.base + k : nullptr; }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
+  // unchecked forms for stages that lie entirely inside the operand (interiorA / interiorB say so)
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M && k0 + bk <= K; }
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx&, int, int k) const { return Xs + c.base + k; }
+  DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ws + (k * N + n); }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldx; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = k; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
@@ -228,6 +233,10 @@ struct DenseDgradOp {
     if (k >= K || n >= N) return nullptr;
     return (kc.t0 ? Ws2 : Ws) + (n * kc.t1 + (int)kc.off);
   }
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M && k0 + bk <= K; }
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx& kc, int, int) const { return (kc.t0 ? Ds2 + c.i0 : Ds + c.base) + kc.off; }
+  DQN_HD const float* ptrB_u(const KCtx& kc, int, int n) const { return (kc.t0 ? Ws2 : Ws) + (n * kc.t1 + (int)kc.off); }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = (long long)m * ldd; c.valid = m < M; c.i0 = (int)((long long)m * ldd2); c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const {
@@ -280,6 +289,10 @@ struct DenseWgradOp {
     return cnt >= 4 ? Xs + kc.off + m : (cnt == 0 ? ones : nullptr);
   }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * ldd + n : nullptr; }
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M - 1 && k0 + bk <= K; }       // excludes the ones row
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx&, const KCtx& kc, int m, int) const { return Xs + kc.off + m; }
+  DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ds + ((long long)k * ldd + n); }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const { ACtx c; c.base = m; c.valid = m < M; c.i0 = c.i1 = 0; return c; }
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
@@ -332,6 +345,10 @@ struct ConvFwdOp {
   DQN_HD bool tc_ready() const { return Xs && Ws && (g.Cin % 4 == 0) && (N % 4 == 0); }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const { return (c.valid && k < K) ? Xs + c.base + kc.off : nullptr; }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M && k0 + bk <= K; }
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx& kc, int, int) const { return Xs + c.base + kc.off; }
+  DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ws + (k * N + n); }
   DQN_HD void set_class(int) {}
   DQN_HD ACtx prepA(int m) const {
     ACtx c; c.valid = m < M; c.i0 = c.i1 = 0; c.base = 0;
@@ -392,6 +409,10 @@ struct ConvWgradOp {
     return cnt >= 4 ? Xs + kc.off + c.base : (cnt == 0 ? ones : nullptr);
   }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * N + n : nullptr; }
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= kin() && k0 + bk <= K; }          // excludes the ones row
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx& kc, int, int) const { return Xs + kc.off + c.base; }
+  DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ds + ((long long)k * N + n); }
   DQN_HD void set_class(int) {}
   DQN_HD long long moff(int m) const {
     uint32_t t, ci, kh, kw;
@@ -458,6 +479,10 @@ struct ConvDgradOp {
     if (k >= K || n >= N) return nullptr;
     return Ws + kc.offb + (long long)(n * g.Cout);
   }
+  DQN_HD bool interiorA(int, int, int, int) const { return false; }            // tap bounds depend on the row: always the checked form
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx& kc, int, int) const { return Ds + c.base + kc.off; }
+  DQN_HD const float* ptrB_u(const KCtx& kc, int, int n) const { return Ws + kc.offb + (long long)(n * g.Cout); }
   DQN_HD void set_class(int z) {
     ph = z / g.S; pw = z - ph * g.S;
     AH = (g.IH - ph + g.S - 1) / g.S; BW = (g.IW - pw + g.S - 1) / g.S;

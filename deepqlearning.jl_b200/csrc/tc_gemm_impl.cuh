@@ -255,6 +255,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");   // L2 only: operands stream
 #endif
 }
+__device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive when this thread's prior cp.async have landed
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -355,18 +358,38 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
         kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 7) * 4);   // one k decode per thread and stage: its k row (MN-major) or k chunk (K-major)
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
 #ifndef TC_EXP_NOLOAD
+        // a stage that lies entirely inside the operand (all but the last m tile / k stage) takes the unchecked form: no
+        // predicates, no zero-fill source select - the loaders' instruction stream is what bounds the short-k layers
+        if (op.interiorA(m0, k0, BM, BK)) {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) {
-          const float* p;
-          if (A_MN) p = op.ptrA(actx[i], kc, m0 + ((tid % MPT) + MPT * i) * 4, k0 + tid / MPT);
-          else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
-          cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
+          for (int i = 0; i < A_PER; ++i) {
+            const float* p = A_MN ? op.ptrA_u(actx[i], kc, m0 + ((tid % MPT) + MPT * i) * 4, k0 + tid / MPT)
+                                  : op.ptrA_u(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
+            cp_async16_full(a_st + a_off[i], p);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < A_PER; ++i) {
+            const float* p;
+            if (A_MN) p = op.ptrA(actx[i], kc, m0 + ((tid % MPT) + MPT * i) * 4, k0 + tid / MPT);
+            else p = op.ptrA(actx[i], kc, m0 + (tid >> 3) + i * (LOADERS / 8), k0 + (tid & 7) * 4);
+            cp_async16(a_st + a_off[i], p ? p : zero_src, p ? 16u : 0u);
+          }
         }
+        if (op.interiorB(n0, k0, BN, BK)) {
 #pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-          const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
-                                : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
-          cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
+          for (int i = 0; i < B_PER; ++i) {
+            const float* p = B_MN ? op.ptrB_u(kc, k0 + b_kk[i], n0 + b_n[i])
+                                  : op.ptrB_u(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);
+            cp_async16_full(b_hi + b_off[i], p);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < B_PER; ++i) {
+            const float* p = B_MN ? op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i])
+                                  : op.ptrB(A_MN ? op.prepK(k0 + b_kk[i]) : kc, k0 + b_kk[i], n0 + b_n[i]);   // K-major B shares A's k chunk
+            cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
+          }
         }
 #endif
         // the barrier receives this thread's arrival once all of its copies above have landed
