@@ -141,6 +141,8 @@ struct dqn_engine {
   long long w_scale_lo = 0, w_scale_hi = 0;
   int tc_split = 0;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
+  bool towers_updated = false;
+  int merge_fwd = 0;       // 1: online and target forward share launches layer by layer; measured slower than two lanes on B200 (0.571 vs 0.539 ms/step)
 };
 
 namespace {
@@ -228,43 +230,66 @@ void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everyt
 }
 
 // ---- network schedule ---------------------------------------------------------------------------
-// Xs: the input batch as fp32 for the tensor-core path (null => fp32 CUDA-core kernels only); w1s: the first conv layer's
-// weights pre-scaled by 1/255 when Xs holds raw byte values
-void forward(E* e, const float* P, const void* X, int x_u8, int rows, ActBufs& bufs, const char* tag, const float* Xs, const float* w1s) {
-  const void* cur = X; int cur_u8 = x_u8;
-  const float* cur_s = Xs;
-  const bool tcm = Xs != nullptr;
+// One forward pass: parameters P applied to the rows of X.  Xs: the input batch as fp32 for the tensor-core path (null => fp32
+// CUDA-core kernels only); w1s: the first conv layer's weights pre-scaled by 1/255 when Xs holds raw byte values.
+struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; };
+
+// Layer by layer over all passes.  On the tensor-core path the passes of a layer (online network on [s ; s'], target network on s')
+// and the two towers of a Dense layer share ONE launch: the persistent kernels serialise on the machine anyway, and one launch
+// rounds the tile count to SM multiples once instead of once per pass.
+void forward(E* e, const Pass* ps, int np) {
+  const void* cur[2]; int cur_u8[2]; const float* cur_s[2];
+  for (int p = 0; p < np; ++p) { cur[p] = ps[p].X; cur_u8[p] = ps[p].x_u8; cur_s[p] = ps[p].Xs; }
   char nm[64];
   for (size_t l = 0; l < e->convs.size(); ++l) {
     const ConvL& c = e->convs[l];
-    ConvFwdOp op{};
-    op.X = cur; op.x_u8 = cur_u8; op.W = P + c.w.off; op.Y = bufs.conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
-    op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
-    op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
-    if (tcm) { op.Xs = cur_s; op.Ws = (l == 0 && cur_u8) ? w1s : P + c.w.off; op.a_single = (l == 0 && cur_u8); }
-    snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, tag);
-    const double fl = 2.0 * op.M * op.N * op.K;
-    const double by = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8 ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
-    if (!tc_conv_fwd(e, nm, op, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
-    cur = bufs.conv_out[l]; cur_u8 = 0; cur_s = bufs.conv_out[l];
+    ConvFwdOp ops[2]; double fl[2], by[2], fls = 0, bys = 0;
+    for (int p = 0; p < np; ++p) {
+      ConvFwdOp& op = ops[p]; op = ConvFwdOp{};
+      const int rows = ps[p].rows;
+      op.X = cur[p]; op.x_u8 = cur_u8[p]; op.W = ps[p].P + c.w.off; op.Y = ps[p].bufs->conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
+      op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
+      op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
+      if (ps[p].Xs) { op.Xs = cur_s[p]; op.Ws = (l == 0 && cur_u8[p]) ? ps[p].w1s : ps[p].P + c.w.off; op.a_single = (l == 0 && cur_u8[p]); }
+      fl[p] = 2.0 * op.M * op.N * op.K;
+      by[p] = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8[p] ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
+      fls += fl[p]; bys += by[p];
+    }
+    snprintf(nm, sizeof nm, "conv%zu_fwd", l + 1);
+    if (!(np > 1 && tc_conv_fwd(e, nm, ops, np, fls, bys))) {
+      for (int p = 0; p < np; ++p) {
+        snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, ps[p].tag);
+        if (!tc_conv_fwd(e, nm, &ops[p], 1, fl[p], by[p])) launch_igemm(e, nm, ops[p], ops[p], 1, false, fl[p], by[p]);
+      }
+    }
+    for (int p = 0; p < np; ++p) { cur[p] = ps[p].bufs->conv_out[l]; cur_u8[p] = 0; cur_s[p] = ps[p].bufs->conv_out[l]; }
   }
   for (int l = 0; l < e->depth; ++l) {
-    DenseFwdOp ops[2];
-    for (int t = 0; t < e->ntow; ++t) {
-      const Mat& w = e->tow[t][l];
-      DenseFwdOp& op = ops[t]; op = DenseFwdOp{};
-      op.X = l == 0 ? cur : (const void*)bufs.tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8 : 0;
-      op.W = P + w.off; op.C = bufs.tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
-      op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
-      if (tcm) { op.Xs = l == 0 ? (cur_u8 ? nullptr : cur_s) : bufs.tow_out[t][l - 1]; op.Ws = P + w.off; op.a_single = 0; }
+    DenseFwdOp ops[4]; double fl[2] = {0, 0}, by[2] = {0, 0};
+    for (int p = 0; p < np; ++p)
+      for (int t = 0; t < e->ntow; ++t) {
+        const Mat& w = e->tow[t][l];
+        const int rows = ps[p].rows;
+        DenseFwdOp& op = ops[p * e->ntow + t]; op = DenseFwdOp{};
+        op.X = l == 0 ? cur[p] : (const void*)ps[p].bufs->tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8[p] : 0;
+        op.W = ps[p].P + w.off; op.C = ps[p].bufs->tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
+        op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
+        if (ps[p].Xs) { op.Xs = l == 0 ? (cur_u8[p] ? nullptr : cur_s[p]) : ps[p].bufs->tow_out[t][l - 1]; op.Ws = ps[p].P + w.off; op.a_single = 0; }
+        fl[p] += 2.0 * rows * op.N * op.K;
+        by[p] += 4.0 * ((double)rows * op.K / (l == 0 ? e->ntow : 1) + (double)(op.K + 1) * op.N + (double)rows * op.N);
+      }
+    snprintf(nm, sizeof nm, "dense%d_fwd", l + 1);
+    if (!(np > 1 && tc_dense_fwd(e, nm, ops, np * e->ntow, fl[0] + fl[1], by[0] + by[1]))) {
+      for (int p = 0; p < np; ++p) {
+        DenseFwdOp* o = ops + p * e->ntow;
+        snprintf(nm, sizeof nm, "dense%d_fwd_%s", l + 1, ps[p].tag);
+        if (!tc_dense_fwd(e, nm, o, e->ntow, fl[p], by[p])) launch_igemm(e, nm, o[0], o[e->ntow - 1], e->ntow, false, fl[p], by[p]);
+      }
     }
-    if (e->ntow == 1) ops[1] = ops[0];
-    snprintf(nm, sizeof nm, "dense%d_fwd_%s", l + 1, tag);
-    double fl = 0, by = 0;
-    for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * rows * ops[t].N * ops[t].K; by += 4.0 * ((double)rows * ops[t].K / (l == 0 ? e->ntow : 1) + (double)(ops[t].K + 1) * ops[t].N + (double)rows * ops[t].N); }
-    if (!tc_dense_fwd(e, nm, ops, e->ntow, fl, by)) launch_igemm(e, nm, ops[0], ops[1], e->ntow, false, fl, by);
   }
 }
+
+void enqueue_adam(E* e, long long lo, long long hi, cudaStream_t s);
 
 void backward(E* e, bool conc) {
   const int B = e->B;
@@ -342,10 +367,19 @@ void backward(E* e, bool conc) {
       }
     }
   }
-  if (conc && e->cfg.world > 1 && trunk) {               // every Dense gradient is enqueued: reduce that bucket now, behind the conv backward
+  e->towers_updated = false;
+  if (conc && trunk) {
+    // Every Dense gradient is enqueued (weight gradients on lane 2) and so is the last reader of the Dense weights (the gradient into the
+    // trunk, on the main lane): reduce that bucket and run its Adam update now, on the third lane, behind the conv backward.  The Dense
+    // layers hold 98 % of the parameters (12.9 of 13.2 MB in config 3), so almost all of the optimizer's HBM traffic leaves the critical path.
     order_after(e, e->stream3, e->stream2);
-    ncclResult_t r = g_nccl.AllReduce(e->grad + e->tower_off, e->grad + e->tower_off, (size_t)(e->nint - e->tower_off), ncclFloat, ncclSum, e->comm, e->stream3);
-    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    if (e->cfg.world > 1) {
+      ncclResult_t r = g_nccl.AllReduce(e->grad + e->tower_off, e->grad + e->tower_off, (size_t)(e->nint - e->tower_off), ncclFloat, ncclSum, e->comm, e->stream3);
+      if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    order_after(e, e->stream3, e->stream);
+    enqueue_adam(e, e->tower_off, e->nint, e->stream3);
+    e->towers_updated = true;
   }
   for (int l = (int)e->convs.size() - 1; l >= 0; --l) {
     const ConvL& c = e->convs[l];
@@ -391,6 +425,22 @@ void backward(E* e, bool conc) {
   }
 }
 
+// Adam over the parameter range [lo, hi) (both multiples of 4 floats), plus its share of max|g|
+void enqueue_adam(E* e, long long lo, long long hi, cudaStream_t s) {
+  if (hi <= lo) return;
+  const long long n4 = (hi - lo) / 4;
+  const int grid = (int)std::min<long long>(4LL * e->nsm, (n4 + 255) / 256);
+  cudaStream_t keep = e->ls; e->ls = s;                       // profiling events go to the lane the kernel runs on
+  {
+    Scope sc(e, "adam", 0, 7.0 * (hi - lo) * 4);
+    adam_kernel<<<grid, 256, 0, s>>>(e->theta + lo, e->adam_m + lo, e->adam_v + lo, e->grad + lo, n4,
+                                     (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st,
+                                     e->w_on_s, 0, e->w_scale_lo - lo, e->w_scale_hi - lo, 1.0f / 255.0f);
+    CK(cudaGetLastError());
+  }
+  e->ls = keep;
+}
+
 void enqueue_gather(E* e) {       // observation rows of the sampled transitions -> batch (and its tensor-core operand planes)
   const long long rb = e->obs_row_bytes;
   const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
@@ -424,13 +474,20 @@ void enqueue_step(E* e, bool sample) {
   const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? (e->elem_bytes == 1 ? e->xb_f : (const float*)e->xb) : nullptr;
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
   e->ev_next = 0;
-  if (conc) order_after(e, e->stream2, e->stream);            // fork: the gathered batch is ready
-  {
-    Lane lane(e, conc);
-    forward(e, e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s);
+  const Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s};
+  const Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s};
+  if (xs && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
+    const Pass both[2] = {p_on, p_tg};
+    forward(e, both, 2);
+  } else {
+    if (conc) order_after(e, e->stream2, e->stream);          // fork: the gathered batch is ready
+    {
+      Lane lane(e, conc);
+      forward(e, &p_tg, 1);
+    }
+    forward(e, &p_on, 1);
+    if (conc) order_after(e, e->stream, e->stream2);          // join before the head needs Q_target(s')
   }
-  forward(e, e->theta, e->xb, e->elem_bytes == 1, 2 * B, e->on, "online", xs, e->w_on_s);
-  if (conc) order_after(e, e->stream, e->stream2);            // join before the head needs Q_target(s')
   {
     HeadArgs h{};
     const int L = e->depth - 1;
@@ -459,13 +516,10 @@ void enqueue_step(E* e, bool sample) {
     if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     if (split) order_after(e, e->stream, e->stream3);
   }
-  {
-    Scope sc(e, "adam", 0, 7.0 * e->nint * 4);
-    adam_kernel<<<2 * e->nsm * 2, 256, 0, e->stream>>>(e->theta, e->adam_m, e->adam_v, e->grad, e->nint / 4,
-                                                       (double)e->cfg.learning_rate, e->cfg.adam_beta1, e->cfg.adam_beta2, e->cfg.adam_eps, 1.0f, e->st,
-                                                       e->w_on_s, 0, e->w_scale_lo, e->w_scale_hi, 1.0f / 255.0f);
-    CK(cudaGetLastError());
-  }
+  if (e->towers_updated) {
+    order_after(e, e->stream, e->stream3);                  // the Dense bucket's update (and its max|g|) is complete
+    enqueue_adam(e, 0, e->tower_off, e->stream);
+  } else enqueue_adam(e, 0, e->nint, e->stream);
   {
     Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
     tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
@@ -819,6 +873,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     CK(cudaStreamCreateWithFlags(&e->stream3, cudaStreamNonBlocking));
     e->ls = e->stream;
     { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
     build_topology(e);
     allocate(e);
     tc_init(e);
@@ -1046,7 +1101,8 @@ int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* 
       const int c = (int)std::min<long long>(chunk, n - t0);
       CK(cudaMemcpyAsync(h->stage, (const uint8_t*)obs + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
       relayout(h, h->stage, h->xb, c, h->elem_bytes == 1, 0, 1);
-      forward(h, which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, c, h->on, "act", nullptr, nullptr);
+      const Pass pa{which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, (int)c, &h->on, "act", nullptr, nullptr};
+      forward(h, &pa, 1);
       float* q = h->on.tow_out[h->ntow - 1][L];
       if (h->cfg.dueling) {
         q = (float*)h->ws;

@@ -268,8 +268,8 @@ __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool
 
 template <int BN, int R, int NBUF, class Op>
 __global__ void __launch_bounds__(THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, int nsplit, float* __restrict__ ws, long long ws_stride,
-               const float* __restrict__ zero_src, int MT, int NT, int ntiles) {
+tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, const __grid_constant__ Op opc, const __grid_constant__ Op opd,
+               int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src, int MT, int NT, int ntiles) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
   using L = Lay<BN, R, NBUF, A_MN, B_MN>;
   using TB = typename L::TB;
@@ -308,7 +308,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
     const int nt = r % NT;
     zs = r / NT;
     const int zi = zs / nsplit, split = zs - zi * nsplit;
-    op = (Op::Z_IS_CLASS || zi == 0) ? opa : opb;
+    op = (Op::Z_IS_CLASS || zi == 0) ? opa : (zi == 1 ? opb : (zi == 2 ? opc : opd));   // up to four operand sets share one launch
     if (Op::Z_IS_CLASS) op.set_class(zi);
     m0 = mt * BM; n0 = nt * BN;
     if (m0 >= op.M || n0 >= op.N) return false;
@@ -592,7 +592,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, i
 namespace {
 
 template <int BN, int R, int NBUF, class Op>
-void tc_launch_v(dqn_engine* e, const Op& a, const Op& b, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
+void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
   using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -600,7 +600,8 @@ void tc_launch_v(dqn_engine* e, const Op& a, const Op& b, int nsplit, long long 
     attr_set = true;
   }
   const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
-  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(a, b, nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
+  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
+                                                                            nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
   CK(cudaGetLastError());
 }
 
@@ -610,7 +611,11 @@ int tc_pick_split(dqn_engine* e, long long tiles0, int ktiles, int bn, long long
   const double stage_us = bn == 64 ? 0.33 : 0.22, tile_us = 1.0;
   int best = 1; double best_t = 1e30;
   const int max_ns = std::max(1, std::min(64, ktiles / 4));
-  for (int ns = 1; ns <= max_ns; ++ns) {
+  // accuracy floor: the tensor core truncates when it adds into an accumulator, so at most 32 stages (64 adds per interleaved
+  // accumulator) go into one partial sum; the partial sums are then added in fp32 with round-to-nearest
+  const int min_ns = std::min(max_ns, (ktiles + 31) / 32);
+  best = min_ns;
+  for (int ns = min_ns; ns <= max_ns; ++ns) {
     if (ns > 1 && (long long)nz * ns * out_elems > e->ws_floats) break;
     const int per = (ktiles + ns - 1) / ns;
     if (ns > 1 && (long long)per * (ns - 1) >= ktiles) continue;             // a split with an empty last range
@@ -622,57 +627,54 @@ int tc_pick_split(dqn_engine* e, long long tiles0, int ktiles, int bn, long long
   return best;
 }
 
+// ops[0..nops): operand sets of one launch (the two towers, the online and the target network; a dgrad op carries its parity
+// classes itself: nops = 1, nz = classes)
 template <class Op>
-bool launch_tc(dqn_engine* e, const char* name, Op a, Op b, int nz, bool allow_split, double flops, double bytes) {
+bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz, bool allow_split, double flops, double bytes) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32 || !e->arena) return false;
-  if (!a.tc_ready() || (nz == 2 && !Op::Z_IS_CLASS && !b.tc_ready())) return false;   // operand planes missing or shapes not 16-byte granular
-  Op a0 = a;
-  if (Op::Z_IS_CLASS) a0.set_class(0);
-  int M = a0.M, N = a0.N, K = a0.K;
-  if (!Op::Z_IS_CLASS && nz == 2) { M = std::max(M, b.M); N = std::max(N, b.N); K = std::max(K, b.K); }
+  if (nops < 1 || nops > 4) return false;
+  int M = 0, N = 0, K = 0;
+  for (int i = 0; i < nops; ++i) {
+    if (!ops[i].tc_ready()) return false;                       // operand planes missing or shapes not 16-byte granular
+    Op a0 = ops[i];
+    if (Op::Z_IS_CLASS) a0.set_class(0);
+    M = std::max(M, a0.M); N = std::max(N, a0.N); K = std::max(K, a0.K);
+  }
   if (M < 64 || N < 24 || K < 32) return false;                 // small / odd layers stay on the fp32 CUDA-core kernel
   const int bn = N <= 32 ? 32 : 64;
   const int MT = (M + tc::BM - 1) / tc::BM, NT = (N + bn - 1) / bn;
-  const long long tiles0 = (long long)MT * NT * nz;
+  long long tiles0 = 0;                                         // tiles that hold work (operand sets may differ in M)
+  for (int i = 0; i < nops; ++i) { Op a0 = ops[i]; if (Op::Z_IS_CLASS) a0.set_class(0); tiles0 += (long long)((a0.M + tc::BM - 1) / tc::BM) * ((a0.N + bn - 1) / bn); }
+  if (Op::Z_IS_CLASS) tiles0 *= nz;
   const int ktiles = (K + tc::BK - 1) / tc::BK;
   int nsplit = 1;
-  if (!Op::Z_IS_CLASS && (allow_split || tiles0 < e->nsm))      // splitk_reduce has no notion of dgrad parity classes
+  if (!Op::Z_IS_CLASS && (allow_split || tiles0 < e->nsm || ktiles > 32))   // splitk_reduce has no notion of dgrad parity classes
     nsplit = e->tc_split > 0 ? std::min(e->tc_split, std::max(1, ktiles / 4)) : tc_pick_split(e, tiles0, ktiles, bn, (long long)M * N, nz);
   const long long ws_stride = (long long)M * N;
-  const int ntiles = (int)(tiles0 * nsplit);
+  const int ntiles = MT * NT * nz * nsplit;
   {
     Scope sc(e, name, flops, bytes);
-    // short k loops: two accumulator sets (overlapped epilogue) and a single main accumulator - at most ~150 truncating adds per
-    // output; long k loops: the main product interleaved over two accumulators, one set (the epilogue is a small fraction there)
-    const int ksteps = ((ktiles + nsplit - 1) / nsplit) * (tc::BK / 8);
-    (void)ksteps;
-    if (bn == 32) tc_launch_v<32, 2, 2, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
-    else tc_launch_v<64, 2, 1, Op>(e, a, b, nsplit, ws_stride, MT, NT, ntiles);
+    if (bn == 32) tc_launch_v<32, 2, 2, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+    else tc_launch_v<64, 2, 1, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
-    dim3 g2((unsigned)std::min<long long>((ws_stride / 4 + 255) / 256, 4 * e->nsm), nz);
-    splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(a, b, nsplit, e->lws, ws_stride);
-    CK(cudaGetLastError());
+    for (int z = 0; z < nz; z += 2) {
+      dim3 g2((unsigned)std::min<long long>((ws_stride / 4 + 255) / 256, 4 * e->nsm), std::min(2, nz - z));
+      splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(ops[z], ops[std::min(z + 1, nops - 1)], nsplit, e->lws + (long long)z * nsplit * ws_stride, ws_stride);
+      CK(cudaGetLastError());
+    }
   }
   return true;
 }
 
-bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, false, fl, by); }
-bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int ntow, double fl, double by) {
-  return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, false, fl, by);
-}
-bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, false, fl, by); }
-bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double fl, double by) {
-  return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, false, fl, by);
-}
-bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double fl, double by) {
-  return launch_tc(e, name, op, op, op.g.S * op.g.S, false, fl, by);
-}
-bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double fl, double by) {
-  return launch_tc(e, name, ops[0], ops[ntow - 1], ntow, true, fl, by);
-}
-bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double fl, double by) { return launch_tc(e, name, op, op, 1, true, fl, by); }
+bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp* ops, int nops, double fl, double by) { return launch_tc(e, name, ops, nops, nops, false, fl, by); }
+bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int nops, double fl, double by) { return launch_tc(e, name, ops, nops, nops, false, fl, by); }
+bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, 1, false, fl, by); }
+bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double fl, double by) { return launch_tc(e, name, ops, ntow, ntow, false, fl, by); }
+bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, op.g.S * op.g.S, false, fl, by); }
+bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double fl, double by) { return launch_tc(e, name, ops, ntow, ntow, true, fl, by); }
+bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, 1, true, fl, by); }
 
 // first conv layer on raw bytes: (re)build its 1/255-scaled weight copy for both networks
 void tc_params_changed(dqn_engine* e) {
