@@ -142,6 +142,7 @@ struct dqn_engine {
   int tc_split = 0;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
+  int a8 = 0;              // 1: the first conv layer (forward and weight gradient) reads the byte batch directly, no fp32 copy of it exists
   int merge_fwd = 0;       // 1: online and target forward share launches layer by layer; measured slower than two lanes on B200 (0.571 vs 0.539 ms/step)
 };
 
@@ -232,7 +233,7 @@ void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everyt
 // ---- network schedule ---------------------------------------------------------------------------
 // One forward pass: parameters P applied to the rows of X.  Xs: the input batch as fp32 for the tensor-core path (null => fp32
 // CUDA-core kernels only); w1s: the first conv layer's weights pre-scaled by 1/255 when Xs holds raw byte values.
-struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; };
+struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; bool tc; };
 
 // Layer by layer over all passes.  On the tensor-core path the passes of a layer (online network on [s ; s'], target network on s')
 // and the two towers of a Dense layer share ONE launch: the persistent kernels serialise on the machine anyway, and one launch
@@ -250,7 +251,11 @@ void forward(E* e, const Pass* ps, int np) {
       op.X = cur[p]; op.x_u8 = cur_u8[p]; op.W = ps[p].P + c.w.off; op.Y = ps[p].bufs->conv_out[l]; op.act = c.w.act; op.nimg = rows; op.g = c.g;
       op.M = rows * c.g.OH * c.g.OW; op.N = c.g.Cout; op.K = c.w.K;
       op.vecA = (c.g.Cin % 4 == 0); op.vecB = (c.g.Cout % 4 == 0);
-      if (ps[p].Xs) { op.Xs = cur_s[p]; op.Ws = (l == 0 && cur_u8[p]) ? ps[p].w1s : ps[p].P + c.w.off; op.a_single = (l == 0 && cur_u8[p]); }
+      if (ps[p].tc) {
+        const bool raw = (l == 0 && cur_u8[p]);                 // raw byte observations: exact single-plane operand, weights pre-scaled by 1/255
+        op.Xs = cur_s[p]; op.Ws = raw ? ps[p].w1s : ps[p].P + c.w.off; op.a_single = raw;
+        if (raw && e->a8) { op.a8 = 1; op.Xs = nullptr; }       // ... read straight from the byte batch
+      }
       fl[p] = 2.0 * op.M * op.N * op.K;
       by[p] = (double)rows * c.g.IH * c.g.IW * c.g.Cin * (cur_u8[p] ? 1 : 4) + (double)(op.K + 1) * op.N * 4 + (double)op.M * op.N * 4;
       fls += fl[p]; bys += by[p];
@@ -274,7 +279,7 @@ void forward(E* e, const Pass* ps, int np) {
         op.X = l == 0 ? cur[p] : (const void*)ps[p].bufs->tow_out[t][l - 1]; op.ldx = w.K; op.x_u8 = l == 0 ? cur_u8[p] : 0;
         op.W = ps[p].P + w.off; op.C = ps[p].bufs->tow_out[t][l]; op.ldc = w.N; op.act = w.act; op.M = rows; op.N = w.N; op.K = w.K;
         op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
-        if (ps[p].Xs) { op.Xs = l == 0 ? (cur_u8[p] ? nullptr : cur_s[p]) : ps[p].bufs->tow_out[t][l - 1]; op.Ws = ps[p].P + w.off; op.a_single = 0; }
+        if (ps[p].tc) { op.Xs = l == 0 ? (cur_u8[p] ? nullptr : cur_s[p]) : ps[p].bufs->tow_out[t][l - 1]; op.Ws = ps[p].P + w.off; op.a_single = 0; }
         fl[p] += 2.0 * rows * op.N * op.K;
         by[p] += 4.0 * ((double)rows * op.K / (l == 0 ? e->ntow : 1) + (double)(op.K + 1) * op.N + (double)rows * op.N);
       }
@@ -399,6 +404,7 @@ void backward(E* e, bool conc) {
     // a bias row that would open a 128-row tile of its own (257 = 2 x 128 + 1 rows in the first layer) is summed by colsum_kernel instead
     const bool split_bias = e->arena && (c.w.K % 128 == 0) && c.w.K <= 256 && (c.g.Cout % 4 == 0) && c.g.Cout <= 1024;   // worth a launch only when it saves >= 1/3 of the tiles
     if (split_bias) { wg_tc.M = c.w.K; wg_tc.no_bias = 1; }
+    if (wg.a_single && e->a8) { wg_tc.a8 = 1; wg_tc.Xs = nullptr; }     // first layer: the byte batch itself is the operand
     {
       if (conc) order_after(e, e->stream2, e->stream);
       Lane lane(e, conc);
@@ -474,9 +480,10 @@ void enqueue_step(E* e, bool sample) {
   const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? (e->elem_bytes == 1 ? e->xb_f : (const float*)e->xb) : nullptr;
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
   e->ev_next = 0;
-  const Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s};
-  const Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s};
-  if (xs && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
+  const bool tcp = e->arena && e->obs_row_bytes % 16 == 0 && (xs != nullptr || e->a8);
+  const Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s, tcp};
+  const Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s, tcp};
+  if (tcp && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
     const Pass both[2] = {p_on, p_tg};
     forward(e, both, 2);
   } else {
@@ -1101,7 +1108,7 @@ int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* 
       const int c = (int)std::min<long long>(chunk, n - t0);
       CK(cudaMemcpyAsync(h->stage, (const uint8_t*)obs + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
       relayout(h, h->stage, h->xb, c, h->elem_bytes == 1, 0, 1);
-      const Pass pa{which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, (int)c, &h->on, "act", nullptr, nullptr};
+      const Pass pa{which == DQN_NET_TARGET ? h->theta_t : h->theta, h->xb, h->elem_bytes == 1, (int)c, &h->on, "act", nullptr, nullptr, false};
       forward(h, &pa, 1);
       float* q = h->on.tow_out[h->ntow - 1][L];
       if (h->cfg.dueling) {

@@ -167,6 +167,7 @@ struct KCtx { long long off; int t0, t1, t2; long long offb; };
 // ------------------------------------------------------------------------------------------------
 // Dense forward:  C[m][n] = act( sum_k X[m][k] W[k][n] + W[K][n] )
 struct DenseFwdOp {
+  static constexpr bool HAS_A8 = false;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = false, B_KCONTIG = false, Z_IS_CLASS = false;
   const void* X; long long ldx; int x_u8;
   const float* W;            // [(K+1)][N]
@@ -209,6 +210,7 @@ struct DenseFwdOp {
 
 // Dense dgrad:  dX[m][n] (+)= sum_k D[m][k] W[n][k]  ;  times act'(Y[m][n]) when apply_act
 struct DenseDgradOp {
+  static constexpr bool HAS_A8 = false;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = false, B_KCONTIG = true, Z_IS_CLASS = false;
   const float* D; long long ldd;
   const float* W;            // [(Kin+1)][Nout]; here GEMM-N = Kin, GEMM-K = Nout
@@ -275,6 +277,7 @@ struct DenseDgradOp {
 
 // Dense wgrad:  dW[m][n] = sum_k [X 1][k][m] D[k][n],  m in [0, Kin], k over the batch rows
 struct DenseWgradOp {
+  static constexpr bool HAS_A8 = false;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = true, B_KCONTIG = false, Z_IS_CLASS = false;
   const void* X; long long ldx; int x_u8;
   const float* D; long long ldd;
@@ -336,13 +339,22 @@ struct ConvGeom {
 
 // Conv forward (NHWC, weights [(KH*KW*Cin+1)][Cout], taps already flipped to cross-correlation order)
 struct ConvFwdOp {
+  static constexpr bool HAS_A8 = true;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = false, B_KCONTIG = false, Z_IS_CLASS = false;
   const void* X; int x_u8;
   const float* W; float* Y; int act; int nimg; ConvGeom g;
   int M, N, K;
   int vecA, vecB;
   const float* Xs; const float* Ws; float* Ys; long long lo_delta; int a_single;
-  DQN_HD bool tc_ready() const { return Xs && Ws && (g.Cin % 4 == 0) && (N % 4 == 0); }
+  int a8;                    // tensor-core path reads the byte tensor X itself (16 consecutive k per chunk) instead of an fp32 copy Xs
+  // byte chunks: 16 consecutive k are 16 contiguous, 16-byte aligned bytes iff a tap row (KW*Cin) is a multiple of 32 and pixel
+  // strides (S*Cin, IW*Cin, image size) are multiples of 16
+  DQN_HD bool tc8_ready() const {
+    return a8 && x_u8 && X && Ws && (N % 4 == 0) && ((g.KW * g.Cin) % 32 == 0) && ((g.S * g.Cin) % 16 == 0) && ((g.IW * g.Cin) % 16 == 0) &&
+           (((long long)g.IH * g.IW * g.Cin) % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  }
+  DQN_HD bool tc_ready() const { return a8 ? tc8_ready() : (Xs && Ws && (g.Cin % 4 == 0) && (N % 4 == 0)); }
+  DQN_HD const uint8_t* ptrA8(const ACtx& c, const KCtx& kc, int, int k) const { return (c.valid && k < K) ? (const uint8_t*)X + c.base + kc.off : nullptr; }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const { return (c.valid && k < K) ? Xs + c.base + kc.off : nullptr; }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
   DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M && k0 + bk <= K; }
@@ -394,6 +406,7 @@ struct ConvFwdOp {
 
 // Conv wgrad: dW[m][co] = sum_pix [im2col(X) 1][pix][m] D[pix][co];  m = (kh,kw,ci) or the bias row
 struct ConvWgradOp {
+  static constexpr bool HAS_A8 = true;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = true, B_KCONTIG = false, Z_IS_CLASS = false;
   const void* X; int x_u8;
   const float* D; float* dW; int nimg; ConvGeom g;
@@ -401,8 +414,16 @@ struct ConvWgradOp {
   int vecA, vecB;
   const float* Xs; const float* Ds; const float* ones; long long lo_delta; int a_single; float out_scale;
   int no_bias;               // 1: M = KH*KW*Cin, the bias gradient (column sums of D) is produced by colsum_kernel instead of a ones row
+  int a8;                    // tensor-core path reads the byte tensor X itself (16 consecutive m per chunk); needs no_bias
   DQN_HD int kin() const { return no_bias ? M : M - 1; }
-  DQN_HD bool tc_ready() const { return Xs && Ds && ones && (g.Cin % 4 == 0) && (N % 4 == 0); }
+  DQN_HD bool tc8_ready() const {
+    return a8 && no_bias && x_u8 && X && Ds && (N % 4 == 0) && (M % 16 == 0) && ((g.KW * g.Cin) % 16 == 0) && ((g.S * g.Cin) % 16 == 0) &&
+           ((g.IW * g.Cin) % 16 == 0) && (((long long)g.IH * g.IW * g.Cin) % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  }
+  DQN_HD bool tc_ready() const { return a8 ? tc8_ready() : (Xs && Ds && ones && (g.Cin % 4 == 0) && (N % 4 == 0)); }
+  DQN_HD const uint8_t* ptrA8(const ACtx& c, const KCtx& kc, int m, int k) const {     // 16 consecutive m (taps x channels) at pixel k
+    return (c.valid && k < K && m + 16 <= kin()) ? (const uint8_t*)X + kc.off + c.base : nullptr;
+  }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int m, int k) const {     // 4 consecutive m (channels of one tap) at pixel k
     if (!c.valid || k >= K) return nullptr;
     const int cnt = kin() - m;
@@ -458,6 +479,7 @@ struct ConvWgradOp {
 // Conv dgrad by stride-parity class (ph,pw): rows are the input pixels with ih%S==ph, iw%S==pw, and only
 // the taps kh = ph + S*th, kw = pw + S*tw can reach them:  oh = ih/S - th, ow = iw/S - tw.
 struct ConvDgradOp {
+  static constexpr bool HAS_A8 = false;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = false, B_KCONTIG = true, Z_IS_CLASS = true;
   const float* D; const float* W; float* dX; const float* Yprev; int act; int apply_act; int nimg; ConvGeom g;
   int ph, pw, AH, BW, TH, TW;

@@ -26,7 +26,9 @@
 #ifndef TC_PRODUCER_CPASYNC
 #define TC_PRODUCER_CPASYNC 1      // 1: cp.async producers (faster in the full step on B200), 0: ld.global.nc -> st.shared
 #endif
+#ifndef TC_CP_CG
 #define TC_CP_CA 1
+#endif
 #ifndef TC_HI_TRUNC
 #define TC_HI_TRUNC 1
 #endif
@@ -87,14 +89,20 @@ template <> struct AStage<true> {                             // MN-major source
   static constexpr int BYTES = BK * PITCH;
 };
 
+// byte operands (raw observations): 32 k per row are 32 bytes
+template <bool MN> struct AStage8;
+template <> struct AStage8<false> { static constexpr int PITCH = BK + 16; static constexpr int BYTES = BM * PITCH; };   // row r: 32 bytes + 16 of padding
+template <> struct AStage8<true>  { static constexpr int PITCH = BM + 16; static constexpr int BYTES = BK * PITCH; };   // k row kk: 128 bytes + 16
+
 // One persistent CTA per SM.  Shared-memory ring: STAGES slots of {A staging, B raw(=hi), B lo}; DEPTH stages of cp.async traffic stay
 // in flight behind the stage being finished, across tile boundaries (the ring never drains between tiles).
 // TMEM (all 512 columns): NBUF accumulator sets of NACC x BN columns (the epilogue of tile i overlaps the main loop of tile i+1 when
 // NBUF = 2), then a ring of AST A-operand stages of 64 columns each (32 k-columns of the hi plane, 32 of the lo plane).
-template <int BN, int R, int NBUF, bool A_MN, bool B_MN> struct Lay {
+template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false> struct Lay {
   using TB = Tile<BN, B_MN>;
   using SA = AStage<A_MN>;
-  static constexpr int A_BYTES = (SA::BYTES + 1023) / 1024 * 1024;
+  using SA8 = AStage8<A_MN>;
+  static constexpr int A_BYTES = ((A8 ? SA8::BYTES : SA::BYTES) + 1023) / 1024 * 1024;
   static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;            // A staging, B_hi(raw), B_lo
   static constexpr int TAIL = 1024 + 256;                              // alignment slack + barriers / tmem address
@@ -256,7 +264,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 #endif
 }
 __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
+#ifdef TC_CP_CA
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive when this thread's prior cp.async have landed
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -266,14 +278,21 @@ __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN, int R, int NBUF, class Op>
+// byte k -> the fp32 bit pattern of float(k): 0x4B000000 | k is 2^23 + k, exactly
+__device__ __forceinline__ uint32_t byte_to_f32(uint32_t w, int j) {
+  return __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)) - 8388608.0f);
+}
+
+template <int BN, int R, int NBUF, bool A8, class Op>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, const __grid_constant__ Op opc, const __grid_constant__ Op opd,
                int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src, int MT, int NT, int ntiles) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
-  using L = Lay<BN, R, NBUF, A_MN, B_MN>;
+  using L = Lay<BN, R, NBUF, A_MN, B_MN, A8>;
   using TB = typename L::TB;
   using SA = typename L::SA;
+  using SA8 = typename L::SA8;
+  static_assert(!A8 || Op::HAS_A8, "byte operands: conv forward / conv weight gradient only");
   constexpr int STAGES = L::STAGES, NACC = L::NACC, AST = L::AST;
   constexpr uint32_t ACOL0 = L::ACC_COLS;                        // first TMEM column of the A-operand ring
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -343,24 +362,40 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
+    // byte operand: 256 chunks of 16 bytes per stage - K-major: row (tid/2 + 64 i), half c = tid & 1; MN-major: k row tid/4, m chunks (tid%4) + 4 i
+    constexpr int A_PER8 = 256 / LOADERS;
     int is = 0; uint32_t iph = 0;                              // ring slot / phase of the next stage
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
       ACtx actx[A_PER];
+      if constexpr (A8) {
 #pragma unroll
-      for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(A_MN ? m0 + ((tid % MPT) + MPT * i) * 4 : m0 + (tid >> 3) + i * (LOADERS / 8));
+        for (int i = 0; i < A_PER8; ++i) actx[i] = op.prepA(A_MN ? m0 + ((tid % MPT) + MPT * i) * 16 : m0 + (tid >> 1) + i * (LOADERS / 2));
+      } else {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) actx[i] = op.prepA(A_MN ? m0 + ((tid % MPT) + MPT * i) * 4 : m0 + (tid >> 3) + i * (LOADERS / 8));
+      }
       for (int it = 0; it < nk; ++it) {
         const int k0 = (kt0 + it) * BK;
         const uint32_t a_st = sbase + is * L::STAGE_BYTES;
         const uint32_t b_hi = a_st + L::A_BYTES;
         KCtx kc; kc.off = 0; kc.offb = 0; kc.t0 = kc.t1 = kc.t2 = 0;
-        kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 7) * 4);   // one k decode per thread and stage: its k row (MN-major) or k chunk (K-major)
+        if constexpr (A8) kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 1) * 16);
+        else kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 7) * 4);   // one k decode per thread and stage: its k row (MN-major) or k chunk (K-major)
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
 #ifndef TC_EXP_NOLOAD
         // a stage that lies entirely inside the operand (all but the last m tile / k stage) takes the unchecked form: no
         // predicates, no zero-fill source select - the loaders' instruction stream is what bounds the short-k layers
-        if (op.interiorA(m0, k0, BM, BK)) {
+        if constexpr (A8) {
+#pragma unroll
+          for (int i = 0; i < A_PER8; ++i) {
+            const uint8_t* p; uint32_t off;
+            if (A_MN) { const int mc = (tid % MPT) + MPT * i; p = op.ptrA8(actx[i], kc, m0 + mc * 16, k0 + tid / MPT); off = (tid / MPT) * SA8::PITCH + mc * 16; }
+            else { const int r = (tid >> 1) + i * (LOADERS / 2); p = op.ptrA8(actx[i], kc, m0 + r, k0 + (tid & 1) * 16); off = r * SA8::PITCH + (tid & 1) * 16; }
+            cp_async16(a_st + off, p ? (const void*)p : (const void*)zero_src, p ? 16u : 0u);
+          }
+        } else if (op.interiorA(m0, k0, BM, BK)) {
 #pragma unroll
           for (int i = 0; i < A_PER; ++i) {
             const float* p = A_MN ? op.ptrA_u(actx[i], kc, m0 + ((tid % MPT) + MPT * i) * 4, k0 + tid / MPT)
@@ -432,7 +467,26 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         mbar_wait(bar_landed + 8 * s, ph);                     // every loader's copies of this stage have landed
 #ifndef TC_EXP_NOFIN
         uint32_t v[32];
-        if (A_MN) {
+        if constexpr (A8) {                                    // bytes -> the fp32 words of their values (exact TF32 operands: no lo plane)
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              uint32_t b;
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a_st + (uint32_t)(i * SA8::PITCH + row)));
+              v[i] = byte_to_f32(b, 0);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 f = lds128(a_st + (uint32_t)(row * SA8::PITCH + i * 16));
+              const uint32_t w[4] = {__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w)};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[16 * i + 4 * q + j] = byte_to_f32(w[q], j);
+            }
+          }
+        } else if (A_MN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
         } else {
@@ -591,16 +645,16 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #ifndef TC_KERNEL_ONLY
 namespace {
 
-template <int BN, int R, int NBUF, class Op>
+template <int BN, int R, int NBUF, bool A8, class Op>
 void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long ws_stride, int MT, int NT, int ntiles) {
-  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, A8>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, A8, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set = true;
   }
   const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
-  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
+  tc::tc_gemm_kernel<BN, R, NBUF, A8, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
                                                                             nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles);
   CK(cudaGetLastError());
 }
@@ -654,8 +708,18 @@ bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz,
   const int ntiles = MT * NT * nz * nsplit;
   {
     Scope sc(e, name, flops, bytes);
-    if (bn == 32) tc_launch_v<32, 2, 2, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
-    else tc_launch_v<64, 2, 1, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+    bool a8 = false;
+    if constexpr (Op::HAS_A8) { a8 = ops[0].a8 != 0; for (int i = 1; i < nops; ++i) a8 = a8 && ops[i].a8 != 0; }
+    if constexpr (Op::HAS_A8) {
+      if (a8) {
+        if (bn == 32) tc_launch_v<32, 2, 2, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+        else tc_launch_v<64, 2, 1, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+      }
+    }
+    if (!a8) {
+      if (bn == 32) tc_launch_v<32, 2, 2, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+      else tc_launch_v<64, 2, 1, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles);
+    }
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
@@ -690,14 +754,20 @@ void tc_init(dqn_engine* e) {
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
   const bool bytes = e->elem_bytes == 1;
-  const long long o_xb = take(bytes ? (long long)e->rows_on * e->obs_elems : 0);
+  e->a8 = 0;
+  if (bytes && !e->convs.empty() && !getenv("DQN_NO_A8")) {     // byte-operand form of the first conv layer: geometry must give 16-byte chunks
+    const dqn::ConvGeom& g = e->convs[0].g;
+    e->a8 = ((g.KW * g.Cin) % 32 == 0) && ((g.S * g.Cin) % 16 == 0) && ((g.IW * g.Cin) % 16 == 0) && (((long long)g.IH * g.IW * g.Cin) % 16 == 0) &&
+            (g.Cout % 4 == 0) && (e->convs[0].w.K % 128 == 0) && e->convs[0].w.K <= 256;
+  }
+  const long long o_xb = take((bytes && !e->a8) ? (long long)e->rows_on * e->obs_elems : 0);
   e->w_scale_lo = e->w_scale_hi = 0;
   if (bytes && !e->convs.empty()) { e->w_scale_lo = e->convs[0].w.off; e->w_scale_hi = e->convs[0].w.off + (long long)e->convs[0].w.K * e->convs[0].w.N; }
   const long long wb = e->w_scale_hi - e->w_scale_lo;
   const long long o_won = take(wb), o_wtg = take(wb), o_ones = take(64);
   e->arena = dalloc<float>(off);
   float* a = e->arena;
-  e->xb_f = bytes ? a + o_xb : nullptr;
+  e->xb_f = (bytes && !e->a8) ? a + o_xb : nullptr;
   e->w_on_s = wb ? a + o_won : nullptr; e->w_tg_s = wb ? a + o_wtg : nullptr; e->ones = a + o_ones;
   const float one = 1.f;
   CK(cudaMemcpy(e->ones, &one, sizeof(float), cudaMemcpyHostToDevice));       // {1,0,0,0}

@@ -37,11 +37,11 @@ static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long
   constexpr int R = BN == 32 ? 2 : TEST_R, NBUF = BN == 32 ? 2 : (TEST_R == 1 ? 2 : 1);
   using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
   static bool attr = false;
-  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
+  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, false, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
   Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
   const int MT = (o0.M + 127) / 128, NT = (o0.N + BN - 1) / BN, ntiles = MT * NT * nz * nsplit;
   const int grid = ntiles < g_nsm ? ntiles : g_nsm;
-  tc::tc_gemm_kernel<BN, R, NBUF, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
+  tc::tc_gemm_kernel<BN, R, NBUF, false, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
 }
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
