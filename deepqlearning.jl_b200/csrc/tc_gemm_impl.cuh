@@ -37,28 +37,34 @@ namespace tc {
 
 #ifdef TC_TRACE
 __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (producer warp 0 and the MMA warp): tuning aid of the selftest
-#define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 512) tc_trace[(st) * 16 + (ev)] = clock64(); } while (0)
+#define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 1000) tc_trace[(st) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define TRACE(st, ev) do { } while (0)
 #endif
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
-#ifndef TC_LOAD_WARPS
-#define TC_LOAD_WARPS 4
-#endif
-#ifndef TC_NGRP
-#define TC_NGRP 2
-#endif
-constexpr int LOAD_WARPS = TC_LOAD_WARPS;    // loader warps: chunk addresses + cp.async only (an LDGSTS that waits for a queue slot blocks nothing else)
+// Warp roles of the 1024-thread CTA (eight warpgroups; register budgets are re-balanced per role with setmaxnreg).  Every role is a
+// serial instruction stream per warp - measured 6 cycles per instruction on B200 for these address / convert chains - so the way to
+// more throughput is more warps per role with less work each, not fewer instructions:
+//   warps  0- 7  loaders     chunk addresses + cp.async only (an LDGSTS that waits for a queue slot blocks nothing else)
+//   warps  8-23  converters  two groups of 8 warps that take alternate stages; in a group, warp w handles TMEM lane quarter w & 3 and
+//                            the k half (w >> 2) & 1 of its rows
+//   warps 24-27  epilogue    warp & 3 = the TMEM lane quarter it may read
+//   warps 28-30  MMA issue   one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s); one thread can issue a tcgen05
+//                            instruction every ~75 cycles, three streams keep the tensor core fed.  Warp 31 idles (completes the warpgroup).
+constexpr int LOAD_WARPS = 8;
 constexpr int LOADERS = 32 * LOAD_WARPS;
-constexpr int NGRP = TC_NGRP;    // converter groups (4 warps each: one per TMEM lane quarter) that take alternate stages
-constexpr int CONV_WARPS = 4 * NGRP;
-constexpr int EPI_WARPS = 4;     // epilogue warps: warp & 3 = the TMEM lane quarter it may read
-constexpr int NMMA = 3;          // MMA-issuing warps: one per product (hi*hi, lo*hi, hi*lo), each with its own accumulator(s) -
-                                 // one thread can issue a tcgen05 instruction every ~75 cycles, three streams keep the tensor core fed
+constexpr int NGRP = 2;
+constexpr int GW = 8;            // warps per converter group
+constexpr int CONV_WARPS = GW * NGRP;
+constexpr int EPI_WARPS = 4;
+constexpr int NMMA = 3;
 constexpr int CONV_WARP0 = LOAD_WARPS, EPI_WARP0 = CONV_WARP0 + CONV_WARPS, MMA_WARP0 = EPI_WARP0 + EPI_WARPS;
-constexpr int THREADS = 32 * (MMA_WARP0 + NMMA);              // 608: warps 0-3 loaders, 4-11 converters, 12-15 epilogue, 16-18 MMA
+constexpr int THREADS = 1024;
+static_assert(MMA_WARP0 + NMMA <= THREADS / 32 && CONV_WARP0 % 4 == 0 && EPI_WARP0 % 4 == 0 && MMA_WARP0 % 4 == 0, "warpgroup-aligned roles");
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // shared-memory tile of one operand plane for one stage
 template <int ROWS, bool MN> struct Tile;
@@ -310,7 +316,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   const bool a_lo = !opa.a_single;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, LOADERS); mbar_init(bar_full + 8 * s, 4); mbar_init(bar_empty + 8 * s, NMMA); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, NMMA); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -345,6 +351,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
   if (warp < LOAD_WARPS) {
+    reg_dec<56>();
     // ================= loaders: chunk addresses + cp.async into ring slot, completion signalled on landed[slot] =================
     constexpr int A_PER = BM * (BK / 4) / LOADERS;             // 8 chunks of A per thread per stage
     constexpr int B_PER = B_CH / LOADERS;                      // BN/16 chunks of B
@@ -365,6 +372,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
     // byte operand: 256 chunks of 16 bytes per stage - K-major: row (tid/2 + 64 i), half c = tid & 1; MN-major: k row tid/4, m chunks (tid%4) + 4 i
     constexpr int A_PER8 = 256 / LOADERS;
     int is = 0; uint32_t iph = 0;                              // ring slot / phase of the next stage
+    int ltr = 0; (void)ltr;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
@@ -383,7 +391,9 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         KCtx kc; kc.off = 0; kc.offb = 0; kc.t0 = kc.t1 = kc.t2 = 0;
         if constexpr (A8) kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 1) * 16);
         else kc = op.prepK(A_MN ? k0 + tid / MPT : k0 + (tid & 7) * 4);   // one k decode per thread and stage: its k row (MN-major) or k chunk (K-major)
+        if (warp == 0) TRACE(ltr, 0);
         mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
+        if (warp == 0) TRACE(ltr, 1);
 #ifndef TC_EXP_NOLOAD
         // a stage that lies entirely inside the operand (all but the last m tile / k stage) takes the unchecked form: no
         // predicates, no zero-fill source select - the loaders' instruction stream is what bounds the short-k layers
@@ -429,6 +439,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #endif
         // the barrier receives this thread's arrival once all of its copies above have landed
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_landed + 8 * is) : "memory");
+        if (warp == 0) TRACE(ltr, 2);
+        ++ltr;
         if (++is == STAGES) { is = 0; iph ^= 1; }
       }
     }
@@ -440,10 +452,10 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
     //   B: lo of the raw plane -> B lo plane; then the stage is handed to the MMA warps.
     // One stage is a serial chain of several hundred cycles for a warp (wait, LDS, split, tcgen05.st, wait::st, fences); two groups
     // working on alternate stages overlap two such chains.
-    constexpr int GT = 128;                                    // threads per group: one per row of the tile
+    constexpr int GT = 32 * GW;                                // threads per group: two per row of the tile (k halves)
     constexpr int B_PER = B_CH / GT;
-    const int cw = warp - CONV_WARP0, grp = cw >> 2, gtid = tid - 32 * CONV_WARP0 - grp * GT;
-    const int q4 = warp & 3;
+    const int cw = warp - CONV_WARP0, grp = cw / GW, gw = cw % GW, gtid = tid - 32 * CONV_WARP0 - grp * GT;
+    const int q4 = gw & 3, kh = gw >> 2;                       // CONV_WARP0 is a multiple of 4: gw & 3 == warp & 3, the lane quarter this warp may write
     const int row = q4 * 32 + lane;
     uint32_t b_off[B_PER];
 #pragma unroll
@@ -452,8 +464,9 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       if (B_MN) { const int g = e % (BN / 4), kk = e / (BN / 4); b_off[i] = (g >> 3) * TB::LBO + kk * 128 + (((g & 7) ^ ((kk & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
-    const uint32_t a_rd = A_MN ? (uint32_t)(row * 4) : (uint32_t)(row * SA::PITCH);
-    const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0;
+    const uint32_t a_rd = A8 ? (A_MN ? (uint32_t)(kh * 16 * SA8::PITCH + row) : (uint32_t)(row * SA8::PITCH + kh * 16))
+                             : (A_MN ? (uint32_t)(kh * 16 * SA::PITCH + row * 4) : (uint32_t)(row * SA::PITCH + kh * 64));
+    const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0 + (uint32_t)(kh * 16);
     int gg = 0;                                                // global stage counter (all tiles)
     int s = grp; uint32_t ph = 0;                              // ring slot / phase of this group's next stage
     int as = grp % AST;                                        // its TMEM A-ring slot
@@ -465,33 +478,31 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         const uint32_t a_st = sbase + s * L::STAGE_BYTES;
         const uint32_t b_hi = a_st + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
         mbar_wait(bar_landed + 8 * s, ph);                     // every loader's copies of this stage have landed
+        if (gw == 0) TRACE(gg, 3);
 #ifndef TC_EXP_NOFIN
-        uint32_t v[32];
+        uint32_t v[16];                                        // this thread's 16 k values of its row
         if constexpr (A8) {                                    // bytes -> the fp32 words of their values (exact TF32 operands: no lo plane)
           if (A_MN) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               uint32_t b;
-              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a_st + (uint32_t)(i * SA8::PITCH + row)));
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a_st + a_rd + (uint32_t)(i * SA8::PITCH)));
               v[i] = byte_to_f32(b, 0);
             }
           } else {
+            const float4 f = lds128(a_st + a_rd);
+            const uint32_t w[4] = {__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w)};
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 f = lds128(a_st + (uint32_t)(row * SA8::PITCH + i * 16));
-              const uint32_t w[4] = {__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w)};
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[16 * i + 4 * q + j] = byte_to_f32(w[q], j);
-            }
+              for (int j = 0; j < 4; ++j) v[4 * q + j] = byte_to_f32(w[q], j);
           }
         } else if (A_MN) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
+          for (int i = 0; i < 16; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const float4 f = lds128(a_st + a_rd + i * 16);
             v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
           }
@@ -506,29 +517,32 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
           mbar_wait(bar_empty + 8 * (g0 % STAGES), (uint32_t)((g0 / STAGES) & 1));
         }
         tc_fence_after();
+        if (gw == 0) TRACE(gg, 4);
 #ifndef TC_EXP_NOFIN
         const uint32_t ta = a_tm + (uint32_t)(as * 64);
-        tmem_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-        tmem_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+        tmem_st16(ta, v);
         if (a_lo) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
-          tmem_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-          tmem_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
+          tmem_st16(ta + 32, v);
         }
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+        if (gw == 0) TRACE(gg, 5);
         tmem_st_wait();
+        if (gw == 0) TRACE(gg, 6);
         fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core's async proxy
 #endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);          // one arrival per warp of the group
+        if (gw == 0) TRACE(gg, 7);
         s += NGRP; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
         as += NGRP; if (as >= AST) as -= AST;
       }
     }
   } else if (warp < MMA_WARP0) {
+    reg_inc<96>();
     // ================= epilogue: TMEM -> registers -> bias/activation or act' -> 16-byte stores =================
     const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
     constexpr int EPI_UNROLL = TC_EPI_UNROLL;                  // column chunks in flight: their bias / act' loads overlap
@@ -592,12 +606,16 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       if (lane == 0) mbar_arrive(bar_acce + 8 * buf);          // accumulator set free again
       if (++buf == NBUF) { buf = 0; aph ^= 1; }
     }
+  } else if (warp >= MMA_WARP0 + NMMA) {
+    reg_dec<40>();                                             // idle warp that completes the MMA warpgroup
   } else {
+    reg_dec<40>();
     // ================= MMA issuers =================
     constexpr uint32_t idesc = make_idesc2(BM, BN, false, B_MN);   // A comes from TMEM: K-major by construction
     const int role = warp - MMA_WARP0;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
     int s = 0; uint32_t ph = 0;
     int as = 0;
+    int mtr = 0; (void)mtr;
     int buf = 0; uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
@@ -607,6 +625,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
       for (int it = 0; it < nk; ++it) {
         mbar_wait(bar_full + 8 * s, ph);
+
         tc_fence_after();
         if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
           const uint32_t b_hi = sbase + s * L::STAGE_BYTES + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
@@ -628,6 +647,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
           if (it == nk - 1) umma_commit(bar_accf + 8 * buf);      // ... and publishes the accumulators after the tile's last stage
         }
         __syncwarp();
+        ++mtr;
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++as == AST) as = 0;
       }

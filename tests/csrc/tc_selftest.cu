@@ -166,11 +166,11 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   {
     std::vector<long long> tr(8192);
     CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 8192));
-    printf("  trace CTA0: stage: P.top empty-ok issued | landed bar-ok | fin:lds'd aempty-ok st-waited fenced done | gap | M.wait full-ok issued\n");
+    printf("  trace CTA0 stage: L.top L.empty-ok L.issued | C.landed-ok C.slot-ok C.st-issued C.st-waited C.arrived   (cycles)\n");
     const long long t0 = tr[0];
-    for (int it = 8; it < 36; ++it) {
+    for (int it = 16; it < 56; ++it) {
       printf("  %2d:", it);
-      for (int j = 0; j < 14; ++j) { if (j == 10) continue; printf(" %7lld", tr[it * 16 + j] ? tr[it * 16 + j] - t0 : -1); }
+      for (int j = 0; j < 8; ++j) printf(" %7lld", tr[it * 8 + j] ? tr[it * 8 + j] - t0 : -1);
       printf("\n");
     }
     std::vector<long long> z(8192, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 8192));
