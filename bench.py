@@ -73,6 +73,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_traffic():
+    """per-launch DRAM bytes of the step's kernels from the committed ncu capture (profiles/*_traffic_*.json), newest file wins"""
+    import glob
+    best = {}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic_*.json"))):
+        try:
+            best = json.load(open(f))
+            best["_file"] = os.path.basename(f)
+        except Exception:
+            pass
+    return best
+
+
 def run_reference(args):
     """The reference's CPU path on this box's host cores (Flux-equivalent restatement, torch-CPU, all threads)."""
     rank = int(os.environ.get("RANK", 0))
@@ -205,17 +218,24 @@ def main():
         tot = sum(k["ms"] * 1 for k in prof)
         kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"])][:12]
         top = max(prof, key=lambda k: k["ms"])
+        traffic = load_traffic()
+        tr = traffic.get(top["name"], {}).get("dram_bytes")
         if top["flops"] > 0:
             tf32_peak = 0.5 * peaks["bf16_sus"]
             ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
-            roof = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+            roof = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": tr,
                     "peak_note": f"dense TF32 = 1/2 of the {peaks['src']} sustained bf16 cuBLAS peak ({peaks['bf16_sus']} TFLOP/s); algorithmic FLOPs of the launch"}
         else:
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-            roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+            roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": tr,
                     "peak_note": f"{peaks['src']} HBM copy bandwidth"}
         step_flops = 26.36e9
         roof["step_tflops_algorithmic"] = step_flops * (args.steps / (ms * 1e-3)) / 1e12
+        roof["traffic_source"] = traffic.get("_file")
+        # the HBM-bound kernels of the step, against the measured copy bandwidth (algorithmic bytes of DESIGN.md section 2)
+        roof["hbm_kernels"] = [{"kernel": k["name"], "achieved": k["bytes"] / (k["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                "frac": k["bytes"] / (k["ms"] * 1e-3) / 1e9 / peaks["hbm"], "traffic": traffic.get(k["name"], {}).get("dram_bytes")}
+                               for k in prof if k["name"] in ("gather_rows", "adam")]
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) --------------------------------
     cpu = None

@@ -726,8 +726,16 @@ __global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __
   if (op.can_store4()) {                     // N % 4 == 0: four columns per thread, vector epilogue (also writes the split planes)
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
       float4 s = make4(0, 0, 0, 0);
-      for (int k = 0; k < nsplit; ++k) {
-        const float4 p = *reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i);
+      int k = 0;
+      for (; k + 8 <= nsplit; k += 8) {        // eight independent loads in flight (small grids are latency bound), added in ascending order
+        float4 p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k + j)) * ws_stride + i));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s.x += p[j].x; s.y += p[j].y; s.z += p[j].z; s.w += p[j].w; }
+      }
+      for (; k < nsplit; ++k) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i));
         s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
       }
       op.store4((int)(i / op.N), (int)(i % op.N), s);

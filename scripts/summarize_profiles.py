@@ -56,8 +56,37 @@ def raw(tag, path, name):
     print(out)
 
 
+# names of the tensor-core launches of one eager step, in launch order (scripts/one_step.py, math mode 1, single lane)
+STEP_ORDER = ["conv1_fwd_target", "conv2_fwd_target", "conv3_fwd_target", "dense1_fwd_target", "conv1_fwd_online", "conv2_fwd_online", "conv3_fwd_online",
+              "dense1_fwd_online", "dense1_wgrad", "dense1_dgrad", "conv3_wgrad", "conv3_dgrad", "conv2_wgrad", "conv2_dgrad", "conv1_wgrad"]
+
+
+def traffic(tag, path, name):
+    """per-launch DRAM bytes (read + write) of the first eager step's kernels -> profiles/<tag>_traffic_<name>.json (bench.py reads it)"""
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr = rows[0]
+    ik, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ur, uw = unit.get(rows[1][ir], 1.0), unit.get(rows[1][iw], 1.0)
+    out, tc = {}, 0
+    for r in rows[2:]:
+        b = float(r[ir]) * ur + float(r[iw]) * uw
+        if "tc_gemm_kernel" in r[ik]:
+            if tc < len(STEP_ORDER):
+                out[STEP_ORDER[tc]] = {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80]}
+            tc += 1
+        else:
+            key = "gather_rows" if "gather_rows" in r[ik] else ("adam" if "adam" in r[ik] else r[ik].split("(")[0])
+            out.setdefault(key, {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80]})
+    dst = os.path.join(ROOT, "profiles", f"{tag}_traffic_{name}.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(dst)
+
+
 if __name__ == "__main__":
     tag, kind, path = sys.argv[1:4]
     name = sys.argv[4] if len(sys.argv) > 4 else os.path.splitext(os.path.basename(path))[0]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    (launches if kind == "launches" else raw)(tag, path, name)
+    {"launches": launches, "raw": raw, "traffic": traffic}[kind](tag, path, name)
