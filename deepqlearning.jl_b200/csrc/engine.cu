@@ -142,6 +142,7 @@ struct dqn_engine {
   int tc_split = 0;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
+  int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction
   int a8 = 0;              // 1: the first conv layer (forward and weight gradient) reads the byte batch directly, no fp32 copy of it exists
   int merge_fwd = 0;       // 1: online and target forward share launches layer by layer; measured slower than two lanes on B200 (0.571 vs 0.539 ms/step)
 };
@@ -284,6 +285,21 @@ void forward(E* e, const Pass* ps, int np) {
         by[p] += 4.0 * ((double)rows * op.K / (l == 0 ? e->ntow : 1) + (double)(op.K + 1) * op.N + (double)rows * op.N);
       }
     snprintf(nm, sizeof nm, "dense%d_fwd", l + 1);
+    if (l == e->depth - 1 && l > 0 && e->fuse_heads && e->tow[e->ntow - 1][l].N <= HEADS_MAXN && e->tow[0][l].N <= HEADS_MAXN) {
+      // the thin output layers of all passes and towers: one warp per row
+      HeadJobs jobs{}; int total = 0;
+      for (int p = 0; p < np; ++p)
+        for (int t = 0; t < e->ntow; ++t) {
+          const DenseFwdOp& op = ops[p * e->ntow + t];
+          jobs.j[jobs.n++] = HeadJob{(const float*)op.X, op.ldx, op.W, op.C, op.M, op.N, op.K, op.act};
+          total += op.M;
+        }
+      snprintf(nm, sizeof nm, "heads_fwd_%s", np > 1 ? "both" : ps[0].tag);
+      Scope sc(e, nm, fl[0] + fl[1], by[0] + by[1]);
+      heads_fwd_kernel<<<(total + 7) / 8, 256, 0, e->ls>>>(jobs);
+      CK(cudaGetLastError());
+      continue;
+    }
     if (!(np > 1 && tc_dense_fwd(e, nm, ops, np * e->ntow, fl[0] + fl[1], by[0] + by[1]))) {
       for (int p = 0; p < np; ++p) {
         DenseFwdOp* o = ops + p * e->ntow;
@@ -341,7 +357,13 @@ void backward(E* e, bool conc) {
       snprintf(nm, sizeof nm, "dense%d_dgrad", l + 1);
       double fl = 0, by = 0;
       for (int t = 0; t < e->ntow; ++t) { fl += 2.0 * B * dg[t].N * dg[t].K; by += 4.0 * ((double)B * dg[t].K + (double)dg[t].N * dg[t].K + 2.0 * B * dg[t].N); }
-      if (!tc_dense_dgrad2(e, nm, dg, e->ntow, fl, by)) launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
+      if (l == e->depth - 1 && e->fuse_heads && dg[0].K <= HEADS_MAXN && dg[e->ntow - 1].K <= HEADS_MAXN && dg[0].N == dg[e->ntow - 1].N) {
+        HeadGradJobs jobs{};
+        for (int t = 0; t < e->ntow; ++t) jobs.j[jobs.n++] = HeadGradJob{dg[t].D, dg[t].W, dg[t].Y, dg[t].dX, B, dg[t].K, dg[t].N, dg[t].act};
+        Scope sc(e, "heads_dgrad", fl, by);
+        heads_dgrad_kernel<<<dim3((unsigned)(((long long)B * dg[0].N + 255) / 256), e->ntow), 256, 0, e->ls>>>(jobs);
+        CK(cudaGetLastError());
+      } else if (!tc_dense_dgrad2(e, nm, dg, e->ntow, fl, by)) launch_igemm(e, nm, dg[0], dg[1], e->ntow, false, fl, by);
     } else if (trunk) {
       // gradient into the trunk: both towers in one contraction (K = N_val + N_adv) - no second launch, no read-modify-write
       const Mat& w0 = e->tow[0][0]; const Mat& w1 = e->tow[e->ntow - 1][0];
@@ -881,6 +903,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     e->ls = e->stream;
     { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
+    { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
     build_topology(e);
     allocate(e);
     tc_init(e);

@@ -527,6 +527,64 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ D
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The last Dense layer of each tower (Dense(k, 1) and Dense(k, |A|), DUEL:36-58) is far too thin for a tiled contraction:
+// 3.6 kFLOP per row.  One warp per (tower, row): lanes stride over k, N <= HEADS_MAXN running sums, a butterfly per output,
+// lane 0 adds the bias row and applies the activation.  Fixed summation order: deterministic.
+constexpr int HEADS_MAXN = 8;
+struct HeadJob {
+  const float* X; long long ldx;       // input rows (previous layer's output)
+  const float* W;                      // augmented matrix [(K+1)][N]
+  float* C;                            // out [rows][N]
+  int rows, N, K, act;
+};
+struct HeadJobs { HeadJob j[4]; int n; };
+__global__ void __launch_bounds__(256) heads_fwd_kernel(const HeadJobs jobs) {
+  int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  int ji = 0;
+  while (ji < jobs.n && w >= jobs.j[ji].rows) { w -= jobs.j[ji].rows; ++ji; }
+  if (ji >= jobs.n) return;
+  const HeadJob& jb = jobs.j[ji];
+  const float* x = jb.X + (long long)w * jb.ldx;
+  float acc[HEADS_MAXN];
+#pragma unroll
+  for (int n = 0; n < HEADS_MAXN; ++n) acc[n] = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < jb.K; k += 32) {
+    const float xv = __ldg(x + k);
+    const float* wr = jb.W + (long long)k * jb.N;
+#pragma unroll
+    for (int n = 0; n < HEADS_MAXN; ++n) if (n < jb.N) acc[n] = fmaf(xv, __ldg(wr + n), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < HEADS_MAXN; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < HEADS_MAXN; ++n)
+      if (n < jb.N) jb.C[(long long)w * jb.N + n] = act_apply(acc[n] + jb.W[(long long)jb.K * jb.N + n], jb.act);
+  }
+}
+
+// reverse of the same layer: dX[b][j] = (sum_n D[b][n] W[j][n]) * act'(Y[b][j]); one thread per (b, j)
+struct HeadGradJob { const float* D; const float* W; const float* Y; float* dX; int rows, N, K, act; };   // K = width of the previous layer
+struct HeadGradJobs { HeadGradJob j[2]; int n; };
+__global__ void __launch_bounds__(256) heads_dgrad_kernel(const HeadGradJobs jobs) {
+  const HeadGradJob& jb = jobs.j[blockIdx.y];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (blockIdx.y >= jobs.n || i >= (long long)jb.rows * jb.K) return;
+  const int b = (int)(i / jb.K), j = (int)(i - (long long)b * jb.K);
+  const float* d = jb.D + (long long)b * jb.N;
+  const float* wr = jb.W + (long long)j * jb.N;
+  float s = 0.f;
+#pragma unroll
+  for (int n = 0; n < HEADS_MAXN; ++n) if (n < jb.N) s = fmaf(__ldg(d + n), __ldg(wr + n), s);
+  jb.dX[i] = s * act_deriv(jb.Y[i], jb.act);
+}
 #endif  // __CUDACC__
 
 }  // namespace dqn
