@@ -128,7 +128,7 @@ struct dqn_engine {
   // nccl
   ncclComm_t comm = nullptr;
   // measurement
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, copy_done = nullptr;
   int counting = 0, launches = 0, launches_per_step = 0;
   int profiling = 0; std::vector<ProfRec> prof; std::vector<cudaEvent_t> ev_pool;
   uint32_t* flush_buf = nullptr; long long flush_n = 0;
@@ -776,7 +776,7 @@ void allocate(E* e) {
   memset(e->host_out, 0, 16);
   CK(cudaHostGetDevicePointer(&e->host_out_dev, e->host_out, 0));
   CK(cudaHostAlloc(&e->idx_h, sizeof(long long) * B, cudaHostAllocDefault));
-  CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1));
+  CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1)); CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
 }
 
 void destroy(E* e) {
@@ -800,6 +800,7 @@ void destroy(E* e) {
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (e->t0) cudaEventDestroy(e->t0);
   if (e->t1) cudaEventDestroy(e->t1);
+  if (e->copy_done) cudaEventDestroy(e->copy_done);
   for (auto ev : e->evs) cudaEventDestroy(ev);
   if (e->stream3) cudaStreamDestroy(e->stream3);
   if (e->stream2) cudaStreamDestroy(e->stream2);
@@ -962,6 +963,14 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
                    const float* td0, int64_t n) {
   return guard(h, [&] {
     if (n < 0 || (n > 0 && (!s || !a || !r || !sp || !done || !td0))) fail(DQN_ERR_INVALID, "null argument");
+    // the reference's asserts (PER:66 td_err + eps > 0; a valid action index) are checked on the host arguments before anything is
+    // enqueued: the call needs no device round trip, and a rejected batch leaves the buffer untouched.  (The ingest kernel raises the
+    // same sticky flags for device-resident input, dqn_replay_add_device; they surface at the next dqn_train_step.)
+    for (long long i = 0; i < n; ++i) {
+      const float base = td0[i] + h->cfg.eps;
+      if (!(base > 0.f)) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
+      if (a[i] < 1 || a[i] > h->cfg.n_actions) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+    }
     const long long rb = h->obs_row_bytes;
     const long long chunk = std::max<long long>(1, std::min<long long>(n, (256LL << 20) / std::max<long long>(1, 2 * rb)));
     const long long per = 2 * rb + 4 + 4 + 1 + 4;
@@ -979,9 +988,11 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
       CK(cudaMemcpyAsync(dr, r + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
       CK(cudaMemcpyAsync(dtd, td0 + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
       CK(cudaMemcpyAsync(dd, done + t0, c, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaEventRecord(h->copy_done, h->stream));             // the caller's buffers are free again once the copies are done ...
       ingest_device(h, ds, da, dr, dsp, dd, dtd, c, slots);
+      if (t0 + c < n) CK(cudaStreamSynchronize(h->stream));   // the staging area is reused by the next chunk
     }
-    check_dev_errors(h);
+    if (n > 0) CK(cudaEventSynchronize(h->copy_done));         // ... the ingest kernels and the sum-tree refresh stay in flight
   });
 }
 
