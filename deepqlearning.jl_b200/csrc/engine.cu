@@ -533,6 +533,20 @@ void enqueue_step(E* e, bool sample) {
     head_loss_kernel<<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
     CK(cudaGetLastError());
   }
+  // update_priorities! (PER:76-80) needs nothing but the TD errors: on the third lane now, beside the whole reverse pass, instead of
+  // 13 us alone at the end of the step (one CTA, twenty dependent tree levels)
+  const bool early_tree = conc;
+  if (early_tree) {
+    order_after(e, e->stream3, e->stream);
+    cudaStream_t keep = e->ls; e->ls = e->stream3;
+    {
+      Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
+      tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream3>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
+                                                                                  1, e->st, 0, e->cfg.adam_beta1, e->cfg.adam_beta2, 0, nullptr);
+      CK(cudaGetLastError());
+    }
+    e->ls = keep;
+  }
   backward(e, conc);
   if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
@@ -549,7 +563,12 @@ void enqueue_step(E* e, bool sample) {
     order_after(e, e->stream, e->stream3);                  // the Dense bucket's update (and its max|g|) is complete
     enqueue_adam(e, 0, e->tower_off, e->stream);
   } else enqueue_adam(e, 0, e->nint, e->stream);
-  {
+  if (early_tree) {
+    if (!e->towers_updated) order_after(e, e->stream, e->stream3);
+    Scope sc(e, "end_of_step", 0, 12);                        // beta powers, sampler counter, (loss, grad_norm, flags) -> host words
+    tree_update_kernel<<<1, 32, 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, 0, 0, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
+    CK(cudaGetLastError());
+  } else {
     Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
     tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
                                                                                1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
