@@ -111,9 +111,13 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false> struct
   static constexpr int A_BYTES = ((A8 ? SA8::BYTES : SA::BYTES) + 1023) / 1024 * 1024;
   static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;            // A staging, B_hi(raw), B_lo
-  static constexpr int TAIL = 1024 + 256;                              // alignment slack + barriers / tmem address
+  static constexpr int TAIL = 1024 + 512;                              // alignment slack + barriers / tmem address
+#ifndef TC_MAX_STAGES
+#define TC_MAX_STAGES 12
+#endif
   static constexpr int FIT = (227 * 1024 - TAIL) / STAGE_BYTES;
-  static constexpr int STAGES = (FIT > 8 ? 8 : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
+  static constexpr int STAGES = (FIT > TC_MAX_STAGES ? TC_MAX_STAGES : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
+  static_assert(STAGES <= 16, "barrier arrays");
   static_assert(STAGES >= 6, "ring too shallow");
   static constexpr int NACC = R + 2;                                   // R interleaved main accumulators + one per correction product
   static constexpr int ACC_COLS = NBUF * NACC * BN;
@@ -305,12 +309,12 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_landed = sbase + STAGES * L::STAGE_BYTES;  // landed[8], full[8], empty[8], acc_full[2], acc_empty[2]: 8 bytes each
-  const uint32_t bar_full = bar_landed + 64;
-  const uint32_t bar_empty = bar_full + 64;
-  const uint32_t bar_accf = bar_empty + 64;
+  const uint32_t bar_landed = sbase + STAGES * L::STAGE_BYTES;  // landed[16], full[16], empty[16], acc_full[2], acc_empty[2]: 8 bytes each
+  const uint32_t bar_full = bar_landed + 128;
+  const uint32_t bar_empty = bar_full + 128;
+  const uint32_t bar_accf = bar_empty + 128;
   const uint32_t bar_acce = bar_accf + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 232);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * L::STAGE_BYTES + 424);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool a_lo = !opa.a_single;
