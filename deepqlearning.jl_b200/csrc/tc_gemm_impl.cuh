@@ -347,10 +347,27 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
     nk = max(min(ktiles, kt0 + per) - kt0, 0);
     return true;
   };
-  // light version for the roles that only need the k extent
+  // light version for the roles that only steer the pipeline (converters, MMA issue): extents (M, N, K) per operand set / parity
+  // class from a table computed once, no operand functor touched per tile
+  int* zdims = reinterpret_cast<int*>(smem + STAGES * L::STAGE_BYTES + 448);
+  {
+    const int nz_all = ntiles / (MT * NT * nsplit);
+    if (tid < nz_all && tid < 16) {
+      Op o = (Op::Z_IS_CLASS || tid == 0) ? opa : (tid == 1 ? opb : (tid == 2 ? opc : opd));
+      if (Op::Z_IS_CLASS) o.set_class(tid);
+      zdims[3 * tid] = o.M; zdims[3 * tid + 1] = o.N; zdims[3 * tid + 2] = o.K;
+    }
+  }
+  __syncthreads();
   auto decode_nk = [&](int t, int& nk) -> bool {
-    Op op; int m0, n0, zs, kt0;
-    return decode(t, op, m0, n0, zs, kt0, nk);
+    const int mt = t % MT, r = t / MT;
+    const int nt = r % NT, zs = r / NT;
+    const int zi = min(zs / nsplit, 15), split = zs - (zs / nsplit) * nsplit;
+    if (mt * BM >= zdims[3 * zi] || nt * BN >= zdims[3 * zi + 1]) return false;
+    const int ktiles = (zdims[3 * zi + 2] + BK - 1) / BK;
+    const int per = (ktiles + nsplit - 1) / nsplit;
+    nk = max(min(ktiles, split * per + per) - split * per, 0);
+    return true;
   };
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
@@ -622,8 +639,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
     int mtr = 0; (void)mtr;
     int buf = 0; uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      Op op; int m0, n0, zs, kt0, nk;
-      if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+      int nk;
+      if (!decode_nk(t, nk)) continue;
       mbar_wait(bar_acce + 8 * buf, aph ^ 1);                  // the epilogue has drained this accumulator set (first NBUF tiles: immediate)
       tc_fence_after();
       const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
