@@ -1,36 +1,31 @@
-// tc_gemm_impl.cuh - tcgen05 / TMEM contraction kernel for DQN_MATH_3XTF32.
+// tc_gemm_impl.cuh - tcgen05 / TMEM contraction kernel for DQN_MATH_3XTF32 (design and measurements: DESIGN.md section 2.1).
 //
-// Same operand functors as the fp32 path (igemm.cuh), different engine: a warp-specialised CTA computes one
-// 128 x BN output tile with the 5th-generation tensor cores.
+// Same operand functors as the fp32 path (igemm.cuh), different engine: one persistent, warp-specialised CTA of 1024 threads per SM
+// walks 128 x BN output tiles (tile = blockIdx.x, +gridDim.x, ...; nothing drains between tiles).
 //
-// 3xTF32: every fp32 operand value is used as two TF32-exact terms x = hi + lo (cvt.rna both, so the split is unbiased).
-// The split happens in SHARED memory: the producers cp.async the plain fp32 tensors (16-byte chunks; im2col rows, dgrad
-// parity classes and the [x 1] bias column are just different chunk addresses - op.ptrA / op.ptrB, nullptr = zero fill)
-// into the hi-plane slots of the UMMA canonical layout, then split their own chunks in place (hi back to the slot, lo to
-// the lo plane).  Global->shared traffic - the measured bottleneck of this kernel family on B200, ~3.6 TB/s chip-wide for
-// 16-byte cp.async - is therefore one pass over the fp32 data; an earlier version that kept hi/lo planes in HBM moved 2x.
+// 3xTF32: every fp32 operand value is used as two TF32 terms x = hi + lo, three products per 8-wide k step
+// (A_hi B_hi | A_lo B_hi | A_hi B_lo; the dropped A_lo B_lo term is O(2^-22)).  The tensor core reads the top 19 bits of a 32-bit
+// operand word, so the raw fp32 word already is hi = trunc_tf32(x); lo = x - hi is exact and gets half a TF32 ulp added to its bit
+// pattern so that the hardware's truncation of it becomes round-to-nearest.  A operand values that are raw bytes are exact: no A_lo.
 //
-//   one persistent CTA per SM (480 threads) walks output tiles blockIdx.x, +gridDim.x, ...; nothing drains between tiles:
-//   warps 0-7   producers: cp.async of 16-byte chunks into the ring (K-major operands in the no-swizzle layout of 8-row x 16-byte
-//               core matrices, MN-major operands in SWIZZLE_128B_BASE32B), DEPTH stages in flight behind the stage being split
-//   warps 8-11  epilogue: tcgen05.ld of one of the NBUF accumulator sets -> bias/activation or act' -> 16-byte stores, while the
-//               MMA warps already work on the next tile in the other set
-//   warps 12-14 one elected lane each issues tcgen05.mma.kind::tf32 for ONE of the three products per 8-wide k step
-//               (A_hi B_hi | A_lo B_hi | A_hi B_lo; the dropped A_lo B_lo term is O(2^-22)); the A_lo stream idles
-//               when A is single-plane (raw byte values are TF32-exact).
-//   accumulators  fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to
-//               1 ulp per MMA), so the correction products get their own accumulators and the main
-//               product is interleaved over R accumulators; the epilogue sums them with round-to-nearest.
+// Data path of one stage (BK = 32):
+//   loaders     cp.async 16-byte chunks of the plain fp32 (or byte) tensors - im2col rows, dgrad parity classes and the [x 1] bias
+//               column are just different chunk addresses (op.ptrA / op.ptrB, nullptr = zero fill) - into ring slot g % STAGES:
+//               A into a padded row-major staging tile, B into the UMMA layout (K-major: no-swizzle 8-row x 16-byte core matrices,
+//               MN-major: SWIZZLE_128B_BASE32B) whose raw plane is the hi plane; completion arrives on landed[slot]
+//   converters  A: staging tile -> registers (one row, 16 k values per thread) -> tcgen05.st into the TMEM ring (hi and lo columns);
+//               B: lo of the raw plane -> B lo plane; fence.proxy.async; arrive on full[slot]
+//   MMA issue   three warps, one per product: tcgen05.mma.kind::tf32 with A from TMEM and B from a shared-memory descriptor, then
+//               tcgen05.commit -> empty[slot] (frees the ring slot and, four stages later, the TMEM A slot)
+//   epilogue    tcgen05.ld of the accumulator set -> round-to-nearest sum -> bias/activation or act' -> 16-byte stores
+// Accumulators: fp32 in TMEM.  The tensor core adds into its accumulator with truncation (one-sided, up to 1 ulp per MMA), so the
+// correction products get their own accumulators and the main product is interleaved over R accumulators.
+// Build knobs kept for experiments (all off): TC_TRACE (stage timestamps of CTA 0, printed by tests/csrc/tc_selftest.cu),
+// TC_EXP_NOLOAD / NOFIN / NOMMA / NOEPI (ablations: timing only, results are garbage), TC_CP_CG, TC_WAIT_IMPL, TC_MAX_STAGES.
 #pragma once
 #include <cstdlib>
-#ifndef TC_PRODUCER_CPASYNC
-#define TC_PRODUCER_CPASYNC 1      // 1: cp.async producers (faster in the full step on B200), 0: ld.global.nc -> st.shared
-#endif
 #ifndef TC_CP_CG
 #define TC_CP_CA 1
-#endif
-#ifndef TC_HI_TRUNC
-#define TC_HI_TRUNC 1
 #endif
 
 namespace tc {
