@@ -234,13 +234,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
-__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// SWIZZLE_128B_BASE32B: word j of 16-byte chunk g is stored at word j ^ (g & 3)
-__device__ __forceinline__ float4 permute_chunk(float4 v, int c) {
-  if (c & 1) { float t = v.x; v.x = v.y; v.y = t; t = v.z; v.z = v.w; v.w = t; }
-  if (c & 2) { float t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
-  return v;
-}
 // lo term of x = trunc_tf32(x) + lo.  The subtraction is exact; adding half a TF32 ulp to the bit pattern makes the tensor core's own
 // truncation of the operand a round-to-nearest (ties away) - the low 13 bits need no masking, the hardware ignores them.
 __device__ __forceinline__ float lo_of_trunc(float x) {
@@ -255,11 +248,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
-// instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
 #ifdef TC_CP_CA
@@ -274,9 +262,6 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 #else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
-}
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrive when this thread's prior cp.async have landed
-  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), major bits 15/16 (1 = MN-major), N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool b_mn) {
