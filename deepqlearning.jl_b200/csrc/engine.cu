@@ -139,7 +139,7 @@ struct dqn_engine {
   float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
-  int tc_split = 0;
+  int tc_split = 0; int tc_tail = 0;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
   int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction

@@ -719,10 +719,12 @@ igemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_st
 
 // out[i] = sum_s ws[(z*nsplit + s)][i], s ascending (deterministic), for the split-K weight gradients
 template <class Op>
-__global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __restrict__ ws, long long ws_stride) {
+__global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __restrict__ ws, long long ws_stride, int m_off = 0, int rows = -1) {
   const int zi = blockIdx.y;
   Op op = zi == 0 ? opa : opb;
-  const long long total = (long long)op.M * op.N;
+  if (Op::Z_IS_CLASS) op.set_class(0);                    // only single-class dgrads are ever split
+  // rows [m_off, m_off + rows) of the output (the tail tiles of a launch, see tc_gemm_impl.cuh); default: all of it
+  const long long total = (long long)(rows < 0 ? op.M : rows) * op.N;
   if (op.can_store4()) {                     // N % 4 == 0: four columns per thread, vector epilogue (also writes the split planes)
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
       float4 s = make4(0, 0, 0, 0);
@@ -738,14 +740,14 @@ __global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __
         const float4 p = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i));
         s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
       }
-      op.store4((int)(i / op.N), (int)(i % op.N), s);
+      op.store4(m_off + (int)(i / op.N), (int)(i % op.N), s);
     }
     return;
   }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < nsplit; ++k) s += ws[((long long)(zi * nsplit + k)) * ws_stride + i];
-    op.store((int)(i / op.N), (int)(i % op.N), s);
+    op.store(m_off + (int)(i / op.N), (int)(i % op.N), s);
   }
 }
 #endif  // __CUDACC__

@@ -41,7 +41,7 @@ static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long
   Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
   const int MT = (o0.M + 127) / 128, NT = (o0.N + BN - 1) / BN, ntiles = MT * NT * nz * nsplit;
   const int grid = ntiles < g_nsm ? ntiles : g_nsm;
-  tc::tc_gemm_kernel<BN, R, NBUF, false, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles);
+  tc::tc_gemm_kernel<BN, R, NBUF, false, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles, 0, 0);
 }
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {

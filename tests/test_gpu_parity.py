@@ -348,13 +348,14 @@ def test_env_switches_keep_parity(lib):
             "e.replay_fill_synthetic(512, 7); l,g=e.train_step(); print('RES', repr(float(l)), repr(float(g)), repr(float(np.abs(e.grads()).sum())))")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for tag, env in (("default", {}), ("merge", {"DQN_MERGE_FWD": "1"}), ("one_lane", {"DQN_STREAMS": "0"}), ("tiled_heads", {"DQN_FUSE_HEADS": "0"}), ("no_a8", {"DQN_NO_A8": "1"})):
+    for tag, env in (("default", {}), ("merge", {"DQN_MERGE_FWD": "1"}), ("one_lane", {"DQN_STREAMS": "0"}), ("tiled_heads", {"DQN_FUSE_HEADS": "0"}), ("no_a8", {"DQN_NO_A8": "1"}),
+                     ("tail_split", {"DQN_TC_TAIL": "1"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, **env})
         line = [x for x in r.stdout.splitlines() if x.startswith("RES")]
         assert line, (tag, r.stdout[-500:], r.stderr[-1500:])
         outs[tag] = [float(x) for x in line[0].split()[1:]]
     ref = outs["default"]
     assert outs["one_lane"] == ref and outs["no_a8"] == ref, outs          # same kernels, same order of operations: bit-identical
-    for tag in ("merge", "tiled_heads"):                                    # different summation order in a few contractions
+    for tag in ("merge", "tiled_heads", "tail_split"):                      # different summation order in a few contractions
         for a, b in zip(outs[tag], ref):
             assert abs(a - b) <= 2e-5 * abs(b), (tag, outs)
