@@ -91,6 +91,7 @@ SIGNATURES = {
     "dqn_get_q": (C.c_int, [_H, C.c_int, _f32p]),
     "dqn_get_targets": (C.c_int, [_H, _f32p, _i32p]),
     "dqn_get_grads": (C.c_int, [_H, _f32p, C.c_int64]),
+    "dqn_get_activation": (C.c_int, [_H, C.c_int, C.c_int, _f32p, C.c_int64]),
     "dqn_timer_start": (C.c_int, [_H]),
     "dqn_timer_stop": (C.c_int, [_H, _f32p]),
     "dqn_launches_per_step": (C.c_int, [_H]),

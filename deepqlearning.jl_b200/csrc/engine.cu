@@ -1191,6 +1191,29 @@ int dqn_get_grads(dqn_engine_t* h, float* flat, int64_t n) {
   return guard(h, [&] { if (n != h->nflux) fail(DQN_ERR_INVALID, "expected %lld", h->nflux); gather_params(h, h->grad, flat); });
 }
 
+// Output of one layer of the online network on the s rows of the last step (rows 0..B-1), in the reference's memory image:
+// conv stage -> (B, C, OH, OW) row-major == Flux (OW, OH, C, B); tower stage -> (B, N).  Parity tests take the ReLU masks from here.
+int dqn_get_activation(dqn_engine_t* h, int stage, int tower, float* out, int64_t n) {
+  return guard(h, [&] {
+    const int nc = (int)h->convs.size();
+    if (stage < 0 || stage >= nc + h->depth || tower < 0 || tower >= h->ntow || !out) fail(DQN_ERR_INVALID, "stage/tower");
+    if (stage < nc) {
+      const ConvGeom& g = h->convs[stage].g;
+      const long long per = (long long)g.OH * g.OW * g.Cout;
+      if (n != h->B * per) fail(DQN_ERR_INVALID, "expected %lld floats", h->B * per);
+      ensure_stage(h, n * 4);
+      const long long total = n;
+      relayout_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 8LL * h->nsm), 256, 0, h->stream>>>((const uint8_t*)h->on.conv_out[stage], h->stage, h->B, g.Cout, g.OH * g.OW, 0, 0, 0);
+      CK(cudaGetLastError());
+      d2h(h, out, (const float*)h->stage, n);
+    } else {
+      const Mat& w = h->tow[tower][stage - nc];
+      if (n != (long long)h->B * w.N) fail(DQN_ERR_INVALID, "expected %lld floats", (long long)h->B * w.N);
+      d2h(h, out, (const float*)h->on.tow_out[tower][stage - nc], n);
+    }
+  });
+}
+
 int dqn_timer_start(dqn_engine_t* h) { return guard(h, [&] { CK(cudaEventRecord(h->t0, h->stream)); }); }
 int dqn_timer_stop(dqn_engine_t* h, float* ms) {
   return guard(h, [&] { CK(cudaEventRecord(h->t1, h->stream)); CK(cudaEventSynchronize(h->t1)); CK(cudaEventElapsedTime(ms, h->t0, h->t1)); });

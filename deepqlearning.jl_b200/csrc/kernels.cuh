@@ -66,10 +66,37 @@ __device__ __forceinline__ int tree_descend(const float* __restrict__ tree, cons
   return node - P;
 }
 
+// Mass of `node` once the leaves held by earlier slots are taken out: fl(tree[node] - sum of the held priorities below it), the
+// held leaves added in slot order (fixed order: bit-exact against oracle/sumtree.py::descend_excl).  shift = levels below `node`.
+__device__ __forceinline__ float tree_mass_excl(const float* __restrict__ tree, int P, int node, int shift, const int* held, int B) {
+  float ex = 0.f;
+  for (int i = 0; i < B; ++i) { const int l = held[i]; if (l >= 0 && ((P + l) >> shift) == node) ex = __fadd_rn(ex, tree[P + l]); }
+  const float m = __fsub_rn(tree[node], ex);
+  return m > 0.f ? m : 0.f;
+}
+// Descent over the tree minus the held leaves: one exact draw of successive sampling without replacement.
+__device__ int tree_descend_excl(const float* __restrict__ tree, int P, float u, const int* held, int B) {
+  int depth = 0; while ((1 << depth) < P) ++depth;
+  float v = __fmul_rn(u, tree_mass_excl(tree, P, 1, depth, held, B));
+  int node = 1;
+  for (int shift = depth - 1; shift >= 0; --shift) {
+    const float l = tree_mass_excl(tree, P, 2 * node, shift, held, B), r = tree_mass_excl(tree, P, 2 * node + 1, shift, held, B);
+    const bool left = (v < l) || (r == 0.f);
+    if (!left) v = __fsub_rn(v, l);
+    node = 2 * node + (left ? 0 : 1);
+  }
+  return node - P;
+}
+
 // B draws without replacement (StatsBase.sample(...; replace=false), PER:85): slot j redraws while a slot
 // i < j holds the same leaf; one check per round over a shared hash table.  One CTA, B <= 1024 threads.
+// Rejection is exactly successive sampling without replacement, but it only terminates quickly while the held leaves carry a small
+// share of the priority mass.  The reference's sampler always succeeds once curr_size >= batch_size, so slots that are still rejected
+// after SAMPLE_MAX_ROUNDS redraws (curr_size barely above B, or a few leaves holding nearly all the mass) are resolved exactly: in slot
+// order, each by a descent over the tree with the held leaves' mass taken out (attempt numbers 0x80000000 + t name those uniforms).
 // The same CTA then gathers the per-sample metadata and importance weights (get_batch, PER:94-102).
 constexpr int SAMPLE_MAX_ROUNDS = 64;
+constexpr int SAMPLE_EXACT_TRIES = 4096;
 __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint64_t seed, DevState* st,
                               int use_call, uint64_t call_in, long long* __restrict__ idx_out,
                               const int* __restrict__ act, const float* __restrict__ rew, const uint8_t* __restrict__ done, float beta,
@@ -86,8 +113,7 @@ __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint
   const uint64_t call = use_call ? call_in : st->sample_call;
   uint32_t attempt = 0;
   int leaf = (j < B) ? tree_descend(tree, top, P, philox_uniform(seed, call, j, 0)) : -1;
-  int round = 0;
-  for (; round < SAMPLE_MAX_ROUNDS; ++round) {
+  for (int round = 0; ; ++round) {
     for (int t = threadIdx.x; t < HT; t += blockDim.x) { keys[t] = -1; owner[t] = 0x7fffffff; }
     __syncthreads();
     int slot = -1;
@@ -104,7 +130,33 @@ __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint
     const int rej = (j < B) && (owner[slot] < j);
     const int any = __syncthreads_or(rej);
     if (!any) break;
-    if (rej) { ++attempt; leaf = tree_descend(tree, top, P, philox_uniform(seed, call, j, attempt)); }
+    if (round < SAMPLE_MAX_ROUNDS) {
+      if (rej) { ++attempt; leaf = tree_descend(tree, top, P, philox_uniform(seed, call, j, attempt)); }
+      continue;
+    }
+    // exact resolution of the slots that are still rejected (see above); `owner` is reused as the list of held leaves
+    int* held = owner;
+    __syncthreads();
+    if (j < B) held[j] = rej ? -1 : leaf;
+    __syncthreads();
+    if (j == 0) {
+      for (int s = 0; s < B; ++s) {
+        if (held[s] >= 0) continue;
+        int pick = -1;
+        for (int t = 0; t < SAMPLE_EXACT_TRIES; ++t) {
+          pick = tree_descend_excl(tree, P, philox_uniform(seed, call, (uint32_t)s, 0x80000000u + (uint32_t)t), held, B);
+          bool dup = false;                       // rounding residue can leave a held leaf reachable: draw again
+          for (int i = 0; i < B; ++i) dup = dup || (held[i] == pick);
+          if (!dup) break;
+          pick = -1;
+        }
+        if (pick < 0) { atomicOr(&st->error, 1); pick = 0; }
+        held[s] = pick;
+      }
+    }
+    __syncthreads();
+    if (j < B) leaf = held[j];
+    break;
   }
   if (j < B) {
     idx_out[j] = leaf;
@@ -114,7 +166,6 @@ __global__ void sample_kernel(const float* __restrict__ tree, int P, int B, uint
       w_b[j] = pow_f32(__fmul_rn((float)st->curr_size, p), -beta);
     }
   }
-  if (j == 0 && round >= SAMPLE_MAX_ROUNDS) atomicOr(&st->error, 1);
 }
 
 // Per-sample metadata gather + importance weights (get_batch, PER:91-102):
@@ -232,6 +283,15 @@ __global__ void ingest_kernel(const uint8_t* __restrict__ s_in, const uint8_t* _
   const long long t = t0 + blockIdx.y;      // transition
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) st->curr_size = new_size;
   const long long slot = (cursor + t) % cap;
+  // the reference's asserts (PER:66 td_err + eps > 0; a valid action index): an offending transition raises the sticky flag and is
+  // NOT stored - its ring slot keeps its previous contents and priority (the host path rejects the whole batch before any copy)
+  const int a_t = a_in[t];
+  const float base_t = __fadd_rn(td0[t], eps);
+  const bool bad_a = a_t < 1 || a_t > n_actions, bad_p = !(base_t > 0.f);
+  if (bad_a || bad_p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&st->error, (bad_a ? 8 : 0) | (bad_p ? 4 : 0)); slot_idx[t] = slot; }
+    return;
+  }
   const long long elems = (long long)C * HW;
   const uint8_t* si = s_in + t * elems * elem_bytes;
   const uint8_t* pi = sp_in + t * elems * elem_bytes;
@@ -244,12 +304,8 @@ __global__ void ingest_kernel(const uint8_t* __restrict__ s_in, const uint8_t* _
     else { ((float*)so)[e] = ((const float*)si)[src]; ((float*)po)[e] = ((const float*)pi)[src]; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int a = a_in[t];
-    if (a < 1 || a > n_actions) atomicOr(&st->error, 8);
-    act[slot] = a; rew[slot] = r_in[t]; done[slot] = d_in[t] ? 1 : 0;
-    const float base = __fadd_rn(td0[t], eps);
-    if (!(base > 0.f)) atomicOr(&st->error, 4);
-    tree[P + slot] = pow_f32(base, alpha);
+    act[slot] = a_t; rew[slot] = r_in[t]; done[slot] = d_in[t] ? 1 : 0;
+    tree[P + slot] = pow_f32(base_t, alpha);
     slot_idx[t] = slot;
   }
 }
@@ -360,7 +416,8 @@ __global__ void head_loss_kernel(HeadArgs h) {
     // s online
     dueling_q(h.V_on, h.A_on, i, nA, h.dueling, q);
     for (int k = 0; k < nA; ++k) h.q_s[(long long)i * nA + k] = q[k];
-    const int a = h.a_b[i] - 1;
+    int a = h.a_b[i] - 1;
+    if (a < 0 || a >= nA) { atomicOr(&h.st->error, 8); a = min(max(a, 0), nA - 1); }   // never index q[] out of range
     const float td = __fsub_rn(q[a], y);
     const float w = h.w_b[i];
     const float x = __fmul_rn(w, td);

@@ -697,10 +697,13 @@ namespace {
 template <int BN, int R, int NBUF, bool A8, class Op>
 void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long ws_stride, int MT, int NT, int ntiles, int tail_t0, int tail_s) {
   using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, A8>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in above 48 KB of dynamic shared memory is a per-device function attribute: one flag per device ordinal, not per process
+  // (a second engine on another GPU of the same process - dqn_group_create - needs its own opt-in)
+  static unsigned long long attr_set[4] = {0, 0, 0, 0};
+  const int dev = e->cfg.device & 255;
+  if (!((attr_set[dev >> 6] >> (dev & 63)) & 1ull)) {
     CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, A8, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
-    attr_set = true;
+    attr_set[dev >> 6] |= 1ull << (dev & 63);
   }
   const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
   tc::tc_gemm_kernel<BN, R, NBUF, A8, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],

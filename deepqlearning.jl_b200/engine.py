@@ -230,6 +230,12 @@ class Engine:
         self._ck(lib.dqn_get_grads(self.h, ptr(out, C.c_float), out.size))
         return out
 
+    def activation(self, stage, tower, shape):
+        """online-network output of layer `stage` (convs first, then the tower's Dense layers) on the s rows of the last step"""
+        out = np.empty((self.B,) + tuple(shape), np.float32)
+        self._ck(lib.dqn_get_activation(self.h, int(stage), int(tower), ptr(out, C.c_float), out.size))
+        return out
+
     # ---- measurement -------------------------------------------------------------------------------
     def timer_start(self):
         self._ck(lib.dqn_timer_start(self.h))

@@ -52,7 +52,9 @@ class PrioritizedReplayBuffer:
         self.engine.update_priorities(indices, td_errors)
 
     def sample_indices(self, call=None):
-        call = self._sample_calls if call is None else call
+        if call is None:                      # the reference's sample(r) advances the buffer's RNG on every call (PER:82-87)
+            call = self._sample_calls
+            self._sample_calls += 1
         return self.engine.sample_indices(call)
 
     def sample(self):

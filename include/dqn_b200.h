@@ -145,6 +145,10 @@ int dqn_get_is_weights(dqn_engine_t* h, float* w_out);           /* importance_w
 int dqn_get_q(dqn_engine_t* h, int which_q, float* q_out);       /* (B, n_actions) */
 int dqn_get_targets(dqn_engine_t* h, float* y_out, int32_t* best_a_out);   /* q_targets SOLVER:217, best_a 1-based SOLVER:212 */
 int dqn_get_grads(dqn_engine_t* h, float* flat, int64_t n);      /* gs in Flux.params order/layout */
+/* output of layer `stage` (conv layers first, then the Dense layers of tower `tower`: 0 = val or the only tower, 1 = adv) of the
+ * online network on the s rows of the last step, in the reference's memory image ((B,C,OH,OW) row-major / (B,N)); the parity
+ * tests read the ReLU masks of the engine's own forward pass from here (Zygote's relu pullback, SOLVER:219-225) */
+int dqn_get_activation(dqn_engine_t* h, int stage, int tower, float* out, int64_t n);
 
 /* ---- measurement ---------------------------------------------------------------------------------- */
 int dqn_timer_start(dqn_engine_t* h);                            /* CUDA event on the engine's stream */

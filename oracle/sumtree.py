@@ -20,6 +20,7 @@ import numpy as np
 from .philox import sample_uniforms
 
 MAX_ROUNDS = 64
+EXACT_TRIES = 4096
 
 
 def next_pow2(n):
@@ -75,21 +76,67 @@ class SumTree:
             node = np.where(go_left, 2 * node, 2 * node + 1)
         return node - self.P
 
+    def _rejected(self, picks):
+        rejected = np.zeros(len(picks), dtype=bool)
+        seen = {}
+        for j in range(len(picks)):
+            if picks[j] in seen:
+                rejected[j] = True
+            else:
+                seen[picks[j]] = j
+        return rejected
+
+    def _mass_excl(self, node, shift, held):
+        """fl(tree[node] - sum of the held priorities below node), held leaves added in slot order (float32)."""
+        ex = np.float32(0)
+        for l in held:
+            if l >= 0 and ((self.P + l) >> shift) == node:
+                ex = np.float32(ex + self.tree[self.P + l])
+        m = np.float32(self.tree[node] - ex)
+        return m if m > 0 else np.float32(0)
+
+    def descend_excl(self, u, held):
+        """One exact draw of successive sampling without replacement: descent over the tree minus the held leaves."""
+        depth = self.P.bit_length() - 1
+        v = np.float32(np.float32(u) * self._mass_excl(1, depth, held))
+        node = 1
+        for shift in range(depth - 1, -1, -1):
+            l = self._mass_excl(2 * node, shift, held)
+            r = self._mass_excl(2 * node + 1, shift, held)
+            left = (v < l) or (r == 0)
+            if not left:
+                v = np.float32(v - l)
+            node = 2 * node + (0 if left else 1)
+        return node - self.P
+
     def sample(self, B, seed, step):
-        """Return (leaf indices int64[B], attempts uint32[B]) for sampling call number `step`."""
+        """Return (leaf indices int64[B], attempts uint32[B]) for sampling call number `step`.
+        MAX_ROUNDS rounds of reject-and-redraw; slots still rejected after that are resolved exactly, in slot order, by a descent that
+        leaves out the held leaves (uniforms named by attempt 0x80000000 + t) - the reference's sampler always succeeds once
+        curr_size >= batch_size (StatsBase.sample(...; replace=false), src/prioritized_experience_replay.jl:83-85)."""
         slots = np.arange(B, dtype=np.uint32)
         attempts = np.zeros(B, dtype=np.uint32)
         picks = self.descend(sample_uniforms(seed, step, slots, attempts))
         for _ in range(MAX_ROUNDS):
-            rejected = np.zeros(B, dtype=bool)
-            seen = {}
-            for j in range(B):
-                if picks[j] in seen:
-                    rejected[j] = True
-                else:
-                    seen[picks[j]] = j
+            rejected = self._rejected(picks)
             if not rejected.any():
                 return picks, attempts
             attempts[rejected] += 1
             picks[rejected] = self.descend(sample_uniforms(seed, step, slots[rejected], attempts[rejected]))
-        raise RuntimeError("sum-tree sampling did not converge to distinct indices")
+        rejected = self._rejected(picks)
+        if not rejected.any():
+            return picks, attempts
+        held = [(-1 if rejected[j] else int(picks[j])) for j in range(B)]
+        for s in range(B):
+            if held[s] >= 0:
+                continue
+            for t in range(EXACT_TRIES):
+                att = np.uint32(0x80000000 + t)
+                pick = int(self.descend_excl(sample_uniforms(seed, step, np.array([s], np.uint32), np.array([att], np.uint32))[0], held))
+                if pick not in held:
+                    break
+            else:
+                raise RuntimeError("sum-tree sampling did not reach distinct indices")
+            held[s] = pick
+            attempts[s] = att
+        return np.asarray(held, np.int64), attempts

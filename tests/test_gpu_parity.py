@@ -3,13 +3,13 @@
 Tolerances (stated once, used everywhere):
   * sampled leaf indices, ring contents, actions, best_a, sum-tree nodes: BIT-EXACT
   * Q-values, TD errors, targets, IS weights, loss: normwise relative error <= 1e-5  (north_star)
-  * gradients, per parameter array, max-norm and L2: <= 5e-5 relative on smooth (tanh / identity) networks, <= 5e-3 on ReLU
-    networks.  The typical distance is ~1e-6 on both (scripts/tc_report.py prints it next to the oracle's own distance to
-    fp64).  The loose bound on ReLU networks is not kernel error: a ReLU unit whose pre-activation lies within rounding
-    distance of zero flips its sub-gradient between ANY two fp32 evaluations (a different summation order is enough - Flux
-    against itself under another BLAS threading would do it).  scripts/relu_flip_study.py shows it on the CPU alone: the
-    fp32 oracle against the fp64 oracle, config 3, 1 batch in 8 has 1e-3 relative error in the conv1/conv2 gradients while
-    all other arrays agree to 3e-7.  The tanh networks (mlp_tanh, conv_tanh) run the same kernels without that discontinuity
+  * gradients, per parameter array, max-norm and L2: <= 5e-5 relative on EVERY network, ReLU networks included.  A ReLU unit
+    whose pre-activation lies within rounding distance of zero flips its sub-gradient between ANY two fp32 evaluations (a
+    different summation order is enough - Flux against itself under another BLAS threading would do it;
+    scripts/relu_flip_study.py shows it on the CPU alone), so the oracle's reverse pass takes the ReLU masks from the engine's
+    own forward activations (dqn_get_activation -> mask_override, oracle/nets.py) and everything else is held to 5e-5: a 1e-3
+    error in any weight- or input-gradient kernel fails the test.  The forward values themselves are compared without any
+    such help (Q within 1e-5, normwise: max|dQ| / max|Q|)
   * Adam: given the engine's own gradients, the updated parameters match the oracle's Flux-Adam to 1 ulp
 """
 import glob
@@ -125,9 +125,37 @@ def test_get_batch_matches_reference_get_batch(lib, name):
     eng.close()
 
 
+def set_relu_masks(spec, net, eng):
+    """mask_override on every ReLU layer of the oracle network <- (engine activation > 0) on the s rows of the step just run"""
+    shape = tuple(spec["obs"])
+    convs = [l for l in spec["layers"] if l[0] == "conv"]
+    nc = len(convs)
+    dueling = isinstance(net, O.DuelingNetwork)
+    all_layers = (net.base.layers if dueling else net.layers)
+    stage = 0
+    for l in all_layers:
+        if isinstance(l, O.Conv):
+            c, h, w = shape
+            shape = (l.cout,) + l.out_hw(h, w)
+            if l.act == O.ACT_RELU:
+                l.mask_override = eng.activation(stage, 0, shape) > 0
+            stage += 1
+    towers = [net.val.layers, net.adv.layers] if dueling else [[l for l in net.layers if isinstance(l, O.Dense)]]
+    for t, layers in enumerate(towers):
+        for li, l in enumerate(layers):
+            if l.act == O.ACT_RELU:
+                l.mask_override = eng.activation(nc + li, t, (l.nout,)) > 0
+
+
+def clear_relu_masks(net):
+    layers = (net.base.layers + net.val.layers + net.adv.layers) if isinstance(net, O.DuelingNetwork) else net.layers
+    for l in layers:
+        if hasattr(l, "mask_override"):
+            del l.mask_override
+
+
 def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, qtol=QTOL, gtol=GTOL):
-    relu_net = any(l[0] in ("dense", "conv") and l[-1] == 1 for l in spec["layers"])
-    gmax_tol = 5e-3 if relu_net else gtol
+    gmax_tol = gtol
     B = spec["B"]
     theta_before = eng.get_params(0)
     m0, v0, bp0 = eng.get_adam_state()
@@ -137,8 +165,10 @@ def check_step(spec, net, tgt, buf, eng, opt, call, double_q, per, gamma=0.99, q
     idx = eng.last_indices()
     assert np.array_equal(idx, want_idx)
     sb, ab, rb, spb, db, _, w = buf.get_batch(idx, total="tree", dequant=util.dequant)
+    set_relu_masks(spec, net, eng)                                           # reverse pass through the engine's own ReLU masks
     out = O.forward_backward(net, tgt, sb, ab - 1, rb, spb, db, w, gamma, double_q, np.float32)
     out64 = O.forward_backward(net, tgt, sb, ab - 1, rb, spb, db, w, gamma, double_q, np.float64)
+    clear_relu_masks(net)
     assert util.relerr(eng.is_weights(), w) < 1e-6
     q, qo, qt = eng.q(0), eng.q(1), eng.q(2)
     scale = max(np.abs(out["q"]).max(), np.abs(out["q_target_sp"]).max())
@@ -359,3 +389,106 @@ def test_env_switches_keep_parity(lib):
     for tag in ("merge", "tiled_heads", "tail_split"):                      # different summation order in a few contractions
         for a, b in zip(outs[tag], ref):
             assert abs(a - b) <= 2e-5 * abs(b), (tag, outs)
+
+
+def test_sampling_curr_size_equals_batch_size_is_a_permutation(lib):
+    # curr_size == batch_size: the reference's sample(...; replace=false) returns every index (PER:83-85); rejection alone does not
+    # terminate here - the exact exclusion descent finishes the batch, bit-identical to the oracle's restatement of it
+    spec, net, tgt, buf, eng = setup_pair(lib, "c1_gridworld", n_fill=32)
+    used_exact = 0
+    for call in range(12):
+        got = eng.sample_indices(call)
+        want, att = buf.tree.sample(32, SEED, call)
+        assert np.array_equal(got, want), f"call {call}"
+        assert sorted(got.tolist()) == list(range(32))
+        used_exact += int((att >= 0x80000000).any())
+    assert used_exact > 0
+    loss, gn = eng.train_step()                                              # and the step runs on such a batch
+    assert np.isfinite(loss) and sorted(eng.last_indices().tolist()) == list(range(32))
+    eng.close()
+
+
+def test_sampler_distribution_matches_successive_sampling(lib):
+    """Inclusion frequencies of the device sampler over 30 000 sampling calls against the exact inclusion probabilities of successive
+    sampling without replacement (what StatsBase's A-ExpJ realises, PER:85; tests/test_oracle_cpu.py checks the A-ExpJ restatement
+    against the same enumeration)."""
+    import itertools
+    n, B = 10, 4
+    spec = dict(util.SPECS["c1_gridworld"]); spec["B"] = B; spec["N"] = n
+    eng = make_engine(lib, spec, B=B, N=n)
+    s, a, r, sp, done = util.random_transitions(spec, n, seed=3)
+    eng.replay_add(s, a, r, sp, done, np.abs(r))
+    p = eng.get_priorities().astype(np.float64)
+    incl = np.zeros(n)
+    for seq in itertools.permutations(range(n), B):
+        rem, pr = p.sum(), 1.0
+        for i in seq:
+            pr *= p[i] / rem
+            rem -= p[i]
+        incl[list(seq)] += pr
+    calls = 30000
+    cnt = np.zeros(n)
+    for call in range(calls):
+        cnt[eng.sample_indices(call)] += 1
+    f = cnt / calls
+    sigma = np.sqrt(incl * (1 - incl) / calls)
+    assert np.all(np.abs(f - incl) <= 4.5 * sigma + 1e-4), (f, incl)
+    eng.close()
+
+
+def test_replay_add_device_matches_host_add(lib):
+    """dqn_replay_add_device (transitions already in HBM, the vectorised-env ingest path) fills the ring exactly like dqn_replay_add,
+    and an offending transition (bad action / td0 + eps <= 0) is reported and not stored."""
+    import ctypes as C
+    import torch
+    spec = util.SPECS["conv_small"]
+    e_host = make_engine(lib, spec)
+    e_dev = make_engine(lib, spec)
+    n = spec["N"] + 11
+    s, a, r, sp, done = util.random_transitions(spec, n, seed=41)
+    td0 = np.abs(r)
+    e_host.replay_add(s, a, r, sp, done, td0)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    for lo, hi in ((0, 100), (100, n)):
+        ts, ta, tr, tsp, td, ttd = dev(s[lo:hi]), dev(a[lo:hi]), dev(r[lo:hi]), dev(sp[lo:hi]), dev(done[lo:hi]), dev(td0[lo:hi])
+        torch.cuda.synchronize()
+        rc = lib._capi.lib.dqn_replay_add_device(e_dev.h, C.c_void_p(ts.data_ptr()), C.c_void_p(ta.data_ptr()), C.c_void_p(tr.data_ptr()),
+                                                 C.c_void_p(tsp.data_ptr()), C.c_void_p(td.data_ptr()), C.c_void_p(ttd.data_ptr()), hi - lo)
+        assert rc == 0, lib._capi.lib.dqn_last_error(e_dev.h)
+    assert e_dev.replay_size() == e_host.replay_size()
+    assert np.array_equal(e_dev.get_tree(), e_host.get_tree())
+    idx = np.arange(0, spec["N"], 7)
+    for x, y in zip(e_dev.replay_read(idx), e_host.replay_read(idx)):
+        assert np.array_equal(x, y)
+    assert np.array_equal(e_dev.sample_indices(3), e_host.sample_indices(3))
+    # an invalid transition: flagged, skipped, everything else untouched
+    before = e_dev.get_tree().copy()
+    bad_a = dev(np.array([1, 99], np.int32)); ok_td = dev(np.array([0.5, 0.5], np.float32))
+    ts, tr, tsp, td = dev(s[:2]), dev(r[:2]), dev(sp[:2]), dev(done[:2])
+    torch.cuda.synchronize()
+    rc = lib._capi.lib.dqn_replay_add_device(e_dev.h, C.c_void_p(ts.data_ptr()), C.c_void_p(bad_a.data_ptr()), C.c_void_p(tr.data_ptr()),
+                                             C.c_void_p(tsp.data_ptr()), C.c_void_p(td.data_ptr()), C.c_void_p(ok_td.data_ptr()), 2)
+    assert rc == lib._capi.DQN_ERR_INVALID
+    after = e_dev.get_tree()
+    P = after.size // 2
+    cur = e_host.replay_size()[1]
+    changed = np.nonzero(after[P:] != before[P:])[0]
+    assert changed.tolist() in ([cur], [])                                   # only the valid transition's leaf (if its priority differs)
+    loss, gn = e_dev.train_step()                                            # the sticky flag was consumed by the failed call
+    assert np.isfinite(loss)
+    e_host.close(); e_dev.close()
+
+
+def test_data_parallel_two_gpus(n_gpus):
+    """world = 2 under torchrun: the all-reduced gradient equals the oracle's gradient of the combined batch, parameters stay
+    identical across ranks (scripts/mgpu_check.py; its output is kept under gpurun_out/ for profiles/)."""
+    if n_gpus < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "scripts", "mgpu_check.py")], capture_output=True, text=True, timeout=900, cwd=root)
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "mgpu_check.log"), "w") as f:
+        f.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
+    assert r.returncode == 0 and r.stdout.count("MGPU OK") == 2, r.stdout[-3000:] + r.stderr[-2000:]
