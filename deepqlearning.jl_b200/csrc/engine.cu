@@ -139,7 +139,7 @@ struct dqn_engine {
   float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
-  int tc_split = 0; int tc_tail = 0;
+  int tc_split = 0; int tc_tail = 0; int tc_tma = 1;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
   int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction
@@ -333,6 +333,10 @@ void backward(E* e, bool conc) {
         op.Ds = e->tow_delta[t][l]; op.ones = e->ones; op.a_single = 0; op.out_scale = 0.f;
       }
     }
+    // TMA feed: the ones row of [x 1] is not a box of the activation matrix - the bias gradient (column sums of delta) goes to colsum_kernel
+    bool split_bias = e->arena && e->tc_tma && e->cfg.math_mode == DQN_MATH_3XTF32 && B >= 32;
+    for (int t = 0; t < e->ntow; ++t) { const Mat& w = e->tow[t][l]; split_bias = split_bias && wg[t].Xs && (w.K % 4 == 0) && w.K >= 64 && (w.N % 32 == 0) && w.N <= 1024; }
+    if (split_bias) for (int t = 0; t < e->ntow; ++t) { wg[t].no_bias = 1; wg[t].M = e->tow[t][l].K; }
     if (e->ntow == 1) wg[1] = wg[0];
     snprintf(nm, sizeof nm, "dense%d_wgrad", l + 1);
     double fl = 0, by = 0;
@@ -341,6 +345,16 @@ void backward(E* e, bool conc) {
       if (conc) order_after(e, e->stream2, e->stream);          // delta of this layer is complete on the main lane
       Lane lane(e, conc);
       if (!tc_dense_wgrad(e, nm, wg, e->ntow, fl, by)) launch_igemm(e, nm, wg[0], wg[1], e->ntow, true, fl, by);
+      if (split_bias) {
+        snprintf(nm, sizeof nm, "dense%d_bgrad", l + 1);
+        for (int t = 0; t < e->ntow; ++t) {
+          const Mat& w = e->tow[t][l];
+          Scope sc(e, nm, 0, 4.0 * B * w.N);
+          colsum_kernel<<<std::min(COLSUM_CTAS, (B + 7) / 8), 256, 0, e->ls>>>(e->tow_delta[t][l], (long long)B, w.N, e->grad + w.off + (long long)w.K * w.N,
+                                                                             e->colsum_part + (e->ls == e->stream ? 0 : COLSUM_CTAS * 1024), e->colsum_ticket + (e->ls == e->stream ? 0 : 1));
+          CK(cudaGetLastError());
+        }
+      }
     }
     // input gradients
     if (l > 0) {

@@ -285,14 +285,16 @@ struct DenseWgradOp {
   int M, N, K;               // M = Kin+1, K = batch rows
   int vecA, vecB;
   const float* Xs; const float* Ds; const float* ones; long long lo_delta; int a_single; float out_scale;   // out_scale: 1/255 when X holds raw bytes
-  DQN_HD bool tc_ready() const { return Xs && Ds && ones && ((M - 1) % 4 == 0) && (N % 4 == 0) && (ldx % 4 == 0) && (ldd % 4 == 0); }
+  int no_bias;               // 1: M = Kin, the bias gradient (column sums of D) is produced by colsum_kernel instead of a ones row
+  DQN_HD int kin() const { return no_bias ? M : M - 1; }
+  DQN_HD bool tc_ready() const { return Xs && Ds && ones && (kin() % 4 == 0) && (N % 4 == 0) && (ldx % 4 == 0) && (ldd % 4 == 0); }
   DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int m, int k) const {     // 4 consecutive m at batch row k
     if (!c.valid || k >= K) return nullptr;
-    const int cnt = (M - 1) - m;
+    const int cnt = kin() - m;
     return cnt >= 4 ? Xs + kc.off + m : (cnt == 0 ? ones : nullptr);
   }
   DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ds + (long long)k * ldd + n : nullptr; }
-  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= M - 1 && k0 + bk <= K; }       // excludes the ones row
+  DQN_HD bool interiorA(int m0, int k0, int bm, int bk) const { return m0 + bm <= kin() && k0 + bk <= K; }       // excludes the ones row
   DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
   DQN_HD const float* ptrA_u(const ACtx&, const KCtx& kc, int m, int) const { return Xs + kc.off + m; }
   DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ds + ((long long)k * ldd + n); }
@@ -301,8 +303,7 @@ struct DenseWgradOp {
   DQN_HD KCtx prepK(int k) const { KCtx c; c.off = (long long)k * ldx; c.t0 = c.t1 = c.t2 = 0; c.offb = 0; return c; }
   DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int m, int k) const {   // 4 consecutive m at batch row k
     if (!c.valid || k >= K) return make4(0, 0, 0, 0);
-    const int kin = M - 1;
-    const int cnt = kin - m;                                // real features left
+    const int cnt = kin() - m;                              // real features left
     float4 v;
     if (cnt <= 0) v = make4(0, 0, 0, 0);
     else if (x_u8) v = load4_u8((const uint8_t*)X + kc.off + m, cnt, vecA);
@@ -314,7 +315,7 @@ struct DenseWgradOp {
     if (k >= K || n >= N) return make4(0, 0, 0, 0);
     return load4_f32(D + (long long)k * ldd + n, N - n, vecB);
   }
-  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < M - 1) ? out_scale : 1.f; }
+  DQN_HD float oscale(int m) const { return (out_scale != 0.f && m < kin()) ? out_scale : 1.f; }
   DQN_HD void store(int m, int n, float v) const { dW[(long long)m * N + n] = v * oscale(m); }
   DQN_HD bool can_store4() const { return N % 4 == 0; }
   DQN_HD void store4(int m, int n, float4 v) const {

@@ -24,6 +24,7 @@
 // TC_EXP_NOLOAD / NOFIN / NOMMA / NOEPI (ablations: timing only, results are garbage), TC_CP_CG, TC_WAIT_IMPL, TC_MAX_STAGES.
 #pragma once
 #include <cstdlib>
+#include <cuda.h>          // CUtensorMap (type only: the encode functions are fetched through cudaGetDriverEntryPoint, no libcuda link)
 #ifndef TC_CP_CG
 #define TC_CP_CA 1
 #endif
@@ -36,6 +37,24 @@ __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (produ
 #else
 #define TRACE(st, ev) do { } while (0)
 #endif
+
+// ---- TMA feed (FEED_TMA launches): the operand stages are moved by cp.async.bulk.tensor, one elected producer thread instead of
+// eight loader warps.  Tensor maps are built on the host per operand set (tc_tma_* below) and travel as a __grid_constant__ struct.
+//   A K-major   (Dense forward / dgrad: rows of the activation / delta matrix): 2-D box 32 fp32 x 128 rows, SWIZZLE_128B - the
+//               converters read chunk j of row r at j ^ (r & 7); conv forward: the same box through an im2col-mode map
+//   A MN-major  (weight gradients: x^T): 2-D box 128 fp32 (m) x 32 rows (k), no swizzle - converters read a column
+//   B MN-major  (weights [K][N] / deltas [K][N]): 3-D box {32 fp32 of n, 32 k rows, BN/32 atoms of n}, SWIZZLE_128B_ATOM_32B -
+//               exactly the SWIZZLE_128B_BASE32B UMMA layout the cp.async loaders write by hand
+//   B K-major   (dgrad: W[n][k]): 2-D box 32 fp32 (k) x BN rows (n), SWIZZLE_128B (UMMA layout type 2, SBO 1024, 32 bytes per k step)
+// Out-of-range rows / columns are zero-filled by the TMA unit: no edge-tile code in the producer.
+enum { TMA_DENSE_FWD = 0, TMA_DENSE_DGRAD = 1, TMA_DENSE_WGRAD = 2, TMA_CONV_FWD = 3 };
+struct TmaMaps {
+  CUtensorMap a[4];              // per operand set; dgrad: per k segment (tower)
+  CUtensorMap b[4];
+  int kind;                      // TMA_*
+  int seg_k;                     // dgrad: k where the second segment starts (0: one segment)
+  int cin, kw, stride, oh, ow;   // conv forward: decode of (pixel, k stage) into im2col coordinates
+};
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-steps of 8)
@@ -99,12 +118,19 @@ template <> struct AStage8<true>  { static constexpr int PITCH = BM + 16; static
 // in flight behind the stage being finished, across tile boundaries (the ring never drains between tiles).
 // TMEM (all 512 columns): NBUF accumulator sets of NACC x BN columns (the epilogue of tile i overlaps the main loop of tile i+1 when
 // NBUF = 2), then a ring of AST A-operand stages of 64 columns each (32 k-columns of the hi plane, 32 of the lo plane).
-template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false> struct Lay {
+template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool TMA = false> struct Lay {
   using TB = Tile<BN, B_MN>;
   using SA = AStage<A_MN>;
   using SA8 = AStage8<A_MN>;
-  static constexpr int A_BYTES = ((A8 ? SA8::BYTES : SA::BYTES) + 1023) / 1024 * 1024;
-  static constexpr int B_BYTES = (TB::BYTES + 1023) / 1024 * 1024;     // every plane starts 1024-byte aligned (swizzled tiles need it)
+  static_assert(!(TMA && A8), "byte operands use the cp.async feed");
+  static_assert(!TMA || BN % 32 == 0, "TMA B boxes come in atoms of 32 columns");
+  static constexpr int A_BYTES = TMA ? BM * BK * 4 : ((A8 ? SA8::BYTES : SA::BYTES) + 1023) / 1024 * 1024;    // TMA boxes are dense (hardware swizzle, no padding)
+  static constexpr int B_PLANE = TMA ? BN * BK * 4 : TB::BYTES;
+  static constexpr int B_BYTES = (B_PLANE + 1023) / 1024 * 1024;       // every plane starts 1024-byte aligned (swizzled tiles need it)
+  // UMMA descriptor of the B planes: MN-major is the same layout in both feeds; K-major is the padded no-swizzle layout for cp.async
+  // and SWIZZLE_128B rows for TMA
+  static constexpr int B_LBO = (TMA && !B_MN) ? 16 : TB::LBO, B_SBO = (TMA && !B_MN) ? 1024 : TB::SBO, B_KSTEP = (TMA && !B_MN) ? 32 : TB::KSTEP;
+  static constexpr uint32_t B_LTYPE = B_MN ? 1u : (TMA ? 2u : 0u);     // 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B, 0 = none
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;            // A staging, B_hi(raw), B_lo
   static constexpr int TAIL = 1024 + 512;                              // alignment slack + barriers / tmem address
 #ifndef TC_MAX_STAGES
@@ -263,6 +289,21 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int n, int off_w, int off_h, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+               ::"r"(dst), "l"(tm), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"((uint16_t)off_w), "h"((uint16_t)off_h) : "memory");
+}
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), major bits 15/16 (1 = MN-major), N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc2(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -273,13 +314,13 @@ __device__ __forceinline__ uint32_t byte_to_f32(uint32_t w, int j) {
   return __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)) - 8388608.0f);
 }
 
-template <int BN, int R, int NBUF, bool A8, class Op>
+template <int BN, int R, int NBUF, bool A8, class Op, bool TMA = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, const __grid_constant__ Op opc, const __grid_constant__ Op opd,
                int nsplit, float* __restrict__ ws, long long ws_stride, const float* __restrict__ zero_src, int MT, int NT, int ntiles,
-               int tail_t0, int tail_s) {
+               int tail_t0, int tail_s, const __grid_constant__ TmaMaps tmaps) {
   constexpr bool A_MN = Op::A_MCONTIG, B_MN = !Op::B_KCONTIG;
-  using L = Lay<BN, R, NBUF, A_MN, B_MN, A8>;
+  using L = Lay<BN, R, NBUF, A_MN, B_MN, A8, TMA>;
   using TB = typename L::TB;
   using SA = typename L::SA;
   using SA8 = typename L::SA8;
@@ -301,7 +342,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   const bool a_lo = !opa.a_single;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, NMMA); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, TMA ? 1 : LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, NMMA); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -376,7 +417,45 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   };
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
-  if (warp < LOAD_WARPS) {
+  if (TMA && warp < LOAD_WARPS) {
+    reg_dec<56>();
+    // ================= TMA producer: one thread, two instructions per stage; the other loader warps have nothing to do =================
+    if (warp == 0) {
+      int is = 0; uint32_t iph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        Op op; int m0, n0, zs, kt0, nk;
+        if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+        const int zi = Op::Z_IS_CLASS ? 0 : min(zs / nsplit, 3);
+        int pw = 0, ph_ = 0, pn = 0;                             // conv forward: first output pixel of the tile -> (ow, oh, image)
+        if (tmaps.kind == TMA_CONV_FWD) { pw = m0 % tmaps.ow; const int q = m0 / tmaps.ow; ph_ = q % tmaps.oh; pn = q / tmaps.oh; }
+        for (int it = 0; it < nk; ++it) {
+          const int k0 = (kt0 + it) * BK;
+          const uint32_t a_st = sbase + is * L::STAGE_BYTES, b_hi = a_st + L::A_BYTES, bar = bar_landed + 8 * is;
+          mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
+          if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)(BM * BK * 4 + BN * BK * 4));
+            if (tmaps.kind == TMA_CONV_FWD) {                    // k stage -> (tap row, tap column, first channel); one tap's 32 channels per stage
+              const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;
+              tma_load_im2col_4d(a_st, &tmaps.a[zi], c0, pw * tmaps.stride, ph_ * tmaps.stride, pn, tw, th, bar);
+              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+            } else if (tmaps.kind == TMA_DENSE_FWD) {
+              tma_load_2d(a_st, &tmaps.a[zi], k0, m0, bar);
+              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+            } else if (tmaps.kind == TMA_DENSE_WGRAD) {
+              tma_load_2d(a_st, &tmaps.a[zi], m0, k0, bar);
+              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+            } else {                                             // dgrad: k segments (towers) have their own delta / weight matrices
+              const int sg = (tmaps.seg_k > 0 && k0 >= tmaps.seg_k) ? 1 : 0, kk = k0 - sg * tmaps.seg_k;
+              tma_load_2d(a_st, &tmaps.a[sg], kk, m0, bar);
+              tma_load_2d(b_hi, &tmaps.b[sg], kk, n0, bar);
+            }
+          }
+          __syncwarp();
+          if (++is == STAGES) { is = 0; iph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < LOAD_WARPS) {
     reg_dec<56>();
     // ================= loaders: chunk addresses + cp.async into ring slot, completion signalled on landed[slot] =================
     constexpr int A_PER = BM * (BK / 4) / LOADERS;             // 8 chunks of A per thread per stage
@@ -487,11 +566,15 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       const int e = gtid + i * GT;
-      if (B_MN) { const int g = e % (BN / 4), kk = e / (BN / 4); b_off[i] = (g >> 3) * TB::LBO + kk * 128 + (((g & 7) ^ ((kk & 3) << 1)) * 16); }
+      if (TMA) b_off[i] = e * 16;                               // dense planes: lo(chunk) goes to the same offset of the lo plane, whatever the swizzle
+      else if (B_MN) { const int g = e % (BN / 4), kk = e / (BN / 4); b_off[i] = (g >> 3) * TB::LBO + kk * 128 + (((g & 7) ^ ((kk & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
-    const uint32_t a_rd = A8 ? (A_MN ? (uint32_t)(kh * 16 * SA8::PITCH + row) : (uint32_t)(row * SA8::PITCH + kh * 16))
+    // TMA staging tiles: K-major = 128-byte rows under SWIZZLE_128B (chunk j of row r at j ^ (r & 7)), MN-major = dense [32 k][128 m]
+    const uint32_t a_rd = TMA ? (A_MN ? (uint32_t)(kh * 16 * (BM * 4) + row * 4) : (uint32_t)(row * 128))
+                        : A8 ? (A_MN ? (uint32_t)(kh * 16 * SA8::PITCH + row) : (uint32_t)(row * SA8::PITCH + kh * 16))
                              : (A_MN ? (uint32_t)(kh * 16 * SA::PITCH + row * 4) : (uint32_t)(row * SA::PITCH + kh * 64));
+    constexpr uint32_t A_KPITCH = TMA ? (uint32_t)(BM * 4) : (uint32_t)SA::PITCH;   // MN-major: bytes between k rows
     const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0 + (uint32_t)(kh * 16);
     int gg = 0;                                                // global stage counter (all tiles)
     int s = grp; uint32_t ph = 0;                              // ring slot / phase of this group's next stage
@@ -525,11 +608,11 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
           }
         } else if (A_MN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = lds32(a_st + a_rd + i * SA::PITCH);
+          for (int i = 0; i < 16; ++i) v[i] = lds32(a_st + a_rd + i * A_KPITCH);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = lds128(a_st + a_rd + i * 16);
+            const float4 f = lds128(TMA ? a_st + a_rd + (uint32_t)(((kh * 4 + i) ^ (row & 7)) * 16) : a_st + a_rd + i * 16);
             v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
           }
         }
@@ -659,11 +742,11 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
           const uint32_t b_hi = sbase + s * L::STAGE_BYTES + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
           const uint32_t a_hi_t = tmem + ACOL0 + (uint32_t)(as * 64), a_lo_t = a_hi_t + 32;
-          constexpr uint32_t LTB = B_MN ? 1u : 0u;               // 1 = SWIZZLE_128B_BASE32B, 0 = no swizzle
+          constexpr uint32_t LTB = L::B_LTYPE;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dbh = make_desc(b_hi + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
-            const uint64_t dbl = make_desc(b_lo_s + j * TB::KSTEP, TB::LBO, TB::SBO, LTB);
+            const uint64_t dbh = make_desc(b_hi + j * L::B_KSTEP, L::B_LBO, L::B_SBO, LTB);
+            const uint64_t dbl = make_desc(b_lo_s + j * L::B_KSTEP, L::B_LBO, L::B_SBO, LTB);
             const int ks = it * (BK / 8) + j;                     // k-step index within this tile
 #ifdef TC_EXP_NOMMA
             if (ks < 0)
@@ -691,23 +774,116 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 
 }  // namespace tc
 
+
+// ---- host side of the TMA feed: tensor maps per operand -------------------------------------------------------------------------
+namespace tc {
+struct TmaApi {
+  typedef CUresult (*EncTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  typedef CUresult (*EncIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncTiled tiled = nullptr; EncIm2col im2col = nullptr; bool tried = false;
+  bool load() {
+    if (!tried) {
+      tried = true;
+      void* f = nullptr; cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess && f) tiled = (EncTiled)f;
+      f = nullptr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &qr) == cudaSuccess && f) im2col = (EncIm2col)f;
+    }
+    return tiled && im2col;
+  }
+};
+inline TmaApi& tma_api() { static TmaApi a; return a; }
+inline bool tma_ok16(const void* p, long long ld_floats) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_floats % 4) == 0; }
+
+// row-major fp32 matrix [rows][ld], `cols` valid columns: box bc x br
+inline bool tma_tiled_2d(CUtensorMap* m, const float* p, long long rows, long long cols, long long ld, int bc, int br, CUtensorMapSwizzle sw) {
+  if (!tma_api().load() || !tma_ok16(p, ld) || rows < 1 || cols < 1) return false;
+  cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t bx[2] = {(cuuint32_t)bc, (cuuint32_t)br}, es[2] = {1, 1};
+  return tma_api().tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool tma_a_kmajor(CUtensorMap* m, const float* p, long long rows, long long kcols, long long ld) { return tma_tiled_2d(m, p, rows, kcols, ld, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B); }
+inline bool tma_a_mnmajor(CUtensorMap* m, const float* p, long long krows, long long mcols, long long ld) { return tma_tiled_2d(m, p, krows, mcols, ld, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE); }
+inline bool tma_b_kmajor(CUtensorMap* m, const float* p, long long nrows, long long kcols, long long ld, int bn) { return tma_tiled_2d(m, p, nrows, kcols, ld, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B); }
+// [krows][ld] with ncols valid columns, n contiguous: {32 n, k, atoms of 32 n}
+inline bool tma_b_mnmajor(CUtensorMap* m, const float* p, long long krows, long long ncols, long long ld, int bn) {
+  if (!tma_api().load() || !tma_ok16(p, ld) || ncols % 32 != 0 || krows < 1) return false;
+  cuuint64_t gd[3] = {32, (cuuint64_t)krows, (cuuint64_t)(ncols / 32)}, gs[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t bx[3] = {32, (cuuint32_t)BK, (cuuint32_t)(bn / 32)}, es[3] = {1, 1, 1};
+  return tma_api().tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// NHWC fp32 activations [nimg][IH][IW][Cin] as an im2col-mode map: 128 output pixels x 32 channels of one filter tap per load
+inline bool tma_a_im2col(CUtensorMap* m, const float* p, int nimg, const dqn::ConvGeom& g) {
+  if (!tma_api().load() || (reinterpret_cast<uintptr_t>(p) & 15) || g.Cin % 32 != 0 || g.KH > 128 || g.KW > 128 || g.S > 8) return false;
+  cuuint64_t gd[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)nimg};
+  cuuint64_t gs[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.IW * g.Cin * 4, (cuuint64_t)g.IH * g.IW * g.Cin * 4};
+  int lo[2] = {0, 0}, up[2] = {-(g.KW - 1), -(g.KH - 1)};       // no padding: base pixels keep the whole filter window inside the image
+  cuuint32_t es[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
+  return tma_api().im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// operand sets of one launch -> maps; false = this launch stays on the cp.async feed
+inline bool tma_build(const dqn::DenseFwdOp* ops, int nops, int bn, TmaMaps& tm) {
+  tm.kind = TMA_DENSE_FWD;
+  for (int i = 0; i < nops; ++i)
+    if (!ops[i].Xs || !tma_a_kmajor(&tm.a[i], ops[i].Xs, ops[i].M, ops[i].K, ops[i].ldx) || !tma_b_mnmajor(&tm.b[i], ops[i].Ws, ops[i].K, ops[i].N, ops[i].N, bn)) return false;
+  return true;
+}
+inline bool tma_build(const dqn::DenseDgradOp* ops, int nops, int bn, TmaMaps& tm) {
+  if (nops != 1) return false;
+  const dqn::DenseDgradOp& o = ops[0];
+  tm.kind = TMA_DENSE_DGRAD; tm.seg_k = o.K1;
+  const int k0 = o.seg0();
+  if (k0 % BK != 0) return false;
+  if (!tma_a_kmajor(&tm.a[0], o.Ds, o.M, k0, o.ldd) || !tma_b_kmajor(&tm.b[0], o.Ws, o.N, k0, k0, bn)) return false;
+  if (o.K1 > 0 && (!tma_a_kmajor(&tm.a[1], o.Ds2, o.M, o.K - o.K1, o.ldd2) || !tma_b_kmajor(&tm.b[1], o.Ws2, o.N, o.K - o.K1, o.K - o.K1, bn))) return false;
+  return true;
+}
+inline bool tma_build(const dqn::DenseWgradOp* ops, int nops, int bn, TmaMaps& tm) {
+  tm.kind = TMA_DENSE_WGRAD;
+  for (int i = 0; i < nops; ++i) {
+    if (!ops[i].no_bias || !ops[i].Xs) return false;            // the ones row of [x 1] is not a box: bias gradient by colsum_kernel
+    if (!tma_a_mnmajor(&tm.a[i], ops[i].Xs, ops[i].K, ops[i].M, ops[i].ldx) || !tma_b_mnmajor(&tm.b[i], ops[i].Ds, ops[i].K, ops[i].N, ops[i].ldd, bn)) return false;
+  }
+  return true;
+}
+inline bool tma_build(const dqn::ConvFwdOp* ops, int nops, int bn, TmaMaps& tm) {
+  tm.kind = TMA_CONV_FWD;
+  for (int i = 0; i < nops; ++i) {
+    const dqn::ConvFwdOp& o = ops[i];
+    if (o.a8 || !o.Xs || o.g.Cin % 32 != 0) return false;
+    if (i > 0 && (o.g.Cin != ops[0].g.Cin || o.g.KW != ops[0].g.KW || o.g.S != ops[0].g.S || o.g.OH != ops[0].g.OH || o.g.OW != ops[0].g.OW)) return false;
+    if (!tma_a_im2col(&tm.a[i], o.Xs, o.nimg, o.g) || !tma_b_mnmajor(&tm.b[i], o.Ws, o.K, o.N, o.N, bn)) return false;
+  }
+  tm.cin = ops[0].g.Cin; tm.kw = ops[0].g.KW; tm.stride = ops[0].g.S; tm.oh = ops[0].g.OH; tm.ow = ops[0].g.OW;
+  return true;
+}
+inline bool tma_build(const dqn::ConvWgradOp*, int, int, TmaMaps&) { return false; }
+inline bool tma_build(const dqn::ConvDgradOp*, int, int, TmaMaps&) { return false; }
+}  // namespace tc
+
 #ifndef TC_KERNEL_ONLY
 namespace {
 
-template <int BN, int R, int NBUF, bool A8, class Op>
-void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long ws_stride, int MT, int NT, int ntiles, int tail_t0, int tail_s) {
-  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, A8>;
+template <int BN, int R, int NBUF, bool A8, class Op, bool TMA = false>
+void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long ws_stride, int MT, int NT, int ntiles, int tail_t0, int tail_s, const tc::TmaMaps& tm) {
+  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, A8, TMA>;
   // the opt-in above 48 KB of dynamic shared memory is a per-device function attribute: one flag per device ordinal, not per process
   // (a second engine on another GPU of the same process - dqn_group_create - needs its own opt-in)
   static unsigned long long attr_set[4] = {0, 0, 0, 0};
   const int dev = e->cfg.device & 255;
   if (!((attr_set[dev >> 6] >> (dev & 63)) & 1ull)) {
-    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, A8, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
+    CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, A8, Op, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set[dev >> 6] |= 1ull << (dev & 63);
   }
   const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
-  tc::tc_gemm_kernel<BN, R, NBUF, A8, Op><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
-                                                                            nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles, tail_t0, tail_s);
+  tc::tc_gemm_kernel<BN, R, NBUF, A8, Op, TMA><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
+                                                                                 nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles, tail_t0, tail_s, tm);
   CK(cudaGetLastError());
 }
 
@@ -773,15 +949,21 @@ bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz,
     Scope sc(e, name, flops, bytes);
     bool a8 = false;
     if constexpr (Op::HAS_A8) { a8 = ops[0].a8 != 0; for (int i = 1; i < nops; ++i) a8 = a8 && ops[i].a8 != 0; }
+    tc::TmaMaps tm; memset(&tm, 0, sizeof tm);
+    // TMA feed wherever the operands are boxes (Dense layers, conv forward over >= 32 input channels); the rest keeps the cp.async loaders
+    const bool tma = e->tc_tma && !a8 && tail_s <= 1 && tc::tma_build(ops, nops, bn, tm);
     if constexpr (Op::HAS_A8) {
       if (a8) {
-        if (bn == 32) tc_launch_v<32, 2, 2, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s);
-        else tc_launch_v<64, 2, 1, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s);
+        if (bn == 32) tc_launch_v<32, 2, 2, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
+        else tc_launch_v<64, 2, 1, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
       }
     }
-    if (!a8) {
-      if (bn == 32) tc_launch_v<32, 2, 2, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s);
-      else tc_launch_v<64, 2, 1, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s);
+    if (!a8 && tma) {
+      if (bn == 32) tc_launch_v<32, 2, 2, false, Op, true>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
+      else tc_launch_v<64, 2, 1, false, Op, true>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
+    } else if (!a8) {
+      if (bn == 32) tc_launch_v<32, 2, 2, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
+      else tc_launch_v<64, 2, 1, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
     }
   }
   if (tail_s > 1) {
@@ -823,6 +1005,7 @@ void tc_init(dqn_engine* e) {
   // off by default: in the three-lane schedule the other lanes' kernels already fill the SMs that an underfilled last round leaves
   // idle (measured 0.499 ms/step with the tail split against 0.486 without, although every affected kernel alone is 20-27 % faster)
   { const char* v = getenv("DQN_TC_TAIL"); e->tc_tail = v ? atoi(v) : 0; }
+  { const char* v = getenv("DQN_TC_TMA"); e->tc_tma = v ? atoi(v) : 1; }
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
   const bool bytes = e->elem_bytes == 1;

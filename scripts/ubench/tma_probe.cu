@@ -123,7 +123,7 @@ int main() {
     const char* names[] = {"NONE", "32B", "64B", "128B", "128B_ATOM_32B", "128B_ATOM_32B_FLIP_8B", "128B_ATOM_64B"};
     const CUtensorMapSwizzle modes[] = {CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_128B,
                                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B_FLIP_8B, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_64B};
-    for (int mi = 0; mi < 7; ++mi) {
+    for (int mi = 3; mi < 5; ++mi) {     // (NONE / 32B / 64B / FLIP_8B were read in an earlier run; ATOM_64B is store-only: a load traps)
       const int bw = mi == 1 ? 8 : mi == 2 ? 16 : 32;            // box width in fp32 = swizzle span
       CUtensorMap tm; cuuint64_t gdim[2] = {(cuuint64_t)Ccols, (cuuint64_t)R}, gstr[1] = {(cuuint64_t)Ccols * 4}; cuuint32_t box[2] = {(cuuint32_t)bw, 16}, es[2] = {1, 1};
       CUresult r = encT(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, modes[mi], CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

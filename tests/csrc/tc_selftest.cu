@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "../../deepqlearning.jl_b200/csrc/igemm.cuh"
 using namespace dqn;
@@ -32,16 +33,25 @@ struct Arena {
 #define TEST_R 2
 #endif
 static int g_nsm = 148;
-template <int BN, class Op>
-static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
+static int g_feed = 0;            // 0: cp.async loaders, 1: TMA producer (where the operands are boxes; other launches fall back and say so)
+template <int BN, bool TMA, class Op>
+static void launch_tc_feed(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero, const tc::TmaMaps& tm) {
   constexpr int R = BN == 32 ? 2 : TEST_R, NBUF = BN == 32 ? 2 : (TEST_R == 1 ? 2 : 1);
-  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG>;
+  using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, false, TMA>;
   static bool attr = false;
-  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, false, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
+  if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, false, Op, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
   Op o0 = op; if (Op::Z_IS_CLASS) o0.set_class(0);
   const int MT = (o0.M + 127) / 128, NT = (o0.N + BN - 1) / BN, ntiles = MT * NT * nz * nsplit;
   const int grid = ntiles < g_nsm ? ntiles : g_nsm;
-  tc::tc_gemm_kernel<BN, R, NBUF, false, Op><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles, 0, 0);
+  tc::tc_gemm_kernel<BN, R, NBUF, false, Op, TMA><<<grid, tc::THREADS, L::SMEM>>>(op, op, op, op, nsplit, ws, ws_stride, zero, MT, NT, ntiles, 0, 0, tm);
+}
+static bool g_last_tma = false;
+template <int BN, class Op>
+static void launch_tc_raw(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
+  tc::TmaMaps tm; memset(&tm, 0, sizeof tm);
+  g_last_tma = g_feed == 1 && tc::tma_build(&op, 1, BN, tm);
+  if (g_last_tma) launch_tc_feed<BN, true>(op, nz, nsplit, ws, ws_stride, zero, tm);
+  else launch_tc_feed<BN, false>(op, nz, nsplit, ws, ws_stride, zero, tm);
 }
 template <int BN, class Op>
 static void run_tc(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero) {
@@ -56,7 +66,7 @@ static void report(const char* name, const std::vector<float>& got, const std::v
   double mx = 0, mr = 0; size_t at = 0;
   for (size_t i = 0; i < ref.size(); ++i) { double d = std::fabs((double)got[i] - ref[i]); if (d > mx) { mx = d; at = i; } mr = std::fmax(mr, std::fabs((double)ref[i])); }
   const bool ok = mx <= g_tol * mr;
-  printf("%s %-28s maxdiff %.3e (ref max %.3e) at %zu: got %g ref %g\n", ok ? "ok  " : "FAIL", name, mx, mr, at, got[at], ref[at]);
+  printf("%s %-5s %-28s maxdiff %.3e (ref max %.3e) at %zu: got %g ref %g\n", ok ? "ok  " : "FAIL", g_last_tma ? "[tma]" : "[cpa]", name, mx, mr, at, got[at], ref[at]);
   if (!ok) ++fails;
 }
 
@@ -90,10 +100,11 @@ template <int BN> static void test_dense(int M, int N, int K) {
   }
   {   // wgrad: both MN-major, with the ones column
     DenseWgradOp op{}; op.X = X.data(); op.ldx = K; op.D = D.data(); op.ldd = N; op.M = K + 1; op.N = N; op.K = M; op.vecA = op.vecB = 1;
-    std::vector<float> ref((K + 1) * N); op.dW = ref.data(); igemm_host(op);
+    if (g_feed == 1) { op.no_bias = 1; op.M = K; }            // TMA feed: no ones row (the bias gradient is a column sum elsewhere)
+    std::vector<float> ref((K + 1) * N, 0.f); op.dW = ref.data(); igemm_host(op);
     DenseWgradOp g = op; g.X = dX; g.D = dD; g.dW = dG; g.Xs = ar.d + oX; g.Ds = ar.d + oD; g.ones = ar.d + oOnes; g.lo_delta = ar.plane;
     run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
-    std::vector<float> got((K + 1) * N); CKC(cudaMemcpy(got.data(), dG, got.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> got((K + 1) * N, 0.f); CKC(cudaMemcpy(got.data(), dG, (size_t)op.M * N * 4, cudaMemcpyDeviceToHost));
     report("dense_wgrad(A:MN B:MN)", got, ref);
   }
   cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dC); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
@@ -184,20 +195,28 @@ int main(int argc, char** argv) {
   { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
     const int it = argc > 2 ? atoi(argv[2]) : 20;
-    bench_dense<64>(41472, 64, 512, it);       // conv2 forward shape
-    bench_dense<64>(37888, 64, 512, it);       // same, exactly one wave of 296 CTAs
-    bench_dense<32>(204800, 32, 256, it);      // conv1 forward shape (with a lo plane here)
-    bench_dense<64>(512, 1024, 3136, it);      // fc1 forward, both towers (64 tiles, no k split here)
-    bench_dense<64>(18944, 128, 512, it);      // two waves of BN=64 tiles
+    for (g_feed = 0; g_feed < 2; ++g_feed) {
+      printf("== feed: %s\n", g_feed ? "TMA" : "cp.async");
+      bench_dense<64>(41472, 64, 512, it);       // conv2 forward shape
+      bench_dense<64>(37888, 64, 512, it);       // same, exactly one wave of 296 CTAs
+      bench_dense<32>(204800, 32, 256, it);      // conv1 forward shape (with a lo plane here)
+      bench_dense<64>(512, 1024, 3136, it);      // fc1 forward, both towers (64 tiles, no k split here)
+      bench_dense<64>(18944, 128, 512, it);      // two waves of BN=64 tiles
+    }
     return 0;
   }
-  printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
-  printf("-- dense M=200 N=128 K=160 (BN=64, two n tiles)\n"); test_dense<64>(200, 128, 160);
-  printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
-  printf("-- conv 4 img 20x20x8 -> 16, 4x4 s2 (BN=32)\n"); test_conv<32>(4, 20, 20, 8, 16, 4, 4, 2);
-  printf("-- conv 3 img 9x9x32 -> 64, 3x3 s1 (BN=64)\n");  test_conv<64>(3, 9, 9, 32, 64, 3, 3, 1);
-  printf("-- dense M=39685 N=64 K=96 (BN=64, 311 tiles: several tiles per persistent CTA)\n"); g_tol = 1e-4; test_dense<64>(39685, 64, 96); g_tol = 2e-5;
-  printf("-- conv 2 img 84x84x4 -> 32, 8x8 s4 (BN=32, conv1 geometry)\n"); test_conv<32>(2, 84, 84, 4, 32, 8, 8, 4);
+  for (g_feed = 0; g_feed < 2; ++g_feed) {
+    printf("==== feed: %s\n", g_feed ? "TMA where the operands are boxes" : "cp.async loaders");
+    printf("-- dense M=256 N=64 K=96 (BN=64)\n");  test_dense<64>(256, 64, 96);
+    printf("-- dense M=200 N=128 K=160 (BN=64, two n tiles)\n"); test_dense<64>(200, 128, 160);
+    printf("-- dense M=130 N=32 K=64 (BN=32)\n");   test_dense<32>(130, 32, 64);
+    printf("-- conv 4 img 20x20x8 -> 16, 4x4 s2 (BN=32)\n"); test_conv<32>(4, 20, 20, 8, 16, 4, 4, 2);
+    printf("-- conv 3 img 9x9x32 -> 64, 3x3 s1 (BN=64)\n");  test_conv<64>(3, 9, 9, 32, 64, 3, 3, 1);
+    printf("-- conv 5 img 20x20x32 -> 64, 4x4 s2 (BN=64, conv2 geometry, tiles cross images)\n");  test_conv<64>(5, 20, 20, 32, 64, 4, 4, 2);
+    printf("-- conv 5 img 9x9x64 -> 64, 3x3 s1 (BN=64, conv3 geometry, two k stages per tap)\n");  test_conv<64>(5, 9, 9, 64, 64, 3, 3, 1);
+    printf("-- dense M=39685 N=64 K=96 (BN=64, 311 tiles: several tiles per persistent CTA)\n"); g_tol = 1e-4; test_dense<64>(39685, 64, 96); g_tol = 2e-5;
+    printf("-- conv 2 img 84x84x4 -> 32, 8x8 s4 (BN=32, conv1 geometry)\n"); test_conv<32>(2, 84, 84, 4, 32, 8, 8, 4);
+  }
   printf(fails ? "SELFTEST FAILED %d\n" : "SELFTEST OK\n", fails);
   return fails ? 1 : 0;
 }

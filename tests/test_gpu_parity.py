@@ -447,7 +447,8 @@ def test_replay_add_device_matches_host_add(lib):
     n = spec["N"] + 11
     s, a, r, sp, done = util.random_transitions(spec, n, seed=41)
     td0 = np.abs(r)
-    e_host.replay_add(s, a, r, sp, done, td0)
+    for lo, hi in ((0, 100), (100, n)):
+        e_host.replay_add(s[lo:hi], a[lo:hi], r[lo:hi], sp[lo:hi], done[lo:hi], td0[lo:hi])
     dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
     for lo, hi in ((0, 100), (100, n)):
         ts, ta, tr, tsp, td, ttd = dev(s[lo:hi]), dev(a[lo:hi]), dev(r[lo:hi]), dev(sp[lo:hi]), dev(done[lo:hi]), dev(td0[lo:hi])
