@@ -7,8 +7,8 @@ All numerical work happens in libdqn_b200.so (hand-written sm_100a CUDA kernels)
 include/dqn_b200.h; importing this package fails if that library is missing."""
 from . import _capi
 from ._capi import DQNError, MATH_FP32, MATH_3XTF32
-from .engine import Engine, make_config, nccl_unique_id
-from .flux import (Chain, Dense, Conv, flattenbatch, DuelingNetwork, create_dueling_network, isrecurrent, flat_params,
+from .engine import Engine, Group, make_config, nccl_unique_id
+from .flux import (Chain, Dense, Conv, LSTM, flattenbatch, DuelingNetwork, create_dueling_network, isrecurrent, flat_params,
                    load_flat_params, identity, relu, tanh, sigmoid)
 from .dist import ControlPlane, shard_seeds
 from .replay import PrioritizedReplayBuffer, DQExperience

@@ -14,7 +14,7 @@ DQN_MAX_LAYERS = 16
 DQN_NCCL_ID_BYTES = 128
 DQN_OK, DQN_ERR_INVALID, DQN_ERR_CUDA, DQN_ERR_STATE, DQN_ERR_NCCL, DQN_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
-LAYER_DENSE, LAYER_CONV, LAYER_FLATTEN = 0, 1, 2
+LAYER_DENSE, LAYER_CONV, LAYER_FLATTEN, LAYER_LSTM = 0, 1, 2, 3
 OBS_F32, OBS_U8 = 0, 1
 NET_ONLINE, NET_TARGET = 0, 1
 Q_S_ONLINE, Q_SP_ONLINE, Q_SP_TARGET = 0, 1, 2
@@ -35,7 +35,8 @@ class dqn_config_t(C.Structure):
                 ("learning_rate", C.c_float), ("discount", C.c_float),
                 ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
                 ("seed", C.c_uint64), ("math_mode", C.c_int32), ("use_graph", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("nccl_id", C.c_uint8 * DQN_NCCL_ID_BYTES), ("max_act_rows", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("nccl_id", C.c_uint8 * DQN_NCCL_ID_BYTES), ("max_act_rows", C.c_int32), ("trace_length", C.c_int32), ("max_episode_length", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class DQNError(RuntimeError):
@@ -63,6 +64,14 @@ SIGNATURES = {
     "dqn_last_error": (C.c_char_p, [_H]),
     "dqn_nccl_unique_id": (C.c_int, [_u8p]),
     "dqn_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "dqn_group_create": (C.c_int, [C.POINTER(dqn_config_t), C.c_int, C.POINTER(C.c_int), C.POINTER(_H)]),
+    "dqn_group_destroy": (None, [_H]),
+    "dqn_group_size": (C.c_int, [_H]),
+    "dqn_group_engine": (_H, [_H, C.c_int]),
+    "dqn_group_last_error": (C.c_char_p, [_H]),
+    "dqn_group_set_params": (C.c_int, [_H, C.c_int, _f32p, C.c_int64]),
+    "dqn_group_sync_target": (C.c_int, [_H]),
+    "dqn_group_train_step": (C.c_int, [_H, _f32p, _f32p]),
     "dqn_num_params": (C.c_int64, [_H]),
     "dqn_set_params": (C.c_int, [_H, C.c_int, _f32p, C.c_int64]),
     "dqn_get_params": (C.c_int, [_H, C.c_int, _f32p, C.c_int64]),
@@ -73,6 +82,10 @@ SIGNATURES = {
     "dqn_replay_size": (C.c_int, [_H, _i64p, _i64p]),
     "dqn_replay_fill_synthetic": (C.c_int, [_H, C.c_int64, C.c_uint64]),
     "dqn_replay_read": (C.c_int, [_H, _i64p, C.c_int64, C.c_void_p, _i32p, _f32p, C.c_void_p, _u8p]),
+    "dqn_episode_add": (C.c_int, [_H, _f32p, _i32p, _f32p, _f32p, _u8p, C.c_int64]),
+    "dqn_episode_count": (C.c_int, [_H, _i64p, _i64p]),
+    "dqn_episode_sample": (C.c_int, [_H, C.c_uint64, _i64p, _i32p]),
+    "dqn_policy_reset": (C.c_int, [_H]),
     "dqn_update_priorities": (C.c_int, [_H, _i64p, _f32p, C.c_int64]),
     "dqn_set_priorities": (C.c_int, [_H, _i64p, _f32p, C.c_int64]),
     "dqn_get_priorities": (C.c_int, [_H, _f32p, C.c_int64]),

@@ -14,13 +14,18 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dqn_b200.h"
 #include "igemm.cuh"
 #include "kernels.cuh"
+#include "lstm.cuh"
 #include "tc_gemm.cuh"
 
 using namespace dqn;
@@ -127,6 +132,8 @@ struct dqn_engine {
   cudaGraphExec_t graph_sample = nullptr, graph_idx = nullptr;
   // nccl
   ncclComm_t comm = nullptr;
+  int nccl_ctas = 0;       // CTAs NCCL may use (NCCL_MAX_CTAS) = SMs the persistent grids leave free while a reduction is in flight
+  int sm_reserve = 0;      // SMs currently held back from the persistent tensor-core grids
   // measurement
   cudaEvent_t t0 = nullptr, t1 = nullptr, copy_done = nullptr;
   int counting = 0, launches = 0, launches_per_step = 0;
@@ -139,9 +146,21 @@ struct dqn_engine {
   float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
-  int tc_split = 0; int tc_tail = 0; int tc_tma = 1;
+  int tc_split = 0; int tc_tail = 0; int tc_tma = 1; int tc_c1 = 1; int tc_tma_wgrad = 0;
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
+  // recurrent engines (one LSTM as the trunk, SOLVER:239-287): the network batch is trace_length * batch_size rows, time-major
+  int lstm = 0, lstm_in = 0, Hh = 0, T = 0, Bep = 0, Lmax = 0;
+  Mat wi{}, wh{}; long long h0_off = 0, c0_off = 0;   // internal parameters: W_i^T with the bias row, W_h^T, state0
+  float *ep_s = nullptr, *ep_sp = nullptr, *ep_r = nullptr; int *ep_a = nullptr, *ep_len = nullptr; uint8_t* ep_done = nullptr;
+  float *xproj_on = nullptr, *xproj_tg = nullptr;      // [2TB][4H], [TB][4H]: x W_i^T + b of every step
+  float *hs_on = nullptr, *hs_tg = nullptr;            // [(2T+1) Bep][H]: h0 | h of the s pass | h of the s' pass;  [(T+1) Bep][H]
+  float *cs_on = nullptr, *cs_sp = nullptr, *cs_tg = nullptr;   // cell states: [(T+1) Bep][H] of the s pass (kept for BPTT), ping-pong pairs of the others
+  float *gates_s = nullptr, *dgates = nullptr, *dcell = nullptr, *whT = nullptr;
+  float *h_act = nullptr, *c_act = nullptr; int act_rows = 0;   // acting hidden state (POLICY:32-34), one row per lane
+  int* ep_start_d = nullptr;
+  // trunk hand-over to the towers (conv trunk: the last conv layer; LSTM trunk: the hidden states)
+  float *trunk_on = nullptr, *trunk_tg = nullptr, *trunk_delta = nullptr; int trunk_act = 0;
   int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction
   int a8 = 0;              // 1: the first conv layer (forward and weight gradient) reads the byte batch directly, no fp32 copy of it exists
   int merge_fwd = 0;       // 1: online and target forward share launches layer by layer; measured slower than two lanes on B200 (0.571 vs 0.539 ms/step)
@@ -234,7 +253,7 @@ void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everyt
 // ---- network schedule ---------------------------------------------------------------------------
 // One forward pass: parameters P applied to the rows of X.  Xs: the input batch as fp32 for the tensor-core path (null => fp32
 // CUDA-core kernels only); w1s: the first conv layer's weights pre-scaled by 1/255 when Xs holds raw byte values.
-struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; bool tc; };
+struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; bool tc; const float* trunk_out = nullptr; };
 
 // Layer by layer over all passes.  On the tensor-core path the passes of a layer (online network on [s ; s'], target network on s')
 // and the two towers of a Dense layer share ONE launch: the persistent kernels serialise on the machine anyway, and one launch
@@ -242,6 +261,7 @@ struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; 
 void forward(E* e, const Pass* ps, int np) {
   const void* cur[2]; int cur_u8[2]; const float* cur_s[2];
   for (int p = 0; p < np; ++p) { cur[p] = ps[p].X; cur_u8[p] = ps[p].x_u8; cur_s[p] = ps[p].Xs; }
+  for (int p = 0; p < np; ++p) if (ps[p].trunk_out) { cur[p] = ps[p].trunk_out; cur_u8[p] = 0; cur_s[p] = ps[p].trunk_out; }   // recurrent trunk: the towers read the hidden states
   char nm[64];
   for (size_t l = 0; l < e->convs.size(); ++l) {
     const ConvL& c = e->convs[l];
@@ -265,6 +285,7 @@ void forward(E* e, const Pass* ps, int np) {
     if (!(np > 1 && tc_conv_fwd(e, nm, ops, np, fls, bys))) {
       for (int p = 0; p < np; ++p) {
         snprintf(nm, sizeof nm, "conv%zu_fwd_%s", l + 1, ps[p].tag);
+        if (l == 0 && tc_conv1_fwd(e, nm, ops[p], fl[p], by[p])) continue;      // raw byte observations: the dedicated first-layer kernel
         if (!tc_conv_fwd(e, nm, &ops[p], 1, fl[p], by[p])) launch_igemm(e, nm, ops[p], ops[p], 1, false, fl[p], by[p]);
       }
     }
@@ -315,26 +336,28 @@ void enqueue_adam(E* e, long long lo, long long hi, cudaStream_t s);
 void backward(E* e, bool conc) {
   const int B = e->B;
   char nm[64];
-  const bool trunk = !e->convs.empty();
-  float* dfeat = trunk ? e->conv_delta.back() : nullptr;
+  const bool trunk = !e->convs.empty() || e->lstm;
+  float* dfeat = trunk ? e->trunk_delta : nullptr;
   for (int l = e->depth - 1; l >= 0; --l) {
     // weight + bias gradients of both towers in one launch
     DenseWgradOp wg[2];
     for (int t = 0; t < e->ntow; ++t) {
       const Mat& w = e->tow[t][l];
       DenseWgradOp& op = wg[t]; op = DenseWgradOp{};
-      if (l == 0) { op.X = trunk ? (const void*)e->on.conv_out.back() : (const void*)e->xb; op.x_u8 = trunk ? 0 : (e->elem_bytes == 1); }
+      if (l == 0) { op.X = trunk ? (const void*)e->trunk_on : (const void*)e->xb; op.x_u8 = trunk ? 0 : (e->elem_bytes == 1); }
       else { op.X = e->on.tow_out[t][l - 1]; op.x_u8 = 0; }
       op.ldx = w.K; op.D = e->tow_delta[t][l]; op.ldd = w.N; op.dW = e->grad + w.off; op.M = w.K + 1; op.N = w.N; op.K = B;
       op.vecA = (w.K % 4 == 0) && al16(op.X); op.vecB = (w.N % 4 == 0);
       if (e->arena) {
         const bool raw_bytes = (l == 0 && !trunk && e->elem_bytes == 1);
-        op.Xs = l == 0 ? (trunk ? e->on.conv_out.back() : (raw_bytes ? nullptr : (const float*)e->xb)) : e->on.tow_out[t][l - 1];
+        op.Xs = l == 0 ? (trunk ? e->trunk_on : (raw_bytes ? nullptr : (const float*)e->xb)) : e->on.tow_out[t][l - 1];
         op.Ds = e->tow_delta[t][l]; op.ones = e->ones; op.a_single = 0; op.out_scale = 0.f;
       }
     }
     // TMA feed: the ones row of [x 1] is not a box of the activation matrix - the bias gradient (column sums of delta) goes to colsum_kernel
-    bool split_bias = e->arena && e->tc_tma && e->cfg.math_mode == DQN_MATH_3XTF32 && B >= 32;
+    // (measured: the extra column-sum launch costs more than the TMA feed gains on this operand, 27.1 + 12.7 us against 27.0 us for fc1 -
+    //  the weight gradients keep the cp.async feed with the ones row unless DQN_TC_TMA_WGRAD=1)
+    bool split_bias = e->arena && e->tc_tma && e->tc_tma_wgrad && e->cfg.math_mode == DQN_MATH_3XTF32 && B >= 32;
     for (int t = 0; t < e->ntow; ++t) { const Mat& w = e->tow[t][l]; split_bias = split_bias && wg[t].Xs && (w.K % 4 == 0) && w.K >= 64 && (w.N % 32 == 0) && w.N <= 1024; }
     if (split_bias) for (int t = 0; t < e->ntow; ++t) { wg[t].no_bias = 1; wg[t].M = e->tow[t][l].K; }
     if (e->ntow == 1) wg[1] = wg[0];
@@ -383,7 +406,7 @@ void backward(E* e, bool conc) {
       const Mat& w0 = e->tow[0][0]; const Mat& w1 = e->tow[e->ntow - 1][0];
       DenseDgradOp op{};
       op.D = e->tow_delta[0][0]; op.ldd = w0.N; op.W = e->theta + w0.off; op.dX = dfeat; op.ldx = w0.K;
-      op.Y = e->on.conv_out.back(); op.ldy = w0.K; op.act = e->convs.back().w.act; op.accumulate = 0; op.apply_act = 1;
+      op.Y = e->trunk_on; op.ldy = w0.K; op.act = e->trunk_act; op.accumulate = 0; op.apply_act = e->lstm ? 0 : 1;
       op.M = B; op.N = w0.K; op.K = w0.N; op.K1 = 0;
       if (e->ntow == 2) { op.K1 = w0.N; op.K = w0.N + w1.N; op.D2 = e->tow_delta[1][0]; op.ldd2 = w1.N; op.W2 = e->theta + w1.off; }
       op.vecA = (w0.N % 4 == 0) && (w1.N % 4 == 0); op.vecB = op.vecA;
@@ -400,7 +423,7 @@ void backward(E* e, bool conc) {
           const Mat& w = e->tow[t][0];
           DenseDgradOp o2{};
           o2.D = e->tow_delta[t][0]; o2.ldd = w.N; o2.W = e->theta + w.off; o2.dX = dfeat; o2.ldx = w.K;
-          o2.Y = e->on.conv_out.back(); o2.ldy = w.K; o2.act = e->convs.back().w.act; o2.accumulate = t > 0; o2.apply_act = (t == e->ntow - 1);
+          o2.Y = e->trunk_on; o2.ldy = w.K; o2.act = e->trunk_act; o2.accumulate = t > 0; o2.apply_act = (t == e->ntow - 1) && !e->lstm;
           o2.M = B; o2.N = w.K; o2.K = w.N; o2.vecA = o2.vecB = 0;
           snprintf(nm, sizeof nm, "dense1_dgrad_t%d", t);
           launch_igemm(e, nm, o2, o2, 1, false, 2.0 * B * o2.N * o2.K, 4.0 * ((double)B * o2.K + (double)o2.N * o2.K + 2.0 * B * o2.N));
@@ -409,7 +432,7 @@ void backward(E* e, bool conc) {
     }
   }
   e->towers_updated = false;
-  if (conc && trunk) {
+  if (conc && trunk && !e->lstm) {
     // Every Dense gradient is enqueued (weight gradients on lane 2) and so is the last reader of the Dense weights (the gradient into the
     // trunk, on the main lane): reduce that bucket and run its Adam update now, on the third lane, behind the conv backward.  The Dense
     // layers hold 98 % of the parameters (12.9 of 13.2 MB in config 3), so almost all of the optimizer's HBM traffic leaves the critical path.
@@ -417,6 +440,7 @@ void backward(E* e, bool conc) {
     if (e->cfg.world > 1) {
       ncclResult_t r = g_nccl.AllReduce(e->grad + e->tower_off, e->grad + e->tower_off, (size_t)(e->nint - e->tower_off), ncclFloat, ncclSum, e->comm, e->stream3);
       if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+      e->sm_reserve = e->nccl_ctas;                          // the conv backward below runs beside this reduction: leave its CTAs room
     }
     order_after(e, e->stream3, e->stream);
     enqueue_adam(e, e->tower_off, e->nint, e->stream3);
@@ -438,7 +462,9 @@ void backward(E* e, bool conc) {
     ConvWgradOp wg_tc = wg;                    // the tensor-core operand holds raw byte values: fold the 1/255 into its epilogue only
     wg_tc.out_scale = wg.a_single ? 1.0f / 255.0f : 0.f;
     // a bias row that would open a 128-row tile of its own (257 = 2 x 128 + 1 rows in the first layer) is summed by colsum_kernel instead
-    const bool split_bias = e->arena && (c.w.K % 128 == 0) && c.w.K <= 256 && (c.g.Cout % 4 == 0) && c.g.Cout <= 1024;   // worth a launch only when it saves >= 1/3 of the tiles
+    // ... and whenever the TMA feed takes the launch (the ones row of [x 1] is not an im2col box)
+    const bool tma_wgrad = e->arena && e->tc_tma && e->tc_tma_wgrad && e->cfg.math_mode == DQN_MATH_3XTF32 && l > 0 && (c.g.Cin % 32 == 0) && (c.g.Cout % 32 == 0) && c.g.Cout <= 1024;
+    const bool split_bias = tma_wgrad || (e->arena && (c.w.K % 128 == 0) && c.w.K <= 256 && (c.g.Cout % 4 == 0) && c.g.Cout <= 1024);   // worth a launch only when it saves >= 1/3 of the tiles
     if (split_bias) { wg_tc.M = c.w.K; wg_tc.no_bias = 1; }
     if (wg.a_single && e->a8) { wg_tc.a8 = 1; wg_tc.Xs = nullptr; }     // first layer: the byte batch itself is the operand
     {
@@ -502,7 +528,147 @@ void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for indices given by
 }
 size_t sample_smem(int B) { int HT = 1; while (HT < 4 * B) HT <<= 1; return 2 * HT * sizeof(int) + TREE_TOP * sizeof(float); }
 
+// ---- recurrent batch_train! (SOLVER:239-287) ---------------------------------------------------------------------------------------
+// x W_i^T + b for all time steps of a pass at once: rows x [in] -> rows x [4H]
+void lstm_xproj(E* e, const float* P, const float* X, int rows, float* out, const char* nm) {
+  DenseFwdOp op{};
+  op.X = X; op.ldx = e->lstm_in; op.x_u8 = 0; op.W = P + e->wi.off; op.C = out; op.ldc = 4 * e->Hh; op.act = DQN_ACT_IDENTITY;
+  op.M = rows; op.N = 4 * e->Hh; op.K = e->lstm_in; op.vecA = (e->lstm_in % 4 == 0) && al16(X); op.vecB = 1;
+  if (e->arena) { op.Xs = X; op.Ws = op.W; op.a_single = 0; }
+  const double fl = 2.0 * rows * op.N * op.K, by = 4.0 * ((double)rows * op.K + (double)(op.K + 1) * op.N + (double)rows * op.N);
+  if (!tc_dense_fwd(e, nm, &op, 1, fl, by)) launch_igemm(e, nm, op, op, 1, false, fl, by);
+}
+void lstm_step_launch(E* e, const LstmFwdArgs& a, int nch, const char* nm) {
+  Scope sc(e, nm, 2.0 * nch * a.B * 4.0 * a.H * a.H, 4.0 * nch * a.B * 10.0 * a.H);
+  dim3 grid((a.H + 31) / 32, (a.B + LSTM_TB - 1) / LSTM_TB, nch), block(32, LSTM_TB);
+  lstm_fwd_step_kernel<<<grid, block, LSTM_TB * a.H * sizeof(float), e->ls>>>(a);
+  CK(cudaGetLastError());
+}
+void lstm_broadcast(E* e, float* dst, const float* src, int rows) {
+  const long long n = (long long)rows * e->Hh;
+  lstm_broadcast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->ls>>>(dst, src, rows, e->Hh);
+  CK(cudaGetLastError());
+}
+
+void enqueue_step_recurrent(E* e, bool sample) {
+  const int TB = e->B, T = e->T, Bep = e->Bep, H = e->Hh, N4 = 4 * e->Hh;
+  const long long d = e->obs_elems, blk = (long long)Bep * H;
+  float* xs = reinterpret_cast<float*>(e->xb);                 // rows 0..TB-1: s (time-major), TB..2TB-1: s'
+  if (sample) {
+    Scope sc(e, "episode_sample", 0, Bep * 8.0 * 22);
+    sample_kernel<<<1, (Bep + 31) / 32 * 32, sample_smem(Bep), e->stream>>>(e->tree, e->P, Bep, e->cfg.seed, e->st, 0, 0, e->idx_d, nullptr, nullptr, nullptr, 0.f,
+                                                                         nullptr, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+  }
+  {
+    Scope sc(e, "episode_gather", 0, 2.0 * TB * d * 4 * 2);
+    episode_gather_kernel<<<dim3(T, Bep), 128, 0, e->stream>>>(e->idx_d, Bep, T, e->Lmax, d, e->cfg.seed, e->st, 0, 0, e->ep_len, e->ep_s, e->ep_sp, e->ep_a, e->ep_r,
+                                                               e->ep_done, xs, xs + (long long)TB * d, e->a_b, e->r_b, e->d_b, e->w_b, e->ep_start_d);
+    CK(cudaGetLastError());
+  }
+  const bool conc = e->use_streams && !e->profiling;
+  e->ev_next = 0;
+  // ---- target network over s' (lane 2) beside the online network over s and s' (two chains per launch)
+  if (conc) order_after(e, e->stream2, e->stream);
+  {
+    Lane lane(e, conc);
+    lstm_xproj(e, e->theta_t, xs + (long long)TB * d, TB, e->xproj_tg, "lstm_xproj_target");
+    lstm_broadcast(e, e->hs_tg, e->theta_t + e->h0_off, Bep);
+    lstm_broadcast(e, e->cs_tg + 2 * blk, e->theta_t + e->c0_off, Bep);
+    for (int t = 0; t < T; ++t) {
+      LstmFwdArgs a{};
+      a.xproj[0] = e->xproj_tg + (long long)t * Bep * N4; a.h_prev[0] = e->hs_tg + t * blk; a.h_out[0] = e->hs_tg + (t + 1) * blk;
+      a.c_prev[0] = t == 0 ? e->cs_tg + 2 * blk : e->cs_tg + ((t - 1) & 1) * blk; a.c_out[0] = e->cs_tg + (t & 1) * blk; a.gates[0] = nullptr;
+      a.Wh = e->theta_t + e->wh.off; a.B = Bep; a.H = H;
+      lstm_step_launch(e, a, 1, "lstm_step_target");
+    }
+    const Pass p_tg{e->theta_t, nullptr, 0, TB, &e->tg, "target", nullptr, nullptr, e->arena != nullptr, e->trunk_tg};
+    forward(e, &p_tg, 1);
+  }
+  lstm_xproj(e, e->theta, xs, 2 * TB, e->xproj_on, "lstm_xproj_online");
+  lstm_broadcast(e, e->hs_on, e->theta + e->h0_off, Bep);
+  lstm_broadcast(e, e->cs_on, e->theta + e->c0_off, Bep);
+  for (int t = 0; t < T; ++t) {
+    LstmFwdArgs a{};
+    // chain 0: the s pass (states kept for BPTT); chain 1: the s' pass.  Block 0 of hs_on / cs_on is state0, block t+1 the s pass after step t,
+    // block T+1+t the s' pass after step t
+    a.xproj[0] = e->xproj_on + (long long)t * Bep * N4; a.h_prev[0] = e->hs_on + t * blk; a.h_out[0] = e->hs_on + (t + 1) * blk;
+    a.c_prev[0] = e->cs_on + t * blk; a.c_out[0] = e->cs_on + (t + 1) * blk; a.gates[0] = e->gates_s + (long long)t * Bep * N4;
+    a.xproj[1] = e->xproj_on + ((long long)TB + (long long)t * Bep) * N4; a.h_prev[1] = t == 0 ? e->hs_on : e->hs_on + (T + t) * blk; a.h_out[1] = e->hs_on + (T + 1 + t) * blk;
+    a.c_prev[1] = t == 0 ? e->cs_on : e->cs_sp + ((t - 1) & 1) * blk; a.c_out[1] = e->cs_sp + (t & 1) * blk; a.gates[1] = nullptr;
+    a.Wh = e->theta + e->wh.off; a.B = Bep; a.H = H;
+    lstm_step_launch(e, a, 2, "lstm_step_online");
+  }
+  {
+    const Pass p_on{e->theta, nullptr, 0, 2 * TB, &e->on, "online", nullptr, nullptr, e->arena != nullptr, e->trunk_on};
+    forward(e, &p_on, 1);
+  }
+  if (conc) order_after(e, e->stream, e->stream2);
+  {
+    HeadArgs h{};
+    const int L = e->depth - 1;
+    if (e->cfg.dueling) { h.V_on = e->on.tow_out[0][L]; h.A_on = e->on.tow_out[1][L]; h.V_tg = e->tg.tow_out[0][L]; h.A_tg = e->tg.tow_out[1][L];
+                          h.dV = e->tow_delta[0][L]; h.dA = e->tow_delta[1][L]; h.act_v = e->tow[0][L].act; h.act_a = e->tow[1][L].act; }
+    else { h.A_on = e->on.tow_out[0][L]; h.A_tg = e->tg.tow_out[0][L]; h.dA = e->tow_delta[0][L]; h.act_a = e->tow[0][L].act; }
+    h.a_b = e->a_b; h.r_b = e->r_b; h.d_b = e->d_b; h.w_b = e->w_b;      // w = the trace mask: loss = (1/T) sum_t sum_i huber(m td) / B  (SOLVER:279-281)
+    h.q_s = e->q_s; h.q_sp_on = e->q_sp_on; h.q_sp_tg = e->q_sp_tg; h.y = e->y; h.best_a = e->best_a; h.td = e->td; h.newp = e->newp;
+    h.B = TB; h.nA = e->cfg.n_actions; h.dueling = e->cfg.dueling; h.double_q = e->cfg.double_q;
+    h.gamma = e->cfg.discount; h.alpha = e->cfg.alpha; h.eps = e->cfg.eps;
+    h.inv_world_B = 1.0f / ((float)TB * (float)e->cfg.world);
+    h.st = e->st;
+    Scope sc(e, "head_loss", 0, TB * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
+    head_loss_kernel<<<1, std::min(1024, (TB + 31) / 32 * 32), 0, e->stream>>>(h);
+    CK(cudaGetLastError());
+  }
+  backward(e, conc);                                           // the towers: weight gradients + the gradient into the hidden states (trunk_delta)
+  // ---- BPTT through the cell
+  {
+    Scope sc(e, "lstm_transpose", 0, 8.0 * H * N4);
+    transpose_kernel<<<dim3((N4 + 31) / 32, (H + 31) / 32), dim3(32, 8), 0, e->stream>>>(e->theta + e->wh.off, e->whT, H, N4);
+    CK(cudaGetLastError());
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    LstmBwdArgs a{};
+    a.dh_out = e->trunk_delta + t * blk; a.dg_next = t == T - 1 ? nullptr : e->dgates + (long long)(t + 1) * Bep * N4; a.WhT = e->whT;
+    a.gates = e->gates_s + (long long)t * Bep * N4; a.c_prev = e->cs_on + t * blk; a.c_cur = e->cs_on + (t + 1) * blk;
+    a.dc = e->dcell; a.dgates = e->dgates + (long long)t * Bep * N4; a.B = Bep; a.H = H; a.first = t == T - 1;
+    Scope sc(e, "lstm_bptt_step", 2.0 * Bep * 4.0 * H * H, 4.0 * Bep * 14.0 * H);
+    lstm_bwd_step_kernel<<<dim3((H + 31) / 32, (Bep + LSTM_TB - 1) / LSTM_TB), dim3(32, LSTM_TB), LSTM_TB * N4 * sizeof(float), e->stream>>>(a);
+    CK(cudaGetLastError());
+  }
+  if (conc) order_after(e, e->stream2, e->stream);
+  {
+    // dW_h = h_{t-1}^T dgates over all (t, b) rows; [dW_i; db] = [x 1]^T dgates: the same weight-gradient contraction the Dense layers use
+    Lane lane(e, conc);
+    DenseWgradOp wh{};
+    wh.X = e->hs_on; wh.ldx = H; wh.x_u8 = 0; wh.D = e->dgates; wh.ldd = N4; wh.dW = e->grad + e->wh.off; wh.M = H; wh.N = N4; wh.K = TB; wh.no_bias = 1;
+    wh.vecA = (H % 4 == 0); wh.vecB = 1;
+    if (e->arena) { wh.Xs = e->hs_on; wh.Ds = e->dgates; wh.ones = e->ones; wh.a_single = 0; wh.out_scale = 0.f; }
+    double fl = 2.0 * wh.M * wh.N * TB, by = 4.0 * ((double)TB * wh.M + (double)TB * wh.N + (double)wh.M * wh.N);
+    if (!tc_dense_wgrad(e, "lstm_wh_wgrad", &wh, 1, fl, by)) launch_igemm(e, "lstm_wh_wgrad", wh, wh, 1, true, fl, by);
+    DenseWgradOp wi{};
+    wi.X = xs; wi.ldx = e->lstm_in; wi.x_u8 = 0; wi.D = e->dgates; wi.ldd = N4; wi.dW = e->grad + e->wi.off; wi.M = e->lstm_in + 1; wi.N = N4; wi.K = TB;
+    wi.vecA = (e->lstm_in % 4 == 0) && al16(xs); wi.vecB = 1;
+    if (e->arena) { wi.Xs = xs; wi.Ds = e->dgates; wi.ones = e->ones; wi.a_single = 0; wi.out_scale = 0.f; }
+    fl = 2.0 * wi.M * wi.N * TB; by = 4.0 * ((double)TB * wi.M + (double)TB * wi.N + (double)wi.M * wi.N);
+    if (!tc_dense_wgrad(e, "lstm_wi_wgrad", &wi, 1, fl, by)) launch_igemm(e, "lstm_wi_wgrad", wi, wi, 1, true, fl, by);
+  }
+  if (conc) order_after(e, e->stream, e->stream2);
+  if (e->cfg.world > 1) {
+    Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
+    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)e->nint, ncclFloat, ncclSum, e->comm, e->stream);
+    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  enqueue_adam(e, 0, e->nint, e->stream);                      // state0 (h0, c0) has a zero gradient: Adam leaves it where it is
+  {
+    Scope sc(e, "end_of_step", 0, 12);
+    tree_update_kernel<<<1, 32, 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, 0, 0, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
+    CK(cudaGetLastError());
+  }
+}
+
 void enqueue_step(E* e, bool sample) {
+  if (e->lstm) { enqueue_step_recurrent(e, sample); return; }
   const int B = e->B;
   if (sample) {
     {
@@ -562,6 +728,7 @@ void enqueue_step(E* e, bool sample) {
     e->ls = keep;
   }
   backward(e, conc);
+  e->sm_reserve = 0;
   if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
     const bool split = conc && !e->convs.empty();          // the Dense bucket is already in flight on the NCCL lane
@@ -591,7 +758,8 @@ void enqueue_step(E* e, bool sample) {
 }
 
 void run_step(E* e, bool sample) {
-  if (e->curr_size < e->B) fail(DQN_ERR_STATE, "replay holds %lld transitions, batch_size is %d (PER:83 @assert r._curr_size >= r.batch_size)", e->curr_size, e->B);
+  const int need = e->lstm ? e->Bep : e->B;
+  if (e->curr_size < need) fail(DQN_ERR_STATE, "replay holds %lld %s, batch_size is %d (PER:83 / episode_replay.jl:73 @assert r._curr_size >= r.batch_size)", e->curr_size, e->lstm ? "episodes" : "transitions", need);
   cudaGraphExec_t& gx = sample ? e->graph_sample : e->graph_idx;
   if (e->cfg.use_graph && !e->profiling) {
     if (!gx) {
@@ -715,7 +883,16 @@ void build_topology(E* e) {
   for (; i < c.n_layers; ++i) {
     const dqn_layer_t& l = c.layers[i];
     if (l.kind == DQN_LAYER_FLATTEN) { if (!dense.empty()) fail(DQN_ERR_UNSUPPORTED, "flattenbatch after a Dense layer"); continue; }
-    if (l.kind != DQN_LAYER_DENSE) fail(DQN_ERR_UNSUPPORTED, "layer %d: only Conv* [flattenbatch] Dense+ chains are supported", i + 1);
+    if (l.kind == DQN_LAYER_LSTM) {
+      // Chain([flattenbatch,] LSTM(in, out), Dense...) - the recurrent models of the reference's tests (test/runtests.jl:116,133,150)
+      if (e->lstm || !dense.empty() || !e->convs.empty()) fail(DQN_ERR_UNSUPPORTED, "layer %d: one LSTM, directly on the (flattened) observation, is supported", i + 1);
+      if (l.in != e->feat) fail(DQN_ERR_INVALID, "LSTM expects %d inputs, gets %d", l.in, e->feat);
+      if (l.out < 1 || l.out % 4 != 0) fail(DQN_ERR_UNSUPPORTED, "LSTM width must be a multiple of 4");
+      if (c.obs_dtype != DQN_OBS_F32) fail(DQN_ERR_UNSUPPORTED, "recurrent engines store Float32 observations");
+      e->lstm = 1; e->lstm_in = l.in; e->Hh = l.out; e->feat = l.out;
+      continue;
+    }
+    if (l.kind != DQN_LAYER_DENSE) fail(DQN_ERR_UNSUPPORTED, "layer %d: only Conv* [flattenbatch] [LSTM] Dense+ chains are supported", i + 1);
     dense.push_back(l);
   }
   if (dense.empty()) fail(DQN_ERR_INVALID, "DeepQLearningError: the qnetwork provided is incompatible with dueling (no trailing Dense layer, DUEL:47-50)");
@@ -729,6 +906,13 @@ void build_topology(E* e) {
   long long off = 0;
   auto place = [&](Mat& m) { m.off = off; off += ((long long)(m.K + 1) * m.N + 3) / 4 * 4; };
   for (auto& cl : e->convs) place(cl.w);
+  if (e->lstm) {
+    // LSTMCell: W_i (4H, in) and W_h (4H, H) column-major = row-major [in][4H], [H][4H]; b rides as the bias row of W_i; state0 = (h0, c0)
+    e->wi = Mat{0, e->lstm_in, 4 * e->Hh, DQN_ACT_IDENTITY}; place(e->wi);
+    e->wh = Mat{0, e->Hh, 4 * e->Hh, DQN_ACT_IDENTITY}; place(e->wh);        // its bias row stays zero
+    e->h0_off = off; off += (e->Hh + 3) / 4 * 4;
+    e->c0_off = off; off += (e->Hh + 3) / 4 * 4;
+  }
   e->tower_off = off;
   for (int t = 0; t < e->ntow; ++t)
     for (int l = 0; l < e->depth; ++l) {
@@ -748,6 +932,14 @@ void build_topology(E* e) {
     }
     for (int co = 0; co < g.Cout; ++co) e->perm.push_back(cl.w.off + (long long)cl.w.K * g.Cout + co);
   }
+  if (e->lstm) {                               // Flux.params(LSTM): Wi, Wh, b, state0[1], state0[2]
+    const int N4 = 4 * e->Hh;
+    for (int k = 0; k < e->lstm_in; ++k) for (int n = 0; n < N4; ++n) e->perm.push_back(e->wi.off + (long long)k * N4 + n);
+    for (int k = 0; k < e->Hh; ++k) for (int n = 0; n < N4; ++n) e->perm.push_back(e->wh.off + (long long)k * N4 + n);
+    for (int n = 0; n < N4; ++n) e->perm.push_back(e->wi.off + (long long)e->lstm_in * N4 + n);
+    for (int j = 0; j < e->Hh; ++j) e->perm.push_back(e->h0_off + j);
+    for (int j = 0; j < e->Hh; ++j) e->perm.push_back(e->c0_off + j);
+  }
   const int HWt = H * W;
   for (int t = 0; t < e->ntow; ++t)
     for (int l = 0; l < e->depth; ++l) {
@@ -764,7 +956,14 @@ void build_topology(E* e) {
 
 void allocate(E* e) {
   const dqn_config_t& c = e->cfg;
-  const int B = e->B = c.batch_size;
+  if (e->lstm) {                               // the network sees trace_length * batch_size rows per pass
+    e->T = c.trace_length > 0 ? c.trace_length : 40;            // SOLVER:15
+    e->Lmax = c.max_episode_length > 0 ? c.max_episode_length : 100;   // SOLVER:21
+    e->Bep = c.batch_size;
+    if (e->T > e->Lmax) e->Lmax = e->T;
+    if ((long long)e->T * e->Bep > 65536) fail(DQN_ERR_UNSUPPORTED, "trace_length * batch_size above 65536");
+  }
+  const int B = e->B = e->lstm ? e->T * c.batch_size : c.batch_size;
   e->rows_on = std::max(2 * B, c.max_act_rows > 0 ? c.max_act_rows : 2 * B);
   e->elem_bytes = c.obs_dtype == DQN_OBS_U8 ? 1 : 4;
   e->obs_elems = (long long)c.obs_c * c.obs_h * c.obs_w;
@@ -774,14 +973,31 @@ void allocate(E* e) {
   e->cap = c.buffer_size;
   int P = 2; while (P < e->cap) P <<= 1;
   e->P = P;
-  e->store_s = dalloc<uint8_t>(e->cap * e->obs_row_bytes);
-  e->store_sp = dalloc<uint8_t>(e->cap * e->obs_row_bytes);
+  if (e->lstm) {
+    // EpisodeReplayBuffer: cap episodes of up to Lmax steps; the transition stores of the feed-forward path stay empty
+    const long long steps = e->cap * e->Lmax;
+    e->ep_s = dalloc<float>(steps * e->obs_elems); e->ep_sp = dalloc<float>(steps * e->obs_elems);
+    e->ep_a = dalloc<int>(steps); e->ep_r = dalloc<float>(steps); e->ep_done = dalloc<uint8_t>(steps); e->ep_len = dalloc<int>(e->cap);
+    e->ep_start_d = dalloc<int>(e->Bep);
+    const long long TB = B, H = e->Hh;
+    e->xproj_on = dalloc<float>(2 * TB * 4 * H); e->xproj_tg = dalloc<float>(TB * 4 * H);
+    e->hs_on = dalloc<float>((2LL * e->T + 1) * e->Bep * H); e->hs_tg = dalloc<float>((e->T + 1LL) * e->Bep * H);
+    e->cs_on = dalloc<float>((e->T + 1LL) * e->Bep * H); e->cs_sp = dalloc<float>(2LL * e->Bep * H); e->cs_tg = dalloc<float>(2LL * e->Bep * H);
+    e->gates_s = dalloc<float>(TB * 4 * H); e->dgates = dalloc<float>(TB * 4 * H); e->dcell = dalloc<float>((long long)e->Bep * H);
+    e->whT = dalloc<float>(4 * H * H);
+    e->act_rows = e->rows_on;
+    e->h_act = dalloc<float>((long long)e->act_rows * H); e->c_act = dalloc<float>((long long)e->act_rows * H);
+    e->trunk_on = e->hs_on + (long long)e->Bep * H; e->trunk_tg = e->hs_tg + (long long)e->Bep * H;
+    e->trunk_delta = dalloc<float>(TB * H); e->trunk_act = DQN_ACT_IDENTITY;
+  }
+  e->store_s = dalloc<uint8_t>(e->lstm ? 1 : e->cap * e->obs_row_bytes);
+  e->store_sp = dalloc<uint8_t>(e->lstm ? 1 : e->cap * e->obs_row_bytes);
   e->act = dalloc<int>(e->cap); e->rew = dalloc<float>(e->cap); e->done = dalloc<uint8_t>(e->cap);
   e->tree = dalloc<float>(2LL * P);
   e->st = dalloc<DevState>(1);
   DevState init{}; init.b1p = c.adam_beta1; init.b2p = c.adam_beta2;
   CK(cudaMemcpy(e->st, &init, sizeof init, cudaMemcpyHostToDevice));
-  e->idx_d = dalloc<long long>(B);
+  e->idx_d = dalloc<long long>(B);                            // (recurrent: the first Bep entries are the sampled episodes)
   e->xb = dalloc<uint8_t>((long long)e->rows_on * e->obs_row_bytes);
   e->a_b = dalloc<int>(B); e->r_b = dalloc<float>(B); e->d_b = dalloc<float>(B); e->w_b = dalloc<float>(B);
   for (auto& cl : e->convs) {
@@ -790,6 +1006,7 @@ void allocate(E* e) {
     e->tg.conv_out.push_back(dalloc<float>(B * per));
     e->conv_delta.push_back(dalloc<float>(B * per));
   }
+  if (!e->convs.empty()) { e->trunk_on = e->on.conv_out.back(); e->trunk_tg = e->tg.conv_out.back(); e->trunk_delta = e->conv_delta.back(); e->trunk_act = e->convs.back().w.act; }
   for (int t = 0; t < e->ntow; ++t)
     for (int l = 0; l < e->depth; ++l) {
       e->on.tow_out[t][l] = dalloc<float>((long long)e->rows_on * e->tow[t][l].N);
@@ -822,7 +1039,9 @@ void destroy(E* e) {
   tc_destroy(e);
   void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
                   e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws, e->ws2,
-                  e->stage, e->flush_buf, e->colsum_part, e->colsum_ticket};
+                  e->stage, e->flush_buf, e->colsum_part, e->colsum_ticket, e->ep_s, e->ep_sp, e->ep_r, e->ep_a, e->ep_len, e->ep_done, e->ep_start_d,
+                  e->xproj_on, e->xproj_tg, e->hs_on, e->hs_tg, e->cs_on, e->cs_sp, e->cs_tg, e->gates_s, e->dgates, e->dcell, e->whT, e->h_act, e->c_act,
+                  e->lstm ? e->trunk_delta : nullptr};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto p : e->on.conv_out) cudaFree(p);
   for (auto p : e->tg.conv_out) cudaFree(p);
@@ -879,6 +1098,7 @@ template <class T> void d2h(E* e, T* dst, const T* src, long long n) {
 
 // tensor-core path (tc_gemm.cuh) needs the engine definition
 #include "tc_gemm_impl.cuh"
+#include "conv1_tc.cuh"
 
 // =================================================================================================
 extern "C" {
@@ -945,8 +1165,19 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
       std::string why;
       if (!g_nccl.load(why)) fail(DQN_ERR_NCCL, "%s", why.c_str());
       ncclUniqueId id; memcpy(&id, cfg->nccl_id, DQN_NCCL_ID_BYTES);
+      // the collective's CTAs must find SMs beside the persistent tensor-core grids: bound NCCL's CTA count and keep that many SMs free
+      // while a reduction is in flight (tc_launch_v); DQN_NCCL_CTAS overrides, an NCCL_MAX_CTAS already in the environment wins
+      { const char* v = getenv("DQN_NCCL_CTAS"); e->nccl_ctas = v ? atoi(v) : 16; }
+      if (e->nccl_ctas > 0) { char buf[16]; snprintf(buf, sizeof buf, "%d", e->nccl_ctas); setenv("NCCL_MAX_CTAS", buf, 0); }
       ncclResult_t r = g_nccl.CommInitRank(&e->comm, cfg->world, id, cfg->rank);
       if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+      // NCCL sets its channels up lazily at the first collectives: do that here, not inside the first timed steps
+      for (int i = 0; i < 4; ++i) {
+        cudaStream_t cs = (i & 1) ? e->stream3 : e->stream;
+        r = g_nccl.AllReduce(e->grad, e->grad, (size_t)((i < 2) ? e->nint : std::max<long long>(e->tower_off, 4)), ncclFloat, ncclSum, e->comm, cs);
+        if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce (warm-up): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        CK(cudaStreamSynchronize(cs));
+      }
     }
     CK(cudaStreamSynchronize(e->stream));
     *out = e;
@@ -996,6 +1227,7 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
                    const float* td0, int64_t n) {
   return guard(h, [&] {
     if (n < 0 || (n > 0 && (!s || !a || !r || !sp || !done || !td0))) fail(DQN_ERR_INVALID, "null argument");
+    if (h->lstm) fail(DQN_ERR_UNSUPPORTED, "recurrent engine: transitions are added as whole episodes (dqn_episode_add)");
     // the reference's asserts (PER:66 td_err + eps > 0; a valid action index) are checked on the host arguments before anything is
     // enqueued: the call needs no device round trip, and a rejected batch leaves the buffer untouched.  (The ingest kernel raises the
     // same sticky flags for device-resident input, dqn_replay_add_device; they surface at the next dqn_train_step.)
@@ -1033,6 +1265,7 @@ int dqn_replay_add_device(dqn_engine_t* h, const void* s, const int32_t* a, cons
                           const float* td0, int64_t n) {
   return guard(h, [&] {
     if (n <= 0) return;
+    if (h->lstm) fail(DQN_ERR_UNSUPPORTED, "recurrent engine: transitions are added as whole episodes (dqn_episode_add)");
     ensure_stage(h, n * 8);
     ingest_device(h, (const uint8_t*)s, a, r, (const uint8_t*)sp, done, td0, n, (long long*)h->stage);
     check_dev_errors(h);
@@ -1157,7 +1390,7 @@ int dqn_train_step(dqn_engine_t* h, float* loss, float* grad_norm) {
 }
 int dqn_train_step_with_indices(dqn_engine_t* h, const int64_t* idx, float* loss, float* grad_norm) {
   return guard(h, [&] {
-    upload_idx(h, idx, h->B, h->idx_d, h->curr_size > 0 ? h->curr_size : 1);
+    upload_idx(h, idx, h->lstm ? h->Bep : h->B, h->idx_d, h->curr_size > 0 ? h->curr_size : 1);   // recurrent: batch_size episode indices
     run_step(h, false);
     fetch_scalars(h, loss, grad_norm);
   });
@@ -1169,6 +1402,33 @@ int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* 
   return guard(h, [&] {
     if (n < 0 || (n > 0 && (!obs || !q_out))) fail(DQN_ERR_INVALID, "null argument");
     const long long rb = h->obs_row_bytes; const int nA = h->cfg.n_actions; const int L = h->depth - 1;
+    if (h->lstm) {
+      // policy.qnetwork(obatch) with a Recur layer (POLICY:38-64): row i is lane i, its hidden state is carried from call to call until
+      // dqn_policy_reset (resetstate!).  Online network only: the target network never acts.
+      if (n > h->act_rows) fail(DQN_ERR_INVALID, "%lld rows, the acting state holds %d lanes (max_act_rows)", (long long)n, h->act_rows);
+      if (which != DQN_NET_ONLINE) fail(DQN_ERR_UNSUPPORTED, "recurrent engine: acting uses the online network");
+      if (n == 0) return;
+      const int H = h->Hh;
+      float* xs = reinterpret_cast<float*>(h->xb);
+      CK(cudaMemcpyAsync(xs, obs, n * rb, cudaMemcpyHostToDevice, h->stream));
+      lstm_xproj(h, h->theta, xs, (int)n, h->xproj_on, "lstm_xproj_act");
+      LstmFwdArgs a{};
+      a.xproj[0] = h->xproj_on; a.h_prev[0] = h->h_act; a.h_out[0] = h->hs_on; a.c_prev[0] = h->c_act; a.c_out[0] = h->c_act; a.gates[0] = nullptr;
+      a.Wh = h->theta + h->wh.off; a.B = (int)n; a.H = H;
+      lstm_step_launch(h, a, 1, "lstm_step_act");
+      CK(cudaMemcpyAsync(h->h_act, h->hs_on, sizeof(float) * n * H, cudaMemcpyDeviceToDevice, h->stream));
+      const Pass pa{h->theta, nullptr, 0, (int)n, &h->on, "act", nullptr, nullptr, false, h->hs_on};
+      forward(h, &pa, 1);
+      float* q = h->on.tow_out[h->ntow - 1][L];
+      if (h->cfg.dueling) {
+        q = (float*)h->ws;
+        dueling_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->on.tow_out[0][L], h->on.tow_out[1][L], (int)n, nA, q);
+        CK(cudaGetLastError());
+      }
+      CK(cudaMemcpyAsync(q_out, q, sizeof(float) * n * nA, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      return;
+    }
     const int chunk = h->rows_on;
     ensure_stage(h, (long long)chunk * rb);
     for (long long t0 = 0; t0 < n; t0 += chunk) {
@@ -1228,6 +1488,66 @@ int dqn_get_activation(dqn_engine_t* h, int stage, int tower, float* out, int64_
   });
 }
 
+// ---- EpisodeReplayBuffer (src/episode_replay.jl) -----------------------------------------------------------------------------------
+int dqn_episode_add(dqn_engine_t* h, const float* s, const int32_t* a, const float* r, const float* sp, const uint8_t* done, int64_t len) {
+  return guard(h, [&] {
+    if (!h->lstm) fail(DQN_ERR_UNSUPPORTED, "not a recurrent engine (no LSTM layer in the chain)");
+    if (len < 1 || len > h->Lmax || !s || !a || !r || !sp || !done) fail(DQN_ERR_INVALID, "episode length %lld outside 1..%d (max_episode_length) or null argument", (long long)len, h->Lmax);
+    for (long long t = 0; t < len; ++t) if (a[t] < 1 || a[t] > h->cfg.n_actions) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+    const long long slot = h->cursor, d = h->obs_elems, base = slot * h->Lmax;
+    CK(cudaMemcpyAsync(h->ep_s + base * d, s, sizeof(float) * len * d, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ep_sp + base * d, sp, sizeof(float) * len * d, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ep_a + base, a, sizeof(int) * len, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ep_r + base, r, sizeof(float) * len, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ep_done + base, done, len, cudaMemcpyHostToDevice, h->stream));
+    const int len32 = (int)len; const float one = 1.f;
+    CK(cudaMemcpyAsync(h->ep_len + slot, &len32, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tree + h->P + slot, &one, sizeof(float), cudaMemcpyHostToDevice, h->stream));   // uniform sampling = unit priorities
+    ensure_stage(h, 64);
+    CK(cudaMemcpyAsync(h->stage, &slot, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    tree_update_kernel<<<1, 32, 0, h->stream>>>(h->tree, h->P, (const long long*)h->stage, nullptr, 1, 0, h->st, 0, 1.0, 1.0, 0, nullptr);
+    CK(cudaGetLastError());
+    h->cursor = (h->cursor + 1) % h->cap;                      // r._idx = mod1(r._idx + 1, r.max_size)
+    h->curr_size = std::min(h->cap, h->curr_size + 1);
+    set_curr_size(h);
+    CK(cudaStreamSynchronize(h->stream));                      // the caller's arrays (and the stack words above) are free again
+  });
+}
+int dqn_episode_count(const dqn_engine_t* h, int64_t* curr_size, int64_t* cursor) {
+  if (!h || !h->lstm) return DQN_ERR_INVALID;
+  if (curr_size) *curr_size = h->curr_size;
+  if (cursor) *cursor = h->cursor;
+  return DQN_OK;
+}
+int dqn_episode_sample(dqn_engine_t* h, uint64_t call, int64_t* idx_out, int32_t* start_out) {
+  return guard(h, [&] {
+    if (!h->lstm) fail(DQN_ERR_UNSUPPORTED, "not a recurrent engine");
+    if (h->curr_size < h->Bep) fail(DQN_ERR_STATE, "replay holds %lld episodes, batch_size is %d (episode_replay.jl:73)", h->curr_size, h->Bep);
+    const int TB = h->B;
+    ensure_stage(h, h->Bep * 8);
+    sample_kernel<<<1, (h->Bep + 31) / 32 * 32, sample_smem(h->Bep), h->stream>>>(h->tree, h->P, h->Bep, h->cfg.seed, h->st, 1, call, (long long*)h->stage,
+                                                                                 nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+    float* xs = reinterpret_cast<float*>(h->xb);
+    episode_gather_kernel<<<dim3(h->T, h->Bep), 128, 0, h->stream>>>((const long long*)h->stage, h->Bep, h->T, h->Lmax, h->obs_elems, h->cfg.seed, h->st, 1, call, h->ep_len,
+                                                                     h->ep_s, h->ep_sp, h->ep_a, h->ep_r, h->ep_done, xs, xs + (long long)TB * h->obs_elems, h->a_b, h->r_b,
+                                                                     h->d_b, h->w_b, h->ep_start_d);
+    CK(cudaGetLastError());
+    if (idx_out) d2h(h, (long long*)idx_out, (const long long*)h->stage, h->Bep);
+    if (start_out) d2h(h, start_out, (const int*)h->ep_start_d, h->Bep);
+    check_dev_errors(h);
+  });
+}
+int dqn_policy_reset(dqn_engine_t* h) {
+  return guard(h, [&] {
+    if (!h->lstm) return;                                      // Flux.reset! is a no-op without recurrent layers
+    cudaStream_t keep = h->ls; h->ls = h->stream;
+    lstm_broadcast(h, h->h_act, h->theta + h->h0_off, h->act_rows);
+    lstm_broadcast(h, h->c_act, h->theta + h->c0_off, h->act_rows);
+    h->ls = keep;
+  });
+}
+
 int dqn_timer_start(dqn_engine_t* h) { return guard(h, [&] { CK(cudaEventRecord(h->t0, h->stream)); }); }
 int dqn_timer_stop(dqn_engine_t* h, float* ms) {
   return guard(h, [&] { CK(cudaEventRecord(h->t1, h->stream)); CK(cudaEventSynchronize(h->t1)); CK(cudaEventElapsedTime(ms, h->t0, h->t1)); });
@@ -1274,5 +1594,118 @@ void* dqn_stream(dqn_engine_t* h) { return h ? (void*)h->stream : nullptr; }
 
 int dqn_host_alloc(void** p, int64_t bytes) { return cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? DQN_OK : DQN_ERR_CUDA; }
 int dqn_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? DQN_OK : DQN_ERR_CUDA; }
+
+}  // extern "C"
+
+// =================================================================================================
+// Single-process data-parallel group: the reference's host is ONE Julia process (SURVEY 8b "Multi-GPU" row), so the boundary offers
+// ndev engines behind one handle.  Every engine keeps its own worker thread (its CUDA context, its NCCL rank): ncclCommInitRank must
+// be entered by all ranks at once, and a step's launches are issued concurrently, exactly as one process per GPU would.
+struct dqn_group {
+  struct Worker {
+    std::thread th; std::mutex mu; std::condition_variable cv;
+    std::function<int()> job; bool has_job = false, done = false, quit = false; int rc = 0;
+  };
+  std::vector<dqn_engine*> eng;
+  std::vector<Worker*> wk;
+  std::string err;
+  static void loop(Worker* w) {
+    for (;;) {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+      if (w->quit) return;
+      std::function<int()> j = w->job; w->has_job = false;
+      lk.unlock();
+      const int rc = j();
+      lk.lock();
+      w->rc = rc; w->done = true;
+      w->cv.notify_all();
+    }
+  }
+  // run f(rank) on every worker, wait for all; returns the first non-zero status
+  int run(const std::function<int(int)>& f) {
+    for (size_t r = 0; r < wk.size(); ++r) {
+      Worker* w = wk[r];
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->job = [f, r] { return f((int)r); }; w->has_job = true; w->done = false;
+      w->cv.notify_all();
+    }
+    int rc = 0;
+    for (size_t r = 0; r < wk.size(); ++r) {
+      Worker* w = wk[r];
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { return w->done; });
+      if (w->rc != 0 && rc == 0) { rc = w->rc; err = "rank " + std::to_string(r) + ": " + (eng[r] ? eng[r]->err : g_create_error); }
+    }
+    return rc;
+  }
+};
+
+extern "C" {
+
+int dqn_group_create(const dqn_config_t* cfg, int ndev, const int* devices, dqn_group_t** out) {
+  if (!cfg || !out || ndev < 1) { g_create_error = "null argument / ndev < 1"; return DQN_ERR_INVALID; }
+  *out = nullptr;
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) { g_create_error = "no CUDA device: libdqn_b200 has no CPU path"; return DQN_ERR_CUDA; }
+  uint8_t id[DQN_NCCL_ID_BYTES] = {0};
+  if (ndev > 1) { const int rc = dqn_nccl_unique_id(id); if (rc != DQN_OK) return rc; }
+  dqn_group* g = new dqn_group();
+  g->eng.assign(ndev, nullptr);
+  for (int r = 0; r < ndev; ++r) { auto* w = new dqn_group::Worker(); g->wk.push_back(w); w->th = std::thread(dqn_group::loop, w); }
+  std::vector<std::string> errs(ndev);
+  const int rc = g->run([&](int r) {
+    dqn_config_t c = *cfg;
+    c.device = devices ? devices[r] : r; c.rank = r; c.world = ndev;
+    c.seed = cfg->seed + (uint64_t)r;                           // every shard samples its own stream (bench.py: shard_seeds)
+    memcpy(c.nccl_id, id, DQN_NCCL_ID_BYTES);
+    const int rr = dqn_engine_create(&c, &g->eng[r]);
+    if (rr != DQN_OK) errs[r] = g_create_error;                // thread-local on the worker: carry it out
+    return rr;
+  });
+  if (rc != DQN_OK) {
+    for (int r = 0; r < ndev; ++r) if (!errs[r].empty()) { g_create_error = "rank " + std::to_string(r) + ": " + errs[r]; break; }
+    dqn_group_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return DQN_OK;
+}
+
+void dqn_group_destroy(dqn_group_t* g) {
+  if (!g) return;
+  g->run([&](int r) { if (g->eng[r]) { dqn_engine_destroy(g->eng[r]); g->eng[r] = nullptr; } return 0; });
+  for (auto* w : g->wk) {
+    { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; w->cv.notify_all(); }
+    w->th.join();
+    delete w;
+  }
+  delete g;
+}
+
+int dqn_group_size(const dqn_group_t* g) { return g ? (int)g->eng.size() : 0; }
+dqn_engine_t* dqn_group_engine(dqn_group_t* g, int rank) { return (g && rank >= 0 && rank < (int)g->eng.size()) ? g->eng[rank] : nullptr; }
+const char* dqn_group_last_error(const dqn_group_t* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+
+int dqn_group_set_params(dqn_group_t* g, int which, const float* flat, int64_t n) {
+  if (!g) return DQN_ERR_INVALID;
+  return g->run([&](int r) { return dqn_set_params(g->eng[r], which, flat, n); });
+}
+int dqn_group_sync_target(dqn_group_t* g) {
+  if (!g) return DQN_ERR_INVALID;
+  return g->run([&](int r) { return dqn_sync_target(g->eng[r]); });
+}
+// one data-parallel batch_train!: every shard samples its own batch, the gradient bucket is all-reduced, identical Adam everywhere.
+// loss = mean of the shards' losses (the loss of the combined batch of B * ndev samples), grad_norm = max|g| of the reduced gradient.
+int dqn_group_train_step(dqn_group_t* g, float* loss, float* grad_norm) {
+  if (!g) return DQN_ERR_INVALID;
+  std::vector<float> l(g->eng.size(), 0.f), gn(g->eng.size(), 0.f);
+  const int rc = g->run([&](int r) { return dqn_train_step(g->eng[r], &l[r], &gn[r]); });
+  if (rc != DQN_OK) return rc;
+  double s = 0; for (float v : l) s += v;
+  if (loss) *loss = (float)(s / l.size());
+  if (grad_norm) *grad_norm = gn[0];
+  return DQN_OK;
+}
 
 }  // extern "C"

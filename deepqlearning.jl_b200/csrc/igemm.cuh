@@ -206,6 +206,11 @@ struct DenseFwdOp {
     *reinterpret_cast<float4*>(C + (long long)m * ldc + n) = y;
     if (Cs) store_split4(Cs + (long long)m * ldc + n, lo_delta, y);
   }
+  // epilogue operand fetched ahead of the accumulator (tensor-core kernel): the bias of columns n..n+3
+  DQN_HD float4 epi_aux4(int, int n) const { return ldg4(W + (long long)K * N + n); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4& b) const {
+    *reinterpret_cast<float4*>(C + (long long)m * ldc + n) = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+  }
 };
 
 // Dense dgrad:  dX[m][n] (+)= sum_k D[m][k] W[n][k]  ;  times act'(Y[m][n]) when apply_act
@@ -273,6 +278,14 @@ struct DenseDgradOp {
     *o = v;
     if (dXs) store_split4(dXs + (long long)m * ldx + n, lo_delta, v);
   }
+  // epilogue operand fetched ahead of the accumulator: the stored layer output whose act' multiplies the gradient
+  DQN_HD float4 epi_aux4(int m, int n) const { return apply_act ? ldg4(Y + (long long)m * ldy + n) : make4(1.f, 1.f, 1.f, 1.f); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4& y) const {
+    float4* o = reinterpret_cast<float4*>(dX + (long long)m * ldx + n);
+    if (accumulate) { const float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
+    *o = v;
+  }
 };
 
 // Dense wgrad:  dW[m][n] = sum_k [X 1][k][m] D[k][n],  m in [0, Kin], k over the batch rows
@@ -322,6 +335,8 @@ struct DenseWgradOp {
     const float sc = oscale(m);
     *reinterpret_cast<float4*>(dW + (long long)m * N + n) = make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
   }
+  DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -403,6 +418,10 @@ struct ConvFwdOp {
     *reinterpret_cast<float4*>(Y + (long long)m * N + n) = y;
     if (Ys) store_split4(Ys + (long long)m * N + n, lo_delta, y);
   }
+  DQN_HD float4 epi_aux4(int, int n) const { return ldg4(W + (long long)K * N + n); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4& b) const {
+    *reinterpret_cast<float4*>(Y + (long long)m * N + n) = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+  }
 };
 
 // Conv wgrad: dW[m][co] = sum_pix [im2col(X) 1][pix][m] D[pix][co];  m = (kh,kw,ci) or the bias row
@@ -475,6 +494,8 @@ struct ConvWgradOp {
     const float sc = oscale(m);
     *reinterpret_cast<float4*>(dW + (long long)m * N + n) = make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
   }
+  DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
 };
 
 // Conv dgrad by stride-parity class (ph,pw): rows are the input pixels with ih%S==ph, iw%S==pw, and only
@@ -575,6 +596,11 @@ struct ConvDgradOp {
     }
     *reinterpret_cast<float4*>(dX + o) = v;
     if (dXs) store_split4(dXs + o, lo_delta, v);
+  }
+  DQN_HD float4 epi_aux4(int m, int n) const { return apply_act ? ldg4(Yprev + out_off(m, n)) : make4(1.f, 1.f, 1.f, 1.f); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4& y) const {
+    if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
+    *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
   }
 };
 

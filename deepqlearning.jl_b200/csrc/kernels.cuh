@@ -396,9 +396,9 @@ __device__ __forceinline__ void dueling_q(const float* V, const float* A, int ro
 
 __global__ void head_loss_kernel(HeadArgs h) {
   __shared__ float red[32];
-  const int i = threadIdx.x;
   float hub = 0.f;
-  if (i < h.B) {
+  // one thread per sample; the recurrent step has trace_length * batch_size rows (> 1024): threads stride over them
+  for (int i = threadIdx.x; i < h.B; i += blockDim.x) {
     float q[HEAD_MAX_ACTIONS];
     const int nA = h.nA;
     // s' online / target
@@ -422,7 +422,7 @@ __global__ void head_loss_kernel(HeadArgs h) {
     const float w = h.w_b[i];
     const float x = __fmul_rn(w, td);
     const float ax = fabsf(x), quad = fminf(ax, 1.f), lin = __fsub_rn(ax, quad);
-    hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), lin);
+    hub += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), lin);
     const float g = __fmul_rn(__fmul_rn(w, fminf(fmaxf(x, -1.f), 1.f)), h.inv_world_B);
     if (h.dueling) {
       h.dV[i] = g * act_deriv(h.V_on[i], h.act_v);

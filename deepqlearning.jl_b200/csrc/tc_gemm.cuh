@@ -5,6 +5,7 @@
 #include "igemm.cuh"
 struct dqn_engine;
 namespace {
+bool tc_conv1_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, double flops, double bytes);
 bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp* ops, int nops, double flops, double bytes);
 bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int nops, double flops, double bytes);
 bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double flops, double bytes);

@@ -24,16 +24,24 @@
 // TC_EXP_NOLOAD / NOFIN / NOMMA / NOEPI (ablations: timing only, results are garbage), TC_CP_CG, TC_WAIT_IMPL, TC_MAX_STAGES.
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 #include <cuda.h>          // CUtensorMap (type only: the encode functions are fetched through cudaGetDriverEntryPoint, no libcuda link)
 #ifndef TC_CP_CG
 #define TC_CP_CA 1
+#endif
+// TMA feed: 1 = both operands by TMA (default), 0 = A by TMA, B by two cp.async warps.  The TMA unit is row-rate bound (~4.2 cycles per
+// box row whatever its width, scripts/ubench/tma_probe.cu), so the 64 B rows of a stage cost it another 270 cycles - but measured in
+// the kernel the all-TMA feed is the faster one (conv2 forward shape 32.0 vs 35.6 us): the stage is paced by the converter / MMA
+// chain, not by the TMA unit, and the two copier warps compete for the issue slots of that chain.
+#ifndef TC_TMA_B
+#define TC_TMA_B 1
 #endif
 
 namespace tc {
 
 #ifdef TC_TRACE
-__device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (producer warp 0 and the MMA warp): tuning aid of the selftest
-#define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 1000) tc_trace[(st) * 8 + (ev)] = clock64(); } while (0)
+__device__ long long tc_trace[16384];    // per-stage timestamps of CTA 0 (producer warp 0, one converter warp, MMA warp 0): tuning aid of the selftest
+#define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 1000) tc_trace[(st) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define TRACE(st, ev) do { } while (0)
 #endif
@@ -46,14 +54,19 @@ __device__ long long tc_trace[8192];     // per-stage timestamps of CTA 0 (produ
 //   B MN-major  (weights [K][N] / deltas [K][N]): 3-D box {32 fp32 of n, 32 k rows, BN/32 atoms of n}, SWIZZLE_128B_ATOM_32B -
 //               exactly the SWIZZLE_128B_BASE32B UMMA layout the cp.async loaders write by hand
 //   B K-major   (dgrad: W[n][k]): 2-D box 32 fp32 (k) x BN rows (n), SWIZZLE_128B (UMMA layout type 2, SBO 1024, 32 bytes per k step)
+//   conv dgrad  per stride-parity class a stride-1 correlation over the delta tensor: im2col map with negative lower corner (zero-filled
+//               halo), tap = the 16-bit offsets; B = one tap's [Cin][Cout] slab of the weights through a 3-D map {Cout, Cin, tap}
+//   conv wgrad  A = x^T: four im2col boxes of 32 pixels x 32 channels per stage (one per 32 rows of the m tile), no swizzle
 // Out-of-range rows / columns are zero-filled by the TMA unit: no edge-tile code in the producer.
-enum { TMA_DENSE_FWD = 0, TMA_DENSE_DGRAD = 1, TMA_DENSE_WGRAD = 2, TMA_CONV_FWD = 3 };
+enum { TMA_DENSE_FWD = 0, TMA_DENSE_DGRAD = 1, TMA_DENSE_WGRAD = 2, TMA_CONV_FWD = 3, TMA_CONV_DGRAD = 4, TMA_CONV_WGRAD = 5 };
 struct TmaMaps {
   CUtensorMap a[4];              // per operand set; dgrad: per k segment (tower)
   CUtensorMap b[4];
   int kind;                      // TMA_*
   int seg_k;                     // dgrad: k where the second segment starts (0: one segment)
-  int cin, kw, stride, oh, ow;   // conv forward: decode of (pixel, k stage) into im2col coordinates
+  int cin, kw, stride, oh, ow;   // conv: decode of (pixel, k stage) into im2col coordinates (dgrad: cin = Cout of the layer, the k channels)
+  int ntaps;                     // conv wgrad: KH * KW
+  int a_slabs;                   // 1: MN-major A staged as four [32 k][32 m] slabs (conv wgrad) instead of one dense [32 k][128 m] tile
 };
 
 constexpr int BM = 128;          // UMMA M
@@ -69,6 +82,7 @@ constexpr int BK = 32;           // fp32 elements per stage along K (4 UMMA k-st
 //                            instruction every ~75 cycles, three streams keep the tensor core fed.  Warp 31 idles (completes the warpgroup).
 constexpr int LOAD_WARPS = 8;
 constexpr int LOADERS = 32 * LOAD_WARPS;
+constexpr int TMA_BLD = 64;      // TMA feed: threads (warps 1-2) that copy the B stage with cp.async while warp 0 drives the TMA unit for A
 constexpr int NGRP = 2;
 constexpr int GW = 8;            // warps per converter group
 constexpr int CONV_WARPS = GW * NGRP;
@@ -123,14 +137,15 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
   using SA = AStage<A_MN>;
   using SA8 = AStage8<A_MN>;
   static_assert(!(TMA && A8), "byte operands use the cp.async feed");
-  static_assert(!TMA || BN % 32 == 0, "TMA B boxes come in atoms of 32 columns");
+  static constexpr bool TMA_B = TMA && (TC_TMA_B != 0);
+  static_assert(!TMA_B || BN % 32 == 0, "TMA B boxes come in atoms of 32 columns");
   static constexpr int A_BYTES = TMA ? BM * BK * 4 : ((A8 ? SA8::BYTES : SA::BYTES) + 1023) / 1024 * 1024;    // TMA boxes are dense (hardware swizzle, no padding)
-  static constexpr int B_PLANE = TMA ? BN * BK * 4 : TB::BYTES;
+  static constexpr int B_PLANE = TMA_B ? BN * BK * 4 : TB::BYTES;
   static constexpr int B_BYTES = (B_PLANE + 1023) / 1024 * 1024;       // every plane starts 1024-byte aligned (swizzled tiles need it)
   // UMMA descriptor of the B planes: MN-major is the same layout in both feeds; K-major is the padded no-swizzle layout for cp.async
   // and SWIZZLE_128B rows for TMA
-  static constexpr int B_LBO = (TMA && !B_MN) ? 16 : TB::LBO, B_SBO = (TMA && !B_MN) ? 1024 : TB::SBO, B_KSTEP = (TMA && !B_MN) ? 32 : TB::KSTEP;
-  static constexpr uint32_t B_LTYPE = B_MN ? 1u : (TMA ? 2u : 0u);     // 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B, 0 = none
+  static constexpr int B_LBO = (TMA_B && !B_MN) ? 16 : TB::LBO, B_SBO = (TMA_B && !B_MN) ? 1024 : TB::SBO, B_KSTEP = (TMA_B && !B_MN) ? 32 : TB::KSTEP;
+  static constexpr uint32_t B_LTYPE = B_MN ? 1u : (TMA_B ? 2u : 0u);   // 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B, 0 = none
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;            // A staging, B_hi(raw), B_lo
   static constexpr int TAIL = 1024 + 512;                              // alignment slack + barriers / tmem address
 #ifndef TC_MAX_STAGES
@@ -140,10 +155,15 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
   static constexpr int STAGES = (FIT > TC_MAX_STAGES ? TC_MAX_STAGES : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
   static_assert(STAGES <= 16, "barrier arrays");
   static_assert(STAGES >= 6, "ring too shallow");
-  static constexpr int NACC = R + 2;                                   // R interleaved main accumulators + one per correction product
+  // cp.async feed: R interleaved main accumulators + one per correction product, three issuing warps (one per product).
+  // TMA feed (its idle loader warps become issuers): six issuing warps = product x k-step parity, each with an accumulator of its own
+  // (R = 2 interleave for all three products) - a thread can issue one tcgen05 instruction per ~75 cycles, so four MMAs + commit per
+  // stage and warp (375 cycles + the barrier wait) left the tensor pipe idle a third of the time (stage trace)
+  static constexpr int NMMA_W = TMA ? 6 : 3;
+  static constexpr int NACC = TMA ? 6 : R + 2;
   static constexpr int ACC_COLS = NBUF * NACC * BN;
   static constexpr int AST_FIT = (512 - ACC_COLS) / 64;
-  static constexpr int AST = 4;                                        // A-operand stages resident in TMEM
+  static constexpr int AST = TMA ? 2 : 4;                              // A-operand stages resident in TMEM
   static_assert(AST_FIT >= AST && AST % NGRP == 0, "TMEM columns");
   static constexpr int SMEM = STAGES * STAGE_BYTES + TAIL;
   static_assert(SMEM <= 227 * 1024, "shared memory");
@@ -342,8 +362,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   const bool a_lo = !opa.a_single;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, TMA ? 1 : LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, NMMA); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, NMMA); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, TMA ? (L::TMA_B ? 1 : 1 + TMA_BLD) : LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, L::NMMA_W); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, L::NMMA_W); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP0) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -417,11 +437,14 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   };
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
-  if (TMA && warp < LOAD_WARPS) {
+  // TMA feed: warps 4 and 5 (idle loaders) are MMA issuers 4 and 5; they run the issuer code at the end of this chain
+  const bool tma_issuer = TMA && (warp == 4 || warp == 5);
+  if (TMA && warp < LOAD_WARPS && !tma_issuer) {
     reg_dec<56>();
-    // ================= TMA producer: one thread, two instructions per stage; the other loader warps have nothing to do =================
+    // ================= TMA producer (warp 0: one thread, one or two instructions per stage) + B copiers (warps 1-2, cp.async) =================
     if (warp == 0) {
       int is = 0; uint32_t iph = 0;
+      int ptr_ = 0; (void)ptr_;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         Op op; int m0, n0, zs, kt0, nk;
         if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
@@ -431,31 +454,101 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         for (int it = 0; it < nk; ++it) {
           const int k0 = (kt0 + it) * BK;
           const uint32_t a_st = sbase + is * L::STAGE_BYTES, b_hi = a_st + L::A_BYTES, bar = bar_landed + 8 * is;
+          TRACE(ptr_, 0);
           mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
+          TRACE(ptr_, 1);
           if (lane == 0) {
-            mbar_expect_tx(bar, (uint32_t)(BM * BK * 4 + BN * BK * 4));
+            uint32_t a_bytes = BM * BK * 4;
+            if (tmaps.kind == TMA_CONV_WGRAD) {                  // only the 32-row slabs that lie inside the filter are loaded
+              int live = 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) live += ((m0 + 32 * j) / tmaps.cin < tmaps.ntaps) ? 1 : 0;
+              a_bytes = (uint32_t)(live * 4096);
+            }
+            mbar_expect_tx(bar, a_bytes + (uint32_t)(L::TMA_B ? BN * BK * 4 : 0));
             if (tmaps.kind == TMA_CONV_FWD) {                    // k stage -> (tap row, tap column, first channel); one tap's 32 channels per stage
+              // im2col-mode coordinates (measured, scripts/ubench/tma_probe.cu): {c, w, h, n} is the first base pixel in input coordinates
+              // (ow*S, oh*S), the box walks base pixels by the map's traversal strides, wraps rows and images, zero-fills past the batch;
+              // the 16-bit offsets are the filter tap
               const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;
               tma_load_im2col_4d(a_st, &tmaps.a[zi], c0, pw * tmaps.stride, ph_ * tmaps.stride, pn, tw, th, bar);
-              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             } else if (tmaps.kind == TMA_DENSE_FWD) {
               tma_load_2d(a_st, &tmaps.a[zi], k0, m0, bar);
-              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             } else if (tmaps.kind == TMA_DENSE_WGRAD) {
               tma_load_2d(a_st, &tmaps.a[zi], m0, k0, bar);
-              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
-            } else {                                             // dgrad: k segments (towers) have their own delta / weight matrices
+              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+            } else if (tmaps.kind == TMA_DENSE_DGRAD) {          // k segments (towers) have their own delta / weight matrices
               const int sg = (tmaps.seg_k > 0 && k0 >= tmaps.seg_k) ? 1 : 0, kk = k0 - sg * tmaps.seg_k;
               tma_load_2d(a_st, &tmaps.a[sg], kk, m0, bar);
-              tma_load_2d(b_hi, &tmaps.b[sg], kk, n0, bar);
+              if (L::TMA_B) tma_load_2d(b_hi, &tmaps.b[sg], kk, n0, bar);
+            } else if (tmaps.kind == TMA_CONV_DGRAD) {
+              if constexpr (Op::Z_IS_CLASS) {
+                // class (ph, pw): row m = input pixel (n, a, b) of the class, k = (th, tw, co): source delta[n][a - th][b - tw][co].
+                // Base pixel = (a - (TH-1), b - (TW-1)) in the zero-padded delta tensor, tap offset = (TH-1-th, TW-1-tw).
+                const int zc = zs / nsplit;
+                const int bq = m0 % op.BW, q = m0 / op.BW, aq = q % op.AH, nq = q / op.AH;
+                const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / op.TW, tw = tap - th * op.TW;
+                tma_load_im2col_4d(a_st, &tmaps.a[zc], c0, bq - (op.TW - 1), aq - (op.TH - 1), nq, op.TW - 1 - tw, op.TH - 1 - th, bar);
+                const int khh = op.ph + th * tmaps.stride, kww = op.pw + tw * tmaps.stride;
+                tma_load_3d(b_hi, &tmaps.b[0], c0, n0, khh * tmaps.kw + kww, bar);
+              }
+            } else {                                             // conv wgrad: k = output pixel, m = (tap, channel)
+              const int pw2 = k0 % tmaps.ow, q2 = k0 / tmaps.ow, ph2 = q2 % tmaps.oh, pn2 = q2 / tmaps.oh;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int mm = m0 + 32 * j, tap = mm / tmaps.cin, c0 = mm - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;
+                // rows past the last tap are never stored: leave their slab alone (and out of the byte count)
+                if (tap < tmaps.ntaps) tma_load_im2col_4d(a_st + j * 4096, &tmaps.a[zi], c0, pw2 * tmaps.stride, ph2 * tmaps.stride, pn2, tw, th, bar);
+              }
+              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             }
           }
           __syncwarp();
+          TRACE(ptr_, 2);
+          ++ptr_;
           if (++is == STAGES) { is = 0; iph ^= 1; }
         }
       }
+    } else if (!L::TMA_B && warp <= TMA_BLD / 32) {
+      // B stage: BN x 32 fp32 = BN * 8 chunks of 16 bytes over 64 threads, into the UMMA layout (same chunk map as the cp.async feed)
+      constexpr int B_PER = B_CH / TMA_BLD;
+      const int btid = tid - 32;
+      uint32_t b_off[B_PER]; int b_kk[B_PER], b_n[B_PER];
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const int e = btid + i * TMA_BLD;
+        if (B_MN) { const int g = e % (BN / 4); b_kk[i] = e / (BN / 4); b_n[i] = g * 4; b_off[i] = (g >> 3) * TB::LBO + b_kk[i] * 128 + (((g & 7) ^ ((b_kk[i] & 3) << 1)) * 16); }
+        else      { const int r = e >> 3; b_kk[i] = (e & 7) * 4; b_n[i] = r; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
+      }
+      int is = 0; uint32_t iph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        Op op; int m0, n0, zs, kt0, nk;
+        if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+        for (int it = 0; it < nk; ++it) {
+          const int k0 = (kt0 + it) * BK;
+          const uint32_t b_hi = sbase + is * L::STAGE_BYTES + L::A_BYTES;
+          KCtx kc; kc.off = 0; kc.offb = 0; kc.t0 = kc.t1 = kc.t2 = 0;
+          if (!B_MN) kc = op.prepK(k0 + (btid & 7) * 4);         // K-major B: this thread's k chunk is the same for all of its rows
+          mbar_wait(bar_empty + 8 * is, iph ^ 1);
+          if (op.interiorB(n0, k0, BN, BK)) {
+#pragma unroll
+            for (int i = 0; i < B_PER; ++i) cp_async16_full(b_hi + b_off[i], op.ptrB_u(kc, k0 + b_kk[i], n0 + b_n[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < B_PER; ++i) {
+              const float* p = op.ptrB(kc, k0 + b_kk[i], n0 + b_n[i]);
+              cp_async16(b_hi + b_off[i], p ? p : zero_src, p ? 16u : 0u);
+            }
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_landed + 8 * is) : "memory");
+          if (++is == STAGES) { is = 0; iph ^= 1; }
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
-  } else if (warp < LOAD_WARPS) {
+  } else if (!TMA && warp < LOAD_WARPS) {
     reg_dec<56>();
     // ================= loaders: chunk addresses + cp.async into ring slot, completion signalled on landed[slot] =================
     constexpr int A_PER = BM * (BK / 4) / LOADERS;             // 8 chunks of A per thread per stage
@@ -550,7 +643,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp < EPI_WARP0) {
+  } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
     // ================= converters: group g owns the stages with (stage index % NGRP) == g =================
     //   A: shared-memory staging tile -> registers (one row per thread) -> TMEM: the raw words are the hi plane (the tensor core reads
     //      the top 19 bits: hi = trunc_tf32(x)), lo = rna_tf32(x - hi) goes to the lo columns;
@@ -566,15 +659,15 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       const int e = gtid + i * GT;
-      if (TMA) b_off[i] = e * 16;                               // dense planes: lo(chunk) goes to the same offset of the lo plane, whatever the swizzle
+      if (L::TMA_B) b_off[i] = e * 16;                          // dense planes: lo(chunk) goes to the same offset of the lo plane, whatever the swizzle
       else if (B_MN) { const int g = e % (BN / 4), kk = e / (BN / 4); b_off[i] = (g >> 3) * TB::LBO + kk * 128 + (((g & 7) ^ ((kk & 3) << 1)) * 16); }
       else      { const int r = e >> 3; b_off[i] = (e & 7) * TB::LBO + (r >> 3) * TB::SBO + (r & 7) * 16; }
     }
     // TMA staging tiles: K-major = 128-byte rows under SWIZZLE_128B (chunk j of row r at j ^ (r & 7)), MN-major = dense [32 k][128 m]
-    const uint32_t a_rd = TMA ? (A_MN ? (uint32_t)(kh * 16 * (BM * 4) + row * 4) : (uint32_t)(row * 128))
+    const uint32_t a_rd = TMA ? (A_MN ? (tmaps.a_slabs ? (uint32_t)(q4 * 4096 + kh * 16 * 128 + lane * 4) : (uint32_t)(kh * 16 * (BM * 4) + row * 4)) : (uint32_t)(row * 128))
                         : A8 ? (A_MN ? (uint32_t)(kh * 16 * SA8::PITCH + row) : (uint32_t)(row * SA8::PITCH + kh * 16))
                              : (A_MN ? (uint32_t)(kh * 16 * SA::PITCH + row * 4) : (uint32_t)(row * SA::PITCH + kh * 64));
-    constexpr uint32_t A_KPITCH = TMA ? (uint32_t)(BM * 4) : (uint32_t)SA::PITCH;   // MN-major: bytes between k rows
+    const uint32_t A_KPITCH = TMA ? (tmaps.a_slabs ? 128u : (uint32_t)(BM * 4)) : (uint32_t)SA::PITCH;   // MN-major: bytes between k rows
     const uint32_t a_tm = tmem + ((uint32_t)(q4 * 32) << 16) + ACOL0 + (uint32_t)(kh * 16);
     int gg = 0;                                                // global stage counter (all tiles)
     int s = grp; uint32_t ph = 0;                              // ring slot / phase of this group's next stage
@@ -616,9 +709,20 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
             v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y); v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
           }
         }
-        float4 vb[B_PER];
+        // everything that does not touch TMEM happens BEFORE the wait for the TMEM slot (the gate that the MMAs of stage gg - AST open):
+        // the B lo plane goes straight into this stage's own shared-memory slot, the A lo words are computed into registers
+        {
+          float4 vb[B_PER];
 #pragma unroll
-        for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+          for (int i = 0; i < B_PER; ++i) vb[i] = lds128(b_hi + b_off[i]);
+#pragma unroll
+          for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+        }
+        uint32_t vl[16];
+        if (a_lo) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vl[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
+        }
 #endif
         // TMEM slot `as` was read by the MMAs of stage gg - AST: their retirement is a completed phase of that stage's empty barrier
         if (gg >= AST) {
@@ -630,13 +734,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #ifndef TC_EXP_NOFIN
         const uint32_t ta = a_tm + (uint32_t)(as * 64);
         tmem_st16(ta, v);
-        if (a_lo) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(lo_of_trunc(__uint_as_float(v[i])));
-          tmem_st16(ta + 32, v);
-        }
-#pragma unroll
-        for (int i = 0; i < B_PER; ++i) sts128(b_lo_s + b_off[i], lo_of_trunc4(vb[i]));
+        if (a_lo) tmem_st16(ta + 32, vl);
         if (gw == 0) TRACE(gg, 5);
         tmem_st_wait();
         if (gw == 0) TRACE(gg, 6);
@@ -650,52 +748,71 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         as += NGRP; if (as >= AST) as -= AST;
       }
     }
-  } else if (warp < MMA_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < MMA_WARP0) {
     reg_inc<96>();
     // ================= epilogue: TMEM -> registers -> bias/activation or act' -> 16-byte stores =================
     const int q4 = warp & 3;                                   // TMEM lane quarter this warp may read
     constexpr int EPI_UNROLL = TC_EPI_UNROLL;                  // column chunks in flight: their bias / act' loads overlap
     int buf = 0; uint32_t aph = 0;
+    int etr = 0; (void)etr;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       Op op; int m0, n0, zs, kt0, nk;
       if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
-      mbar_wait(bar_accf + 8 * buf, aph);
-      tc_fence_after();
       const int m = m0 + q4 * 32 + lane;
       const bool tail = tail_s > 1 && t >= tail_t0;
       const bool part = nsplit > 1 || tail;                    // partial sums to the workspace
       const long long mrel = tail ? m - tail_t0 * BM : m;      // ... rows of the tail tiles are stored relative to the first of them
       const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NACC * BN);
+      // The epilogue's own operands (bias of the columns / stored output whose act' multiplies the gradient) are fetched together, in
+      // the shadow of the chunk's TMEM loads: issued inside store4 they sat behind the TMEM wait and behind each other, four exposed
+      // round trips per chunk - 6800 cycles per tile in the stage trace, a third of the kernel.  (Registers: the launch bound of 1024
+      // threads caps ptxas at 64 per thread, so only the chunk in flight is held.)
+      const bool vec = m < op.M && !part && op.can_store4();
+      if (q4 == 0) TRACE(etr, 12);
+      mbar_wait(bar_accf + 8 * buf, aph);
+      if (q4 == 0) TRACE(etr, 13);
+      tc_fence_after();
 #ifdef TC_EXP_NOEPI
       if (m0 < 0)
 #endif
 #pragma unroll EPI_UNROLL
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
+        float4 aux[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) aux[j] = make4(0.f, 0.f, 0.f, 0.f);
         if (nk > 0) {
           uint32_t q[NACC - 1][16];
           tmem_ld16_nowait(tb + c0, r);
 #pragma unroll
           for (int a = 1; a < NACC; ++a) {
-            if (a == R && !a_lo) continue;                       // accumulator R belongs to A_lo B_hi: never written for a single-plane A
+            if (!TMA && a == R && !a_lo) continue;               // accumulator R belongs to A_lo B_hi: never written for a single-plane A
             tmem_ld16_nowait(tb + a * BN + c0, q[a - 1]);
+          }
+          if (vec && n0 + c0 + 15 < op.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
-            if (a == R && !a_lo) continue;
+            if (!TMA && a == R && !a_lo) continue;
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[a - 1][j])));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = 0u;
+          if (vec && n0 + c0 + 15 < op.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
+          }
         }
         if (m < op.M) {
-          if (!part && op.can_store4() && n0 + c0 + 15 < op.N) {
+          if (vec && n0 + c0 + 15 < op.N) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              op.store4(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+              op.store4x(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), aux[j >> 2]);
           } else if (part && (op.N & 3) == 0 && n0 + c0 + 15 < op.N) {
             float4* wp = reinterpret_cast<float4*>(ws + (long long)zs * ws_stride + mrel * op.N + n0 + c0);
 #pragma unroll
@@ -716,15 +833,23 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       tc_fence_before();                                       // this warp's tcgen05.ld are complete (wait::ld) and ordered before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + 8 * buf);          // accumulator set free again
+      if (q4 == 0) TRACE(etr, 14);
+      ++etr;
       if (++buf == NBUF) { buf = 0; aph ^= 1; }
     }
-  } else if (warp >= MMA_WARP0 + NMMA) {
+  } else if (!TMA && warp >= MMA_WARP0 + NMMA) {
     reg_dec<40>();                                             // idle warp that completes the MMA warpgroup
   } else {
-    reg_dec<40>();
+    if (tma_issuer) reg_dec<56>(); else reg_dec<40>();         // (warps 4-5 share a warpgroup with the producer warps: same setmaxnreg)
     // ================= MMA issuers =================
+    // cp.async feed: three warps, role = product (0: A_hi B_hi over R interleaved accumulators, 1: A_lo B_hi, 2: A_hi B_lo), four MMAs each.
+    // TMA feed: six warps, role = product + 3 * (k-step parity): two MMAs each per stage, every role its own accumulator.
     constexpr uint32_t idesc = make_idesc2(BM, BN, false, B_MN);   // A comes from TMEM: K-major by construction
-    const int role = warp - MMA_WARP0;                         // 0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo
+    const int role = tma_issuer ? warp : warp - MMA_WARP0;     // TMA feed: warps 28-31 -> 0-3, warps 4-5 -> 4-5
+    const int prod = TMA ? role % 3 : role, half = TMA ? role / 3 : 0;
+    const uint64_t dbase = make_desc(0, L::B_LBO, L::B_SBO, L::B_LTYPE) + (uint64_t)((sbase + L::A_BYTES + (prod == 2 ? L::B_BYTES : 0)) >> 4);
+    const uint32_t a_base = tmem + ACOL0 + (prod == 1 ? 32u : 0u);
+    const bool active = prod != 1 || a_lo;                     // a single-plane A (raw bytes) has no A_lo B_hi product
     int s = 0; uint32_t ph = 0;
     int as = 0;
     int mtr = 0; (void)mtr;
@@ -733,32 +858,42 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       int nk;
       if (!decode_nk(t, nk)) continue;
       mbar_wait(bar_acce + 8 * buf, aph ^ 1);                  // the epilogue has drained this accumulator set (first NBUF tiles: immediate)
+      if (role == 0) TRACE(mtr, 11);
       tc_fence_after();
-      const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN);
+      // TMA feed: accumulator (prod, half) at column (2 prod + half) BN; cp.async feed: main accumulators 0..R-1, then one per correction
+      const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN) + (TMA ? (uint32_t)((2 * prod + half) * BN) : (prod == 0 ? 0u : (uint32_t)((R + prod - 1) * BN)));
       for (int it = 0; it < nk; ++it) {
+        if (role == 0) TRACE(mtr, 8);
         mbar_wait(bar_full + 8 * s, ph);
-
+        if (role == 0) TRACE(mtr, 9);
         tc_fence_after();
         if (elect_one()) {                                       // one elected lane, uniform control flow: no per-MMA election loop
-          const uint32_t b_hi = sbase + s * L::STAGE_BYTES + L::A_BYTES, b_lo_s = b_hi + L::B_BYTES;
-          const uint32_t a_hi_t = tmem + ACOL0 + (uint32_t)(as * 64), a_lo_t = a_hi_t + 32;
-          constexpr uint32_t LTB = L::B_LTYPE;
+          const uint64_t d0 = dbase + (uint64_t)((uint32_t)(s * L::STAGE_BYTES) >> 4);
+          const uint32_t a_t = a_base + (uint32_t)(as * 64);
+          const uint32_t more = it > 0 ? 1u : 0u;
+#ifndef TC_EXP_NOMMA
+          if (active) {
+            if (TMA) {
 #pragma unroll
-          for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dbh = make_desc(b_hi + j * L::B_KSTEP, L::B_LBO, L::B_SBO, LTB);
-            const uint64_t dbl = make_desc(b_lo_s + j * L::B_KSTEP, L::B_LBO, L::B_SBO, LTB);
-            const int ks = it * (BK / 8) + j;                     // k-step index within this tile
-#ifdef TC_EXP_NOMMA
-            if (ks < 0)
-#endif
-            if (role == 0) umma_tf32_ts(acc + (uint32_t)((ks % R) * BN), a_hi_t + j * 8, dbh, idesc, ks >= R ? 1u : 0u);
-            else if (role == 1) { if (a_lo) umma_tf32_ts(acc + (uint32_t)(R * BN), a_lo_t + j * 8, dbh, idesc, ks > 0 ? 1u : 0u); }
-            else umma_tf32_ts(acc + (uint32_t)((R + 1) * BN), a_hi_t + j * 8, dbl, idesc, ks > 0 ? 1u : 0u);
+              for (int q = 0; q < BK / 16; ++q) {
+                const int j = half + 2 * q;                       // this role's k steps of the stage
+                umma_tf32_ts(acc, a_t + j * 8, d0 + (uint64_t)(j * (L::B_KSTEP >> 4)), idesc, q > 0 ? 1u : more);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < BK / 8; ++j) {
+                const uint32_t d_t = prod == 0 ? acc + (uint32_t)((j % R) * BN) : acc;
+                const uint32_t flag = (prod == 0 ? j >= R : j > 0) ? 1u : more;
+                umma_tf32_ts(d_t, a_t + j * 8, d0 + (uint64_t)(j * (L::B_KSTEP >> 4)), idesc, flag);
+              }
+            }
           }
+#endif
           umma_commit(bar_empty + 8 * s);                         // frees the smem slot and the TMEM A slot when these MMAs retire ...
           if (it == nk - 1) umma_commit(bar_accf + 8 * buf);      // ... and publishes the accumulators after the tile's last stage
         }
         __syncwarp();
+        if (role == 0) TRACE(mtr, 10);
         ++mtr;
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++as == AST) as = 0;
@@ -831,7 +966,7 @@ inline bool tma_a_im2col(CUtensorMap* m, const float* p, int nimg, const dqn::Co
 inline bool tma_build(const dqn::DenseFwdOp* ops, int nops, int bn, TmaMaps& tm) {
   tm.kind = TMA_DENSE_FWD;
   for (int i = 0; i < nops; ++i)
-    if (!ops[i].Xs || !tma_a_kmajor(&tm.a[i], ops[i].Xs, ops[i].M, ops[i].K, ops[i].ldx) || !tma_b_mnmajor(&tm.b[i], ops[i].Ws, ops[i].K, ops[i].N, ops[i].N, bn)) return false;
+    if (!ops[i].Xs || !tma_a_kmajor(&tm.a[i], ops[i].Xs, ops[i].M, ops[i].K, ops[i].ldx) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], ops[i].Ws, ops[i].K, ops[i].N, ops[i].N, bn))) return false;
   return true;
 }
 inline bool tma_build(const dqn::DenseDgradOp* ops, int nops, int bn, TmaMaps& tm) {
@@ -840,15 +975,15 @@ inline bool tma_build(const dqn::DenseDgradOp* ops, int nops, int bn, TmaMaps& t
   tm.kind = TMA_DENSE_DGRAD; tm.seg_k = o.K1;
   const int k0 = o.seg0();
   if (k0 % BK != 0) return false;
-  if (!tma_a_kmajor(&tm.a[0], o.Ds, o.M, k0, o.ldd) || !tma_b_kmajor(&tm.b[0], o.Ws, o.N, k0, k0, bn)) return false;
-  if (o.K1 > 0 && (!tma_a_kmajor(&tm.a[1], o.Ds2, o.M, o.K - o.K1, o.ldd2) || !tma_b_kmajor(&tm.b[1], o.Ws2, o.N, o.K - o.K1, o.K - o.K1, bn))) return false;
+  if (!tma_a_kmajor(&tm.a[0], o.Ds, o.M, k0, o.ldd) || (TC_TMA_B && !tma_b_kmajor(&tm.b[0], o.Ws, o.N, k0, k0, bn))) return false;
+  if (o.K1 > 0 && (!tma_a_kmajor(&tm.a[1], o.Ds2, o.M, o.K - o.K1, o.ldd2) || (TC_TMA_B && !tma_b_kmajor(&tm.b[1], o.Ws2, o.N, o.K - o.K1, o.K - o.K1, bn)))) return false;
   return true;
 }
 inline bool tma_build(const dqn::DenseWgradOp* ops, int nops, int bn, TmaMaps& tm) {
   tm.kind = TMA_DENSE_WGRAD;
   for (int i = 0; i < nops; ++i) {
     if (!ops[i].no_bias || !ops[i].Xs) return false;            // the ones row of [x 1] is not a box: bias gradient by colsum_kernel
-    if (!tma_a_mnmajor(&tm.a[i], ops[i].Xs, ops[i].K, ops[i].M, ops[i].ldx) || !tma_b_mnmajor(&tm.b[i], ops[i].Ds, ops[i].K, ops[i].N, ops[i].ldd, bn)) return false;
+    if (!tma_a_mnmajor(&tm.a[i], ops[i].Xs, ops[i].K, ops[i].M, ops[i].ldx) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], ops[i].Ds, ops[i].K, ops[i].N, ops[i].ldd, bn))) return false;
   }
   return true;
 }
@@ -858,13 +993,54 @@ inline bool tma_build(const dqn::ConvFwdOp* ops, int nops, int bn, TmaMaps& tm) 
     const dqn::ConvFwdOp& o = ops[i];
     if (o.a8 || !o.Xs || o.g.Cin % 32 != 0) return false;
     if (i > 0 && (o.g.Cin != ops[0].g.Cin || o.g.KW != ops[0].g.KW || o.g.S != ops[0].g.S || o.g.OH != ops[0].g.OH || o.g.OW != ops[0].g.OW)) return false;
-    if (!tma_a_im2col(&tm.a[i], o.Xs, o.nimg, o.g) || !tma_b_mnmajor(&tm.b[i], o.Ws, o.K, o.N, o.N, bn)) return false;
+    if (!tma_a_im2col(&tm.a[i], o.Xs, o.nimg, o.g) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], o.Ws, o.K, o.N, o.N, bn))) return false;
   }
   tm.cin = ops[0].g.Cin; tm.kw = ops[0].g.KW; tm.stride = ops[0].g.S; tm.oh = ops[0].g.OH; tm.ow = ops[0].g.OW;
   return true;
 }
-inline bool tma_build(const dqn::ConvWgradOp*, int, int, TmaMaps&) { return false; }
-inline bool tma_build(const dqn::ConvDgradOp*, int, int, TmaMaps&) { return false; }
+// x [nimg][IH][IW][Cin] as im2col boxes of 32 output pixels x 32 channels (the weight gradient's A operand, k = pixel)
+inline bool tma_a_im2col_wgrad(CUtensorMap* m, const float* p, int nimg, const dqn::ConvGeom& g) {
+  if (!tma_api().load() || (reinterpret_cast<uintptr_t>(p) & 15) || g.Cin % 32 != 0 || g.S > 8) return false;
+  cuuint64_t gd[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)nimg};
+  cuuint64_t gs[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.IW * g.Cin * 4, (cuuint64_t)g.IH * g.IW * g.Cin * 4};
+  int lo[2] = {0, 0}, up[2] = {-(g.KW - 1), -(g.KH - 1)};
+  cuuint32_t es[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
+  return tma_api().im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), gd, gs, lo, up, 32, BK, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool tma_build(const dqn::ConvWgradOp* ops, int nops, int bn, TmaMaps& tm) {
+  if (nops != 1) return false;
+  const dqn::ConvWgradOp& o = ops[0];
+  if (o.a8 || !o.no_bias || !o.Xs || o.g.Cin % 32 != 0 || o.N % 32 != 0) return false;
+  tm.kind = TMA_CONV_WGRAD; tm.a_slabs = 1;
+  tm.cin = o.g.Cin; tm.kw = o.g.KW; tm.stride = o.g.S; tm.oh = o.g.OH; tm.ow = o.g.OW; tm.ntaps = o.g.KH * o.g.KW;
+  return tma_a_im2col_wgrad(&tm.a[0], o.Xs, o.nimg, o.g) && tma_b_mnmajor(&tm.b[0], o.Ds, o.K, o.N, o.N, bn);
+}
+// delta [nimg][OH][OW][Cout] per parity class: a stride-1 correlation with TH x TW taps over the zero-padded delta tensor
+inline bool tma_build(const dqn::ConvDgradOp* ops, int nops, int bn, TmaMaps& tm) {
+  if (nops != 1 || !TC_TMA_B) return false;
+  const dqn::ConvDgradOp& o = ops[0];
+  const dqn::ConvGeom& g = o.g;
+  if (!o.Ds || !o.Ws || g.Cout % 32 != 0 || g.S * g.S > 4 || (reinterpret_cast<uintptr_t>(o.Ds) & 15) || (reinterpret_cast<uintptr_t>(o.Ws) & 15) || !tma_api().load()) return false;
+  tm.kind = TMA_CONV_DGRAD; tm.cin = g.Cout; tm.kw = g.KW; tm.stride = g.S;
+  for (int z = 0; z < g.S * g.S; ++z) {
+    dqn::ConvDgradOp c = o; c.set_class(z);
+    if (c.TH < 1 || c.TW < 1 || c.AH < 1 || c.BW < 1 || c.TH > 16 || c.TW > 16) return false;
+    cuuint64_t gd[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)o.nimg};
+    cuuint64_t gs[3] = {(cuuint64_t)g.Cout * 4, (cuuint64_t)g.OW * g.Cout * 4, (cuuint64_t)g.OH * g.OW * g.Cout * 4};
+    // base pixels b' = b - (TW-1), b in [0, BW): from -(TW-1) to BW - TW = (OW - 1) + upper
+    int lo[2] = {-(c.TW - 1), -(c.TH - 1)}, up[2] = {c.BW - c.TW - (g.OW - 1), c.AH - c.TH - (g.OH - 1)};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (tma_api().im2col(&tm.a[z], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  }
+  // weights [(kh,kw)][Cin][Cout]: B(k = co, n = ci) of one tap is a K-major [Cin][Cout] slab
+  cuuint64_t gd[3] = {(cuuint64_t)g.Cout, (cuuint64_t)g.Cin, (cuuint64_t)(g.KH * g.KW)};
+  cuuint64_t gs[2] = {(cuuint64_t)g.Cout * 4, (cuuint64_t)g.Cin * g.Cout * 4};
+  cuuint32_t bx[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1}, es3[3] = {1, 1, 1};
+  return tma_api().tiled(&tm.b[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(o.Ws), gd, gs, bx, es3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace tc
 
 #ifndef TC_KERNEL_ONLY
@@ -881,7 +1057,7 @@ void tc_launch_v(dqn_engine* e, const Op* ops, int nops, int nsplit, long long w
     CK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, A8, Op, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     attr_set[dev >> 6] |= 1ull << (dev & 63);
   }
-  const int grid = std::min(ntiles, e->nsm);                    // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
+  const int grid = std::min(ntiles, std::max(e->nsm - e->sm_reserve, 1));   // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ... (SMs held back for NCCL while a reduction runs)
   tc::tc_gemm_kernel<BN, R, NBUF, A8, Op, TMA><<<grid, tc::THREADS, L::SMEM, e->ls>>>(ops[0], ops[std::min(1, nops - 1)], ops[std::min(2, nops - 1)], ops[std::min(3, nops - 1)],
                                                                                  nsplit, e->lws, ws_stride, e->arena, MT, NT, ntiles, tail_t0, tail_s, tm);
   CK(cudaGetLastError());
@@ -1006,6 +1182,8 @@ void tc_init(dqn_engine* e) {
   // idle (measured 0.499 ms/step with the tail split against 0.486 without, although every affected kernel alone is 20-27 % faster)
   { const char* v = getenv("DQN_TC_TAIL"); e->tc_tail = v ? atoi(v) : 0; }
   { const char* v = getenv("DQN_TC_TMA"); e->tc_tma = v ? atoi(v) : 1; }
+  { const char* v = getenv("DQN_TC_C1"); e->tc_c1 = v ? atoi(v) : 1; }
+  { const char* v = getenv("DQN_TC_TMA_WGRAD"); e->tc_tma_wgrad = v ? atoi(v) : 0; }
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
   const bool bytes = e->elem_bytes == 1;

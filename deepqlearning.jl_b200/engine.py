@@ -9,7 +9,8 @@ from ._capi import lib, ptr, vptr, DQNError
 
 def make_config(layers, obs_shape, n_actions, *, obs_dtype="f32", dueling=True, double_q=True, prioritized_replay=True,
                 batch_size=32, buffer_size=1000, alpha=0.6, beta=0.4, eps=1e-3, learning_rate=1e-4, discount=1.0,
-                seed=0, device=0, math_mode=_capi.MATH_FP32, use_graph=True, rank=0, world=1, nccl_id=None, max_act_rows=0):
+                seed=0, device=0, math_mode=_capi.MATH_FP32, use_graph=True, rank=0, world=1, nccl_id=None, max_act_rows=0,
+                trace_length=0, max_episode_length=0):
     """obs_shape is the Flux size tuple of one observation: (d,) or (W, H, C)."""
     cfg = _capi.default_config()
     if len(obs_shape) == 1:
@@ -35,6 +36,7 @@ def make_config(layers, obs_shape, n_actions, *, obs_dtype="f32", dueling=True, 
     cfg.learning_rate, cfg.discount = float(learning_rate), float(discount)
     cfg.seed, cfg.device, cfg.math_mode, cfg.use_graph = int(seed), int(device), int(math_mode), int(use_graph)
     cfg.rank, cfg.world, cfg.max_act_rows = int(rank), int(world), int(max_act_rows)
+    cfg.trace_length, cfg.max_episode_length = int(trace_length), int(max_episode_length)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), _capi.DQN_NCCL_ID_BYTES)
     return cfg
@@ -49,14 +51,22 @@ def nccl_unique_id():
 
 
 class Engine:
-    def __init__(self, cfg):
+    def __init__(self, cfg, handle=None):
+        """handle: wrap an engine owned by someone else (a rank of a Group) instead of creating one"""
         self.cfg = cfg
-        h = C.c_void_p()
-        rc = lib.dqn_engine_create(C.byref(cfg), C.byref(h))
-        if rc != 0:
-            raise DQNError(rc, (lib.dqn_last_error(None) or b"").decode())
+        self._owned = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            rc = lib.dqn_engine_create(C.byref(cfg), C.byref(h))
+            if rc != 0:
+                raise DQNError(rc, (lib.dqn_last_error(None) or b"").decode())
+        else:
+            h = C.c_void_p(handle)
         self.h = h
-        self.B = cfg.batch_size
+        self.recurrent = any(cfg.layers[i].kind == _capi.LAYER_LSTM for i in range(cfg.n_layers))
+        self.T = (cfg.trace_length or 40) if self.recurrent else 1
+        self.Bep = cfg.batch_size
+        self.B = cfg.batch_size * self.T          # rows of the step's diagnostics (recurrent: trace_length * batch_size, time-major)
         self.nA = cfg.n_actions
         self.obs_elems = cfg.obs_c * cfg.obs_h * cfg.obs_w
         self.obs_np = np.uint8 if cfg.obs_dtype == _capi.OBS_U8 else np.float32
@@ -65,7 +75,8 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
-            lib.dqn_engine_destroy(self.h)
+            if self._owned:
+                lib.dqn_engine_destroy(self.h)
             self.h = None
 
     __del__ = close
@@ -151,6 +162,28 @@ class Engine:
         self._ck(lib.dqn_get_tree(self.h, ptr(out, C.c_float), out.size))
         return out
 
+    # ---- EpisodeReplayBuffer (recurrent engines) ---------------------------------------------------
+    def episode_add(self, s, a, r, sp, done):
+        a = np.ascontiguousarray(a, np.int32)
+        n = a.size
+        s = np.ascontiguousarray(s, np.float32); sp = np.ascontiguousarray(sp, np.float32)
+        r = np.ascontiguousarray(r, np.float32); done = np.ascontiguousarray(done, np.uint8)
+        assert s.size == n * self.obs_elems and sp.size == s.size and r.size == n and done.size == n
+        self._ck(lib.dqn_episode_add(self.h, ptr(s, C.c_float), ptr(a, C.c_int32), ptr(r, C.c_float), ptr(sp, C.c_float), ptr(done, C.c_uint8), n))
+
+    def episode_count(self):
+        n, c = C.c_int64(), C.c_int64()
+        self._ck(lib.dqn_episode_count(self.h, C.byref(n), C.byref(c)))
+        return n.value, c.value
+
+    def episode_sample(self, call):
+        idx = np.empty(self.Bep, np.int64); start = np.empty(self.Bep, np.int32)
+        self._ck(lib.dqn_episode_sample(self.h, int(call), ptr(idx, C.c_int64), ptr(start, C.c_int32)))
+        return idx, start
+
+    def policy_reset(self):
+        self._ck(lib.dqn_policy_reset(self.h))
+
     def sample_indices(self, call):
         out = np.empty(self.B, np.int64)
         self._ck(lib.dqn_sample_indices(self.h, int(call), ptr(out, C.c_int64)))
@@ -177,7 +210,7 @@ class Engine:
 
     def train_step_with_indices(self, idx):
         idx = np.ascontiguousarray(idx, np.int64)
-        assert idx.size == self.B
+        assert idx.size == (self.Bep if self.recurrent else self.B)
         loss, gn = C.c_float(), C.c_float()
         self._ck(lib.dqn_train_step_with_indices(self.h, ptr(idx, C.c_int64), C.byref(loss), C.byref(gn)))
         return loss.value, gn.value
@@ -200,7 +233,7 @@ class Engine:
 
     # ---- diagnostics -------------------------------------------------------------------------------
     def last_indices(self):
-        out = np.empty(self.B, np.int64)
+        out = np.empty(self.B if not self.recurrent else self.B, np.int64)
         self._ck(lib.dqn_get_last_indices(self.h, ptr(out, C.c_int64)))
         return out
 
@@ -262,3 +295,42 @@ class Engine:
 
     def flush_l2(self):
         self._ck(lib.dqn_flush_l2(self.h))
+
+
+class Group:
+    """ndev engines in ONE process behind dqn_group_create (what a single-process host such as the reference's Julia solver binds):
+    rank r on device r, one NCCL communicator inside.  `engines[r]` is an Engine view of rank r for the per-shard calls."""
+
+    def __init__(self, cfg, ndev, devices=None):
+        g = C.c_void_p()
+        dev = None if devices is None else (C.c_int * ndev)(*devices)
+        rc = lib.dqn_group_create(C.byref(cfg), int(ndev), dev, C.byref(g))
+        if rc != 0:
+            raise DQNError(rc, (lib.dqn_group_last_error(None) or b"").decode())
+        self.g = g
+        self.engines = [Engine(cfg, handle=lib.dqn_group_engine(g, r)) for r in range(ndev)]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DQNError(rc, (lib.dqn_group_last_error(self.g) or b"").decode())
+
+    def set_params(self, flat, which=_capi.NET_ONLINE):
+        flat = np.ascontiguousarray(flat, np.float32)
+        self._ck(lib.dqn_group_set_params(self.g, which, ptr(flat, C.c_float), flat.size))
+
+    def sync_target(self):
+        self._ck(lib.dqn_group_sync_target(self.g))
+
+    def train_step(self):
+        loss, gn = C.c_float(), C.c_float()
+        self._ck(lib.dqn_group_train_step(self.g, C.byref(loss), C.byref(gn)))
+        return loss.value, gn.value
+
+    def close(self):
+        if getattr(self, "g", None):
+            for e in self.engines:
+                e.h = None
+            lib.dqn_group_destroy(self.g)
+            self.g = None
+
+    __del__ = close

@@ -48,6 +48,29 @@ class Conv:
         return dict(kind=_capi.LAYER_CONV, act=self.act, in_=self.cin, out=self.cout, kh=self.kh, kw=self.kw, stride=self.stride)
 
 
+class LSTM:
+    """Flux.LSTM(in, out) = Recur(LSTMCell): Wi (4out, in), Wh (4out, out), b (4out) with the forget-gate slice at 1, state0 = (h0, c0)
+    zeros (out, 1); numpy images (in, 4out), (out, 4out), (4out,), (1, out), (1, out); Flux.params order Wi, Wh, b, h0, c0."""
+
+    def __init__(self, nin, nout, rng=None):
+        self.nin, self.nout = int(nin), int(nout)
+        rng = rng or np.random.default_rng()
+        lim = np.sqrt(6.0 / (nin + 4 * nout))
+        self.Wi = rng.uniform(-lim, lim, (nin, 4 * nout)).astype(np.float32)
+        lim = np.sqrt(6.0 / (nout + 4 * nout))
+        self.Wh = rng.uniform(-lim, lim, (nout, 4 * nout)).astype(np.float32)
+        self.b = np.zeros(4 * nout, np.float32)
+        self.b[nout:2 * nout] = 1.0
+        self.h0 = np.zeros((1, nout), np.float32)
+        self.c0 = np.zeros((1, nout), np.float32)
+
+    def params(self):
+        return [self.Wi, self.Wh, self.b, self.h0, self.c0]
+
+    def desc(self):
+        return dict(kind=_capi.LAYER_LSTM, act=identity, in_=self.nin, out=self.nout)
+
+
 class flattenbatch:
     """src/helpers.jl:6-8"""
 
@@ -106,8 +129,8 @@ def create_dueling_network(m, rng=None):
 
 
 def isrecurrent(m):
-    """src/helpers.jl:25-32 - no recurrent layer type exists in this package yet."""
-    return False
+    """src/helpers.jl:25-32"""
+    return any(isinstance(l, LSTM) for l in m)
 
 
 def flat_params(net):

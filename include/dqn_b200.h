@@ -35,6 +35,7 @@ extern "C" {
 #define DQN_NCCL_ID_BYTES 128
 
 typedef struct dqn_engine dqn_engine_t;
+typedef struct dqn_group dqn_group_t;
 
 typedef enum {
   DQN_OK = 0,
@@ -46,7 +47,8 @@ typedef enum {
 } dqn_status;
 
 enum { DQN_ACT_IDENTITY = 0, DQN_ACT_RELU = 1, DQN_ACT_TANH = 2, DQN_ACT_SIGMOID = 3 };
-enum { DQN_LAYER_DENSE = 0, DQN_LAYER_CONV = 1, DQN_LAYER_FLATTEN = 2 };
+enum { DQN_LAYER_DENSE = 0, DQN_LAYER_CONV = 1, DQN_LAYER_FLATTEN = 2,
+       DQN_LAYER_LSTM = 3 };   /* Flux.LSTM(in, out): makes the engine recurrent (SOLVER:239-287, EpisodeReplayBuffer) */
 enum { DQN_OBS_F32 = 0, DQN_OBS_U8 = 1 };   /* U8: value k stands for Float32(k)/255f0 */
 enum { DQN_NET_ONLINE = 0, DQN_NET_TARGET = 1 };
 enum { DQN_Q_S_ONLINE = 0, DQN_Q_SP_ONLINE = 1, DQN_Q_SP_TARGET = 2 };
@@ -87,7 +89,9 @@ typedef struct {
   int32_t rank, world;        /* data-parallel group; world=1 => no collective */
   uint8_t nccl_id[DQN_NCCL_ID_BYTES];   /* ncclUniqueId from dqn_nccl_unique_id (rank 0), ignored if world==1 */
   int32_t max_act_rows;       /* rows per dqn_q_values chunk (0 => 2*batch_size) */
-  int32_t reserved[7];
+  int32_t trace_length;       /* recurrent engines: SOLVER:15 trace_length (default 40) */
+  int32_t max_episode_length; /* recurrent engines: steps stored per episode (SOLVER:21 max_episode_length, default 100) */
+  int32_t reserved[5];
 } dqn_config_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------ */
@@ -97,6 +101,19 @@ void dqn_engine_destroy(dqn_engine_t* h);
 const char* dqn_last_error(const dqn_engine_t* h);               /* h may be NULL: error of the last failed create on this thread */
 int dqn_nccl_unique_id(uint8_t id_out[DQN_NCCL_ID_BYTES]);
 int dqn_device_count(int* n);
+
+/* ---- single-process data-parallel group (the Julia host is one process, SURVEY 8b "Multi-GPU") -----------------------------------
+ * ndev engines behind one handle: rank r on devices[r] (NULL: 0..ndev-1), world = ndev, sampler seed cfg->seed + r, one NCCL
+ * communicator created inside.  Per-shard calls (dqn_replay_add, dqn_replay_fill_synthetic, dqn_get_params, ...) go through
+ * dqn_group_engine(g, r); the calls below act on all ranks at once (each on its own worker thread). */
+int dqn_group_create(const dqn_config_t* cfg, int ndev, const int* devices, dqn_group_t** out);
+void dqn_group_destroy(dqn_group_t* g);
+int dqn_group_size(const dqn_group_t* g);
+dqn_engine_t* dqn_group_engine(dqn_group_t* g, int rank);
+const char* dqn_group_last_error(const dqn_group_t* g);
+int dqn_group_set_params(dqn_group_t* g, int which, const float* flat, int64_t n);   /* the same parameters on every rank */
+int dqn_group_sync_target(dqn_group_t* g);
+int dqn_group_train_step(dqn_group_t* g, float* loss, float* grad_norm);            /* one data-parallel batch_train! (SOLVER:191-236 over B * ndev samples) */
 
 /* ---- parameters: Flux.params(active_q) / loadparams! (SOLVER:143-144, 173-174, 292, 314-316) ------- */
 int64_t dqn_num_params(const dqn_engine_t* h);
@@ -116,6 +133,16 @@ int dqn_replay_size(const dqn_engine_t* h, int64_t* curr_size, int64_t* cursor);
  * oracle/synthetic.py regenerates any subset on the CPU. */
 int dqn_replay_fill_synthetic(dqn_engine_t* h, int64_t n, uint64_t seed);
 int dqn_replay_read(dqn_engine_t* h, const int64_t* idx, int64_t n, void* s, int32_t* a, float* r, void* sp, uint8_t* done);
+
+/* ---- recurrent engines (a DQN_LAYER_LSTM in the chain): EpisodeReplayBuffer (src/episode_replay.jl) ----------------------------
+ * buffer_size counts EPISODES here (SOLVER:184 EpisodeReplayBuffer(env, solver.buffer_size, batch_size, trace_length)); observations
+ * are Float32; dqn_train_step is then the recurrent batch_train! (SOLVER:239-287): batch_size episodes, trace_length steps, the
+ * start-offset behaviour of src/episode_replay.jl:81-92 preserved.  The step's diagnostics (dqn_get_q, dqn_get_td, dqn_get_targets,
+ * dqn_get_is_weights = the Int32 trace mask as floats) have trace_length * batch_size rows, time-major (row t * batch_size + i). */
+int dqn_episode_add(dqn_engine_t* h, const float* s, const int32_t* a, const float* r, const float* sp, const uint8_t* done, int64_t len);  /* add_episode! :60-66 */
+int dqn_episode_count(const dqn_engine_t* h, int64_t* curr_size, int64_t* cursor);
+int dqn_episode_sample(dqn_engine_t* h, uint64_t call, int64_t* idx_out, int32_t* start_out);   /* indices / ep_start sampling call `call` draws; no state change */
+int dqn_policy_reset(dqn_engine_t* h);                           /* resetstate!(policy) POLICY:32-34: acting hidden state <- state0 */
 
 /* ---- priorities: update_priorities! (PER:76-80) --------------------------------------------------- */
 int dqn_update_priorities(dqn_engine_t* h, const int64_t* idx, const float* td, int64_t n);

@@ -8,6 +8,7 @@ JuliaPOMDP/DeepQLearning.jl (reference citations are into /root/reference):
                                                sample, get_batch
   src/dueling.jl:8-11, 36-58                   DuelingNetwork forward, create_dueling_network
   src/helpers.jl:6-19, 38-46                   flattenbatch, huber_loss, globalnorm
+  src/solver.jl:239-287, src/episode_replay.jl  recurrent batch_train!, EpisodeReplayBuffer (oracle/recurrent.py)
 
 PARITY UNPINNED: the reference is pure Julia, Julia is not installed in this image, the
 arithmetic lives in un-vendored third-party packages (Flux 0.14 / Zygote / NNlib / StatsBase
@@ -27,3 +28,4 @@ from .nets import (ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_SIGMOID, Conv, Dense, F
                    params_of, set_params, flat_params, num_params)
 from .replay import PrioritizedReplayBuffer, DQExperience, pairwise_sum_f32, pow_f32
 from .step import batch_train, Adam, huber_loss, globalnorm, q_targets_of, forward_backward
+from .recurrent import (LSTM, RecurrentQ, make_recurrent_q, EpisodeReplayBuffer, forward_backward_recurrent, batch_train_recurrent)

@@ -10,6 +10,7 @@
 using namespace dqn;
 #define TC_KERNEL_ONLY
 #include "../../deepqlearning.jl_b200/csrc/tc_gemm_impl.cuh"
+#include "../../deepqlearning.jl_b200/csrc/conv1_tc.cuh"
 
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -133,10 +134,11 @@ template <int BN> static void test_conv(int nimg, int IH, int IW, int Cin, int C
   }
   {
     ConvWgradOp op{}; op.X = X.data(); op.D = D.data(); op.nimg = nimg; op.g = g; op.M = K + 1; op.N = Cout; op.K = P; op.vecA = op.vecB = 1;
-    std::vector<float> ref((K + 1) * Cout); op.dW = ref.data(); igemm_host(op);
+    if (g_feed == 1 && Cin % 32 == 0) { op.no_bias = 1; op.M = K; }     // TMA feed: no ones row (bias gradient = column sums, elsewhere)
+    std::vector<float> ref((K + 1) * Cout, 0.f); op.dW = ref.data(); igemm_host(op);
     ConvWgradOp q = op; q.X = dX; q.D = dD; q.dW = dG; q.Xs = ar.d + oX; q.Ds = ar.d + oD; q.ones = ar.d + oOnes; q.lo_delta = ar.plane;
     run_tc<BN>(q, 1, 1, nullptr, 0, ar.d);
-    std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dG, got.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> got(ref.size(), 0.f); CKC(cudaMemcpy(got.data(), dG, (size_t)op.M * Cout * 4, cudaMemcpyDeviceToHost));
     report("conv_wgrad (A:MN B:MN)", got, ref);
   }
   {
@@ -152,6 +154,46 @@ template <int BN> static void test_conv(int nimg, int IH, int IW, int Cin, int C
     cudaFree(dYp);
   }
   cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
+}
+
+// the dedicated first-layer kernel (conv1_tc.cuh) on byte observations against the CPU executor of ConvFwdOp (x_u8: k/255f0 operands)
+static void test_conv1_bytes(int nimg, int IH, int IW, int iters) {
+  ConvGeom g{}; g.IH = IH; g.IW = IW; g.Cin = 4; g.KH = 8; g.KW = 8; g.S = 4; g.OH = (IH - 8) / 4 + 1; g.OW = (IW - 8) / 4 + 1; g.Cout = 32; g.init();
+  const int K = 256, N = 32, P = nimg * g.OH * g.OW;
+  if (!c1::geometry_ok(g)) { printf("FAIL conv1 geometry rejected\n"); ++fails; return; }
+  std::vector<uint8_t> X((size_t)nimg * IH * IW * 4);
+  for (auto& v : X) { s_ ^= s_ << 13; s_ ^= s_ >> 7; s_ ^= s_ << 17; v = (uint8_t)(s_ >> 24); }
+  std::vector<float> W((K + 1) * N), Ws(K * N);
+  for (auto& v : W) v = rnd() * 0.1f;
+  for (int i = 0; i < K * N; ++i) Ws[i] = W[i] * (1.0f / 255.0f);
+  uint8_t* dX; float *dW, *dWs, *dY;
+  CKC(cudaMalloc(&dX, X.size())); CKC(cudaMalloc(&dW, W.size() * 4)); CKC(cudaMalloc(&dWs, Ws.size() * 4)); CKC(cudaMalloc(&dY, (size_t)P * N * 4));
+  CKC(cudaMemcpy(dX, X.data(), X.size(), cudaMemcpyHostToDevice)); CKC(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dWs, Ws.data(), Ws.size() * 4, cudaMemcpyHostToDevice)); CKC(cudaMemset(dY, 0xFF, (size_t)P * N * 4));
+  ConvFwdOp op{}; op.X = dX; op.x_u8 = 1; op.W = dW; op.Ws = dWs; op.Y = dY; op.act = ACT_RELU; op.nimg = nimg; op.g = g; op.M = P; op.N = N; op.K = K; op.a8 = 1;
+  CUtensorMap tm;
+  if (!c1::make_map(&tm, dX, nimg, g)) { printf("FAIL conv1 tensor map\n"); ++fails; return; }
+  const c1::Params pr = c1::make_params(op);
+  const int smem = c1::smem_bytes(pr.patch_slot), ntiles = (P + 127) / 128, grid = ntiles < g_nsm ? ntiles : g_nsm;
+  CKC(cudaFuncSetAttribute(c1::conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, pr, ntiles);
+  CKC(cudaGetLastError()); CKC(cudaDeviceSynchronize());
+  if (iters > 0) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    for (int i = 0; i < iters; ++i) c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, pr, ntiles);
+    cudaEventRecord(b); CKC(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    const double us = 1e3 * ms / iters;
+    printf("bench conv1 dedicated kernel %d img %dx%dx4 (M=%d): %.1f us  %.1f TFLOP/s algorithmic  grid %d\n", nimg, IH, IW, P, us, 2.0 * P * N * K / (us * 1e-6) / 1e12, grid);
+  } else {
+    ConvFwdOp h = op; h.X = X.data(); h.W = W.data(); h.a8 = 0; h.vecA = h.vecB = 1;
+    std::vector<float> ref((size_t)P * N); h.Y = ref.data(); igemm_host(h);
+    std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dY, got.size() * 4, cudaMemcpyDeviceToHost));
+    g_last_tma = true;
+    report("conv1_fwd bytes (dedicated)", got, ref);
+  }
+  cudaFree(dX); cudaFree(dW); cudaFree(dWs); cudaFree(dY);
 }
 
 // timing of one big dense forward (conv2-like and fc1-like shapes) - tuning aid
@@ -175,16 +217,16 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   const double us = 1e3 * ms / iters, tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
 #ifdef TC_TRACE
   {
-    std::vector<long long> tr(8192);
-    CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 8192));
-    printf("  trace CTA0 stage: L.top L.empty-ok L.issued | C.landed-ok C.slot-ok C.st-issued C.st-waited C.arrived   (cycles)\n");
+    std::vector<long long> tr(16384);
+    CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 16384));
+    printf("  trace CTA0, cycles since launch; per stage: P.top P.slot-free P.issued | C.landed C.tmem-free C.st-issued C.st-done C.arrived | M.top M.full M.issued M.acc-free(1st stage of a tile) | per tile index: E.top E.acc-full E.done\n");
     const long long t0 = tr[0];
-    for (int it = 16; it < 56; ++it) {
+    for (int it = 0; it < 40; ++it) {
       printf("  %2d:", it);
-      for (int j = 0; j < 8; ++j) printf(" %7lld", tr[it * 8 + j] ? tr[it * 8 + j] - t0 : -1);
+      for (int j = 0; j < 15; ++j) { if (j == 3 || j == 8 || j == 12) printf(" |"); printf(" %6lld", tr[it * 16 + j] ? tr[it * 16 + j] - t0 : -1); }
       printf("\n");
     }
-    std::vector<long long> z(8192, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 8192));
+    std::vector<long long> z(16384, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 16384));
   }
 #endif
   printf("bench dense M=%d N=%d K=%d BN=%d stages=%d: %.1f us  %.1f TFLOP/s algorithmic (x3 = %.0f TF32)  grid %d\n", M, N, K, BN, L::STAGES, us, tf, 3 * tf, grid.x * grid.y);
@@ -195,6 +237,7 @@ int main(int argc, char** argv) {
   { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
     const int it = argc > 2 ? atoi(argv[2]) : 20;
+    if (argc > 3) { test_conv1_bytes(512, 84, 84, it); test_conv1_bytes(256, 84, 84, it); return 0; }
     for (g_feed = 0; g_feed < 2; ++g_feed) {
       printf("== feed: %s\n", g_feed ? "TMA" : "cp.async");
       bench_dense<64>(41472, 64, 512, it);       // conv2 forward shape
@@ -217,6 +260,11 @@ int main(int argc, char** argv) {
     printf("-- dense M=39685 N=64 K=96 (BN=64, 311 tiles: several tiles per persistent CTA)\n"); g_tol = 1e-4; test_dense<64>(39685, 64, 96); g_tol = 2e-5;
     printf("-- conv 2 img 84x84x4 -> 32, 8x8 s4 (BN=32, conv1 geometry)\n"); test_conv<32>(2, 84, 84, 4, 32, 8, 8, 4);
   }
+  printf("==== dedicated first-layer kernel\n");
+  test_conv1_bytes(5, 84, 84, 0);        // tiles that cross images, a partial last tile
+  test_conv1_bytes(1, 84, 84, 0);
+  test_conv1_bytes(3, 80, 100, 0);       // another geometry of the same family (OW = 24)
+  test_conv1_bytes(300, 84, 84, 0);      // several tiles per persistent CTA: both patch / accumulator buffers wrap
   printf(fails ? "SELFTEST FAILED %d\n" : "SELFTEST OK\n", fails);
   return fails ? 1 : 0;
 }

@@ -493,3 +493,49 @@ def test_data_parallel_two_gpus(n_gpus):
     with open(os.path.join(root, "gpurun_out", "mgpu_check.log"), "w") as f:
         f.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
     assert r.returncode == 0 and r.stdout.count("MGPU OK") == 2, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def _group_case(lib, ndev):
+    """dqn_group_create(ndev): one step on explicit per-shard data against the oracle's gradient of the combined batch."""
+    spec = util.SPECS["conv_small"]
+    B = spec["B"]
+    net = util.make_oracle_net(spec, True, seed=21)
+    tgt = util.perturbed_copy(net, seed=22)
+    cfg = lib.make_config(util.layer_descs(spec), tuple(reversed(spec["obs"])), spec["nA"], obs_dtype="u8", batch_size=B, buffer_size=spec["N"],
+                          learning_rate=spec["lr"], discount=0.99, seed=SEED)
+    grp = lib.Group(cfg, ndev)
+    grp.set_params(O.flat_params(net), 0)
+    grp.set_params(O.flat_params(tgt), 1)
+    bufs = []
+    for r, eng in enumerate(grp.engines):
+        s, a, rr, sp, done = util.random_transitions(spec, 150, seed=60 + r)
+        eng.replay_add(s, a, rr, sp, done, np.abs(rr))
+        buf = util.make_oracle_replay(spec); buf.add_batch(s, a, rr, sp, done, np.abs(rr)); bufs.append(buf)
+    loss, gn = grp.train_step()
+    S, A, R, SP, D, W, losses = [], [], [], [], [], [], []
+    for r, (eng, buf) in enumerate(zip(grp.engines, bufs)):
+        idx = eng.last_indices()
+        want, _ = buf.tree.sample(B, SEED + r, 0)                            # rank r samples with seed + r
+        assert np.array_equal(idx, want)
+        sb, ab, rb, spb, db, _, w = buf.get_batch(idx, total="tree", dequant=util.dequant)
+        S.append(sb); A.append(ab); R.append(rb); SP.append(spb); D.append(db); W.append(w)
+    out = O.forward_backward(net, tgt, np.concatenate(S), np.concatenate(A) - 1, np.concatenate(R), np.concatenate(SP), np.concatenate(D),
+                             np.concatenate(W), 0.99, True, np.float64)
+    gref = np.concatenate([x.ravel() for x in out["grads"]])
+    for eng in grp.engines:
+        assert util.relerr(eng.grads(), gref) < 2e-4
+    assert abs(loss - out["loss"]) <= 1e-5 * abs(out["loss"])
+    th = [eng.get_params(0) for eng in grp.engines]
+    for t in th[1:]:
+        assert np.array_equal(t, th[0])                                      # identical Adam on every rank
+    grp.close()
+
+
+def test_group_of_one_is_a_plain_engine(lib):
+    _group_case(lib, 1)
+
+
+def test_group_single_process_two_gpus(lib, n_gpus):
+    if n_gpus < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _group_case(lib, 2)
