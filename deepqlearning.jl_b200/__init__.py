@@ -11,6 +11,6 @@ from .engine import Engine, Group, make_config, nccl_unique_id
 from .flux import (Chain, Dense, Conv, LSTM, flattenbatch, DuelingNetwork, create_dueling_network, isrecurrent, flat_params,
                    load_flat_params, identity, relu, tanh, sigmoid)
 from .dist import ControlPlane, shard_seeds
-from .replay import PrioritizedReplayBuffer, DQExperience
+from .replay import PrioritizedReplayBuffer, EpisodeReplayBuffer, DQExperience
 from .solver import (DeepQLearningSolver, solve, dqn_train, batch_train, NNPolicy, EpsGreedyPolicy, LinearDecaySchedule,
-                     basic_evaluation, getnetwork, actionvalues, action, value, initialize_replay_buffer, populate_replay_buffer)
+                     basic_evaluation, batched_evaluation, getnetwork, actionvalues, action, value, initialize_replay_buffer, populate_replay_buffer)

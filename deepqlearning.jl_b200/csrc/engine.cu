@@ -1548,6 +1548,65 @@ int dqn_policy_reset(dqn_engine_t* h) {
   });
 }
 
+// ---- vectorised acting on the device (the caller side of the path) ------------------------------------------------
+// One forward of the online network over n lanes (the tensor-core path when the engine runs DQN_MATH_3XTF32), dueling combine, first-max
+// argmax and the epsilon-greedy draw in one kernel: actions never bounce through the host.  obs_layout 0: Flux layout (C,H,W per lane,
+// what dqn_q_values takes), 1: the engine's own H,W,C layout (what a device-side environment writes / dqn_replay_add_device reads back).
+static void act_rows(dqn_engine_t* h, const void* obs_dev, long long n, int obs_layout, float eps, uint64_t call, int32_t* actions_dev, float* q_dev) {
+  const long long rb = h->obs_row_bytes; const int nA = h->cfg.n_actions; const int L = h->depth - 1;
+  if (h->lstm) fail(DQN_ERR_UNSUPPORTED, "recurrent engine: act through dqn_q_values (carried hidden state)");
+  const int chunk = h->rows_on;
+  for (long long t0 = 0; t0 < n; t0 += chunk) {
+    const int c = (int)std::min<long long>(chunk, n - t0);
+    const uint8_t* src = (const uint8_t*)obs_dev + t0 * rb;
+    if (obs_layout == 1 || !h->hwc) CK(cudaMemcpyAsync(h->xb, src, c * rb, cudaMemcpyDeviceToDevice, h->stream));
+    else relayout(h, src, h->xb, c, h->elem_bytes == 1, 0, 1);
+    const bool tcp = h->arena && h->cfg.math_mode == DQN_MATH_3XTF32 && rb % 16 == 0 && (h->elem_bytes == 4 || h->a8);
+    const float* xs = (h->arena && rb % 16 == 0 && h->elem_bytes == 4) ? (const float*)h->xb : nullptr;
+    const Pass pa{h->theta, h->xb, h->elem_bytes == 1, c, &h->on, "act", xs, h->w_on_s, tcp};
+    forward(h, &pa, 1);
+    Scope sc(h, "act_select", 0, (double)c * (nA + 1) * 4);
+    act_select_kernel<<<(c + 127) / 128, 128, 0, h->stream>>>(h->cfg.dueling ? h->on.tow_out[0][L] : nullptr, h->on.tow_out[h->ntow - 1][L], c, nA, h->cfg.dueling, eps,
+                                                            h->cfg.seed ^ 0xAC7105EEDull, call, (int)t0, actions_dev + t0, q_dev ? q_dev + t0 * nA : nullptr);
+    CK(cudaGetLastError());
+  }
+}
+int dqn_act_device(dqn_engine_t* h, const void* obs_dev, int64_t n, int obs_layout, float eps, uint64_t call, int32_t* actions_dev, float* q_dev) {
+  return guard(h, [&] {
+    if (n < 0 || (n > 0 && (!obs_dev || !actions_dev))) fail(DQN_ERR_INVALID, "null argument");
+    cudaStream_t keep = h->ls; h->ls = h->stream;
+    act_rows(h, obs_dev, n, obs_layout, eps, call, actions_dev, q_dev);
+    h->ls = keep;
+  });
+}
+// the same with host buffers (batched evaluation rollouts, SURVEY 8f row 4: one call acts for every evaluation environment)
+int dqn_act(dqn_engine_t* h, const void* obs, int64_t n, float eps, uint64_t call, int32_t* actions_out, float* q_out) {
+  return guard(h, [&] {
+    if (n < 0 || (n > 0 && (!obs || !actions_out))) fail(DQN_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    const long long rb = h->obs_row_bytes; const int nA = h->cfg.n_actions;
+    ensure_stage(h, n * rb + n * 4 + n * nA * 4 + 256);
+    uint8_t* d_obs = h->stage; int* d_act = (int*)(h->stage + (n * rb + 63) / 64 * 64); float* d_q = (float*)((uint8_t*)d_act + (n * 4 + 63) / 64 * 64);
+    CK(cudaMemcpyAsync(d_obs, obs, n * rb, cudaMemcpyHostToDevice, h->stream));
+    cudaStream_t keep = h->ls; h->ls = h->stream;
+    act_rows(h, d_obs, n, 0, eps, call, d_act, q_out ? d_q : nullptr);
+    h->ls = keep;
+    CK(cudaMemcpyAsync(actions_out, d_act, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (q_out) CK(cudaMemcpyAsync(q_out, d_q, sizeof(float) * n * nA, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+// synthetic vectorised environment for the bench (config 5): lanes' next observations (engine layout), rewards, done flags, |r| - all on the device
+int dqn_synth_env_step(dqn_engine_t* h, void* obs_next_dev, float* rew_dev, uint8_t* done_dev, float* td0_dev, int64_t lanes, uint64_t seed, uint64_t step) {
+  return guard(h, [&] {
+    if (h->elem_bytes != 1 || lanes < 1) fail(DQN_ERR_UNSUPPORTED, "synthetic lanes produce byte observations");
+    const long long words = (h->obs_elems + 15) / 16;
+    synth_env_step_kernel<<<dim3((unsigned)std::min<long long>((words + 255) / 256, 8), (unsigned)lanes), 256, 0, h->stream>>>((uint8_t*)obs_next_dev, rew_dev, done_dev, td0_dev,
+                                                                                                                    h->obs_elems, (int)lanes, seed, step);
+    CK(cudaGetLastError());
+  });
+}
+
 int dqn_timer_start(dqn_engine_t* h) { return guard(h, [&] { CK(cudaEventRecord(h->t0, h->stream)); }); }
 int dqn_timer_stop(dqn_engine_t* h, float* ms) {
   return guard(h, [&] { CK(cudaEventRecord(h->t1, h->stream)); CK(cudaEventSynchronize(h->t1)); CK(cudaEventElapsedTime(ms, h->t0, h->t1)); });

@@ -516,6 +516,48 @@ __global__ void dueling_combine_kernel(const float* __restrict__ V, const float*
   for (int k = 0; k < nA; ++k) q[(long long)r * nA + k] = tmp[k];
 }
 
+// Vectorised acting (SOLVER:83 action(exploration_policy, policy, k, obs) over many lanes; POLICY:38-46 argmax; POMDPTools EpsGreedyPolicy):
+// per row Q = dueling combine, greedy action = FIRST maximal index (Julia argmax); with probability eps a uniform random action instead.
+// Uniforms are counter based - Philox(seed; lane, 0 | 1, call) - so a host restatement reproduces the actions.  Actions are 1-based.
+__global__ void act_select_kernel(const float* __restrict__ V, const float* __restrict__ A, int rows, int nA, int dueling, float eps, uint64_t seed,
+                                  uint64_t call, int lane0, int* __restrict__ actions, float* __restrict__ q_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float q[HEAD_MAX_ACTIONS];
+  dueling_q(V, A, r, nA, dueling, q);
+  int best = 0;
+  for (int k = 1; k < nA; ++k) if (q[k] > q[best]) best = k;
+  if (q_out) for (int k = 0; k < nA; ++k) q_out[(long long)r * nA + k] = q[k];
+  int a = best;
+  if (eps > 0.f && philox_uniform(seed, call, (uint32_t)(lane0 + r), 0u) < eps) {
+    a = (int)__fmul_rn(philox_uniform(seed, call, (uint32_t)(lane0 + r), 1u), (float)nA);
+    if (a >= nA) a = nA - 1;
+  }
+  actions[r] = a + 1;
+}
+
+// Synthetic vectorised environment (bench, config 5 of BASELINE.json): lane i's next observation bytes, reward and done flag are a
+// pure function of (seed, step, lane) - the same generator as the synthetic replay fill, so the lanes feed dqn_replay_add_device
+// without touching the host.  obs_next doubles as the lanes' current observation of the next step.
+__global__ void synth_env_step_kernel(uint8_t* __restrict__ obs_next, float* __restrict__ rew, uint8_t* __restrict__ done, float* __restrict__ td0,
+                                      long long elems, int lanes, uint64_t seed, uint64_t step) {
+  const int lane = blockIdx.y;
+  const long long words = (elems + 15) / 16;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)w, (uint32_t)lane, (uint32_t)step, (uint32_t)(step >> 32) ^ 0x5EEDu};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint8_t* o = obs_next + (long long)lane * elems + w * 16;
+    if ((elems & 15) == 0) *reinterpret_cast<uint4*>(o) = make_uint4(c[0], c[1], c[2], c[3]);
+    else for (int q = 0; q < 16; ++q) { const long long e = w * 16 + q; if (e < elems) o[q] = (uint8_t)(c[q >> 2] >> (8 * (q & 3))); }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t c[4] = {0xFFFFFFFEu, (uint32_t)lane, (uint32_t)step, (uint32_t)(step >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float r = ((float)(c[1] >> 8) * 5.9604644775390625e-08f) * 2.f - 1.f;
+    rew[lane] = r; done[lane] = ((c[2] >> 8) < 167772u) ? 1 : 0; td0[lane] = fabsf(r);
+  }
+}
+
 __global__ void copy_f4_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
 }

@@ -231,6 +231,15 @@ class Engine:
         self._ck(lib.dqn_q_values(self.h, which, vptr(obs), n, ptr(out, C.c_float)))
         return out
 
+    def act(self, obs, eps=0.0, call=0, want_q=False):
+        """epsilon-greedy actions (1-based) for a batch of observations: one forward + argmax + exploration draw on the device"""
+        obs = np.ascontiguousarray(obs, self.obs_np)
+        n = obs.size // self.obs_elems
+        a = np.empty(n, np.int32)
+        q = np.empty((n, self.nA), np.float32) if want_q else None
+        self._ck(lib.dqn_act(self.h, vptr(obs), n, float(eps), int(call), ptr(a, C.c_int32), ptr(q, C.c_float) if want_q else None))
+        return (a, q) if want_q else a
+
     # ---- diagnostics -------------------------------------------------------------------------------
     def last_indices(self):
         out = np.empty(self.B if not self.recurrent else self.B, np.int64)

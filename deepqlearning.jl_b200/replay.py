@@ -68,3 +68,34 @@ class PrioritizedReplayBuffer:
     @property
     def _priorities(self):
         return self.engine.get_priorities()
+
+
+class EpisodeReplayBuffer:
+    """src/episode_replay.jl:3-95 with the episodes resident in HBM.  add_exp! collects the running episode on the host and hands it
+    to the engine when it ends (:52-58); `max_size` counts episodes.  One guard the reference lacks: a running episode that reaches the
+    engine's max_episode_length without `done` is stored as it is (the reference keeps appending across resets)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.max_size = int(engine.cfg.buffer_size)
+        self.batch_size = int(engine.cfg.batch_size)
+        self.trace_length = int(engine.T)
+        self.max_len = int(engine.cfg.max_episode_length or 100)
+        self._episode = []
+
+    @property
+    def _curr_size(self):
+        return self.engine.episode_count()[0]
+
+    def is_full(self):
+        return self._curr_size == self.max_size
+
+    def add_exp(self, expe, td_err=None):
+        self._episode.append(expe)
+        if expe.done or len(self._episode) >= self.max_len:
+            self.add_episode(self._episode)
+            self._episode = []
+
+    def add_episode(self, ep):
+        self.engine.episode_add(np.stack([np.asarray(e.s, np.float32) for e in ep]), [e.a for e in ep], [e.r for e in ep],
+                                np.stack([np.asarray(e.sp, np.float32) for e in ep]), [e.done for e in ep])

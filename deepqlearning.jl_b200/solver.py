@@ -14,7 +14,7 @@ import numpy as np
 from . import _capi
 from .engine import Engine, make_config
 from .flux import Chain, DuelingNetwork, create_dueling_network, flat_params, load_flat_params, isrecurrent
-from .replay import PrioritizedReplayBuffer, DQExperience
+from .replay import PrioritizedReplayBuffer, EpisodeReplayBuffer, DQExperience
 
 
 # ---- POMDPTools stand-ins used by the reference's call sites (src/solver.jl:83,155) -----------------
@@ -63,7 +63,9 @@ def getnetwork(policy):
 
 
 def resetstate(policy):
-    pass                                                       # Flux.reset! is a no-op without recurrent layers
+    """src/policy.jl:32-34: Flux.reset!(policy.qnetwork) - the acting hidden state of a recurrent engine goes back to state0"""
+    if policy.engine is not None and policy.engine.recurrent:
+        policy.engine.policy_reset()
 
 
 def action(policy, o):                                         # src/policy.jl:38-46: first maximal index
@@ -97,6 +99,34 @@ def basic_evaluation(policy, env, n_eval, max_episode_length, verbose):
     if verbose:
         print("Evaluation ... Avg Reward %2.2f | Avg Step %2.2f " % (avg_r / n_eval, avg_steps / n_eval))
     return avg_r / n_eval, avg_steps / n_eval, {}
+
+
+def batched_evaluation(policy, env, n_eval, max_episode_length, verbose, make_env=None):
+    """basic_evaluation (src/evaluation_policy.jl:17-42) over n_eval copies of the environment stepped in lockstep: ONE device call
+    (dqn_act: forward + argmax on the GPU) picks the action of every running episode per step instead of one batch-1 forward per
+    environment step.  Same episode accounting as the reference (`step <= max_episode_length`); deterministic environments give the
+    same averages as basic_evaluation."""
+    import copy
+    envs = [make_env() if make_env else copy.deepcopy(env) for _ in range(n_eval)]
+    for e in envs:
+        e.reset()
+    resetstate(policy)
+    r_tot = np.zeros(n_eval); steps = np.zeros(n_eval, np.int64)
+    running = np.array([not e.terminated() for e in envs])
+    call = 0
+    while running.any():
+        live = np.nonzero(running)[0]
+        obs = np.stack([np.asarray(envs[i].observe()) for i in live])
+        acts = policy.engine.act(obs, eps=0.0, call=call)
+        call += 1
+        for i, ai in zip(live, acts):
+            r_tot[i] += envs[i].act(policy.action_map[int(ai) - 1])
+            steps[i] += 1
+            if envs[i].terminated() or steps[i] > max_episode_length:
+                running[i] = False
+    if verbose:
+        print("Evaluation ... Avg Reward %2.2f | Avg Step %2.2f " % (r_tot.mean(), steps.mean()))
+    return float(r_tot.mean()), float(steps.mean()), {}
 
 
 # ---- src/solver.jl:1-28 ----------------------------------------------------------------------------
@@ -166,10 +196,39 @@ def populate_replay_buffer(replay, env, action_indices, max_pop=None, max_steps=
     assert replay._curr_size >= replay.batch_size
 
 
+def generate_episode(env, action_indices, max_steps=100, rng=None):
+    """src/episode_replay.jl:108-130 (random policy)"""
+    rng = rng or np.random.default_rng()
+    acts = list(env.actions())
+    episode = []
+    env.reset()
+    o = env.observe()
+    done, step = False, 1
+    while not done and step < max_steps:
+        a = acts[int(rng.integers(len(acts)))]
+        rew = env.act(a)
+        op = env.observe()
+        done = env.terminated()
+        episode.append(DQExperience(np.asarray(o), action_indices[a], np.float32(rew), np.asarray(op), done))
+        o = op
+        step += 1
+    return episode
+
+
+def populate_episode_buffer(replay, env, action_indices, max_pop=None, max_steps=100, rng=None):
+    """src/episode_replay.jl:97-106"""
+    max_pop = replay.max_size if max_pop is None else max_pop
+    for _ in range(max_pop - replay._curr_size):
+        replay.add_episode(generate_episode(env, action_indices, max_steps=min(max_steps, replay.max_len + 1), rng=rng))
+    assert replay._curr_size >= replay.batch_size
+
+
 def initialize_replay_buffer(solver, env, action_indices, engine):
     """src/solver.jl:180-189."""
     if solver.recurrence:
-        raise NotImplementedError("EpisodeReplayBuffer / recurrent batch_train! is a later row of the scope table (SURVEY 8f)")
+        replay = EpisodeReplayBuffer(engine)                      # src/solver.jl:183-184
+        populate_episode_buffer(replay, env, action_indices, max_pop=solver.train_start, rng=solver.rng)
+        return replay
     replay = PrioritizedReplayBuffer(engine)                  # alpha, beta, eps: the constructor defaults (PER.jl:43-45)
     populate_replay_buffer(replay, env, action_indices, max_pop=solver.train_start, rng=solver.rng)
     return replay
@@ -192,7 +251,9 @@ def solve(solver, env):
     cfg = make_config(_chain_layers(solver.qnetwork), flux_shape, len(action_map), obs_dtype=solver.obs_dtype,
                       dueling=solver.dueling, double_q=solver.double_q, prioritized_replay=solver.prioritized_replay,
                       batch_size=solver.batch_size, buffer_size=solver.buffer_size, learning_rate=solver.learning_rate,
-                      discount=default_discount(env), seed=solver.seed, device=solver.device, math_mode=solver.math_mode)
+                      discount=default_discount(env), seed=solver.seed, device=solver.device, math_mode=solver.math_mode,
+                      trace_length=solver.trace_length if solver.recurrence else 0,
+                      max_episode_length=solver.max_episode_length if solver.recurrence else 0, max_act_rows=max(2 * solver.batch_size, 128))
     engine = Engine(cfg)
     engine.set_params(flat_params(active_q))
     replay = initialize_replay_buffer(solver, env, action_indices, engine)
@@ -239,7 +300,10 @@ def dqn_train(solver, env, policy, replay):
         op = env.observe()
         done = env.terminated()
         exp = DQExperience(np.asarray(obs), ai, np.float32(rew), np.asarray(op), done)
-        replay.add_exp(exp, abs(exp.r) if solver.prioritized_replay else np.float32(0))     # :91-95
+        if solver.recurrence:
+            replay.add_exp(exp)                                                             # :89-90
+        else:
+            replay.add_exp(exp, abs(exp.r) if solver.prioritized_replay else np.float32(0))     # :91-95
         obs = op
         step += 1
         episode_rewards[-1] += rew

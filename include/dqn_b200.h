@@ -165,6 +165,16 @@ int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm);              /* wa
 /* ---- acting: policy.qnetwork(obatch) (POLICY:38-64, SOLVER:83) ------------------------------------ */
 int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* q_out);   /* q_out (n, n_actions) row-major == (|A|, n) column-major */
 
+/* vectorised acting (SOLVER:83 action(exploration_policy, policy, k, obs) for n lanes; POLICY:38-46): forward + dueling combine + first-max
+ * argmax + epsilon-greedy draw on the device.  Uniforms: Philox(seed ^ 0xAC7105EED; lane, {0, 1}, call): lane i explores iff u0 < eps and
+ * then takes action 1 + floor(u1 * n_actions).  Actions are 1-based Int32.  _device: obs / actions / q are DEVICE pointers; obs_layout
+ * 0 = Flux layout per lane (C,H,W), 1 = the engine's H,W,C layout (what dqn_replay_add_device stores).  q may be NULL. */
+int dqn_act(dqn_engine_t* h, const void* obs, int64_t n, float eps, uint64_t call, int32_t* actions_out, float* q_out);
+int dqn_act_device(dqn_engine_t* h, const void* obs_dev, int64_t n, int obs_layout, float eps, uint64_t call, int32_t* actions_dev, float* q_dev);
+/* synthetic vectorised environment step for the bench (BASELINE.json configs[4]): next observations (uint8, engine layout), rewards,
+ * done flags and |r| of `lanes` lanes as a pure function of (seed, step, lane), written to device buffers */
+int dqn_synth_env_step(dqn_engine_t* h, void* obs_next_dev, float* rew_dev, uint8_t* done_dev, float* td0_dev, int64_t lanes, uint64_t seed, uint64_t step);
+
 /* ---- diagnostics of the last step (parity tests) -------------------------------------------------- */
 int dqn_get_last_indices(dqn_engine_t* h, int64_t* idx_out);
 int dqn_get_td(dqn_engine_t* h, float* td_out);                  /* td_vals SOLVER:222 */

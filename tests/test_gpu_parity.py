@@ -369,7 +369,8 @@ def test_tc_selftest():
 
 
 def test_env_switches_keep_parity(lib):
-    """Schedule variants (merged online+target launches, single lane, tiled heads instead of the warp-per-row kernel) compute the same step."""
+    """Schedule / kernel variants (merged online+target launches, single lane, tiled heads instead of the warp-per-row kernel, cp.async
+    instead of the TMA feed, the generic kernel instead of the dedicated first-layer kernel, TMA-fed weight gradients) compute the same step."""
     import subprocess, sys
     code = ("import sys,os; sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests'); import numpy as np, dqn_b200 as lib, util, oracle as O;"
             "spec=util.SPECS['c3_conv']; net=util.make_oracle_net(spec, True, seed=21);"
@@ -379,14 +380,14 @@ def test_env_switches_keep_parity(lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     for tag, env in (("default", {}), ("merge", {"DQN_MERGE_FWD": "1"}), ("one_lane", {"DQN_STREAMS": "0"}), ("tiled_heads", {"DQN_FUSE_HEADS": "0"}), ("no_a8", {"DQN_NO_A8": "1"}),
-                     ("tail_split", {"DQN_TC_TAIL": "1"})):
+                     ("tail_split", {"DQN_TC_TAIL": "1"}), ("cp_async_feed", {"DQN_TC_TMA": "0"}), ("generic_conv1", {"DQN_TC_C1": "0"}), ("tma_wgrad", {"DQN_TC_TMA_WGRAD": "1"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, **env})
         line = [x for x in r.stdout.splitlines() if x.startswith("RES")]
         assert line, (tag, r.stdout[-500:], r.stderr[-1500:])
         outs[tag] = [float(x) for x in line[0].split()[1:]]
     ref = outs["default"]
-    assert outs["one_lane"] == ref and outs["no_a8"] == ref, outs          # same kernels, same order of operations: bit-identical
-    for tag in ("merge", "tiled_heads", "tail_split"):                      # different summation order in a few contractions
+    assert outs["one_lane"] == ref, outs                                    # same kernels, same order of operations: bit-identical
+    for tag in ("merge", "tiled_heads", "tail_split", "no_a8", "cp_async_feed", "generic_conv1", "tma_wgrad"):   # different summation order in a few contractions
         for a, b in zip(outs[tag], ref):
             assert abs(a - b) <= 2e-5 * abs(b), (tag, outs)
 
