@@ -46,7 +46,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.dev)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.dev)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -107,6 +107,120 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+MATH_LABEL = {"fp32": "fp32 (CUDA-core FMA)", "3xtf32": "3xtf32 (tcgen05 kind::tf32, 3-pass split)"}
+
+
+def resolve_math(args):
+    """both arms print the same `config`: 'auto' is the engine's benchmarked mode"""
+    key = "3xtf32" if args.math in ("auto", "3xtf32") or args.math.startswith("3xtf32") else "fp32"
+    args.math_key = key
+    args.math = MATH_LABEL[key]
+
+
+def drqn_config(args):
+    return {"workload": "BASELINE.json configs[3]: recurrent DRQN, Chain(flattenbatch, LSTM(128,128), Dense(128,16)) + dueling, double-Q, "
+                        "EpisodeReplayBuffer of 1000 synthetic episodes (32..100 steps of dim-128 Float32 observations), trace_length 32, batch 64",
+            "batch_per_gpu": 64, "trace_length": 32, "parallelism": "dp1",
+            "l2": "latency-bound by nature (32 sequential LSTM steps per pass); working set far below L2", "math": args.math}
+
+
+def run_drqn(args):
+    """configs[3]: the recurrent batch_train! (src/solver.jl:239-287).  Device-resident steps/s, end-to-end steps/s (one whole episode added
+    from pinned host memory per 8 steps + the scalars read back), and the CPU restatement (oracle/recurrent.py, numpy) beside it."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    d, H, nA, T, B, cap, L = 128, 128, 16, 32, 64, 1000, 100
+    rng = np.random.default_rng(11)
+    import oracle as O
+    if args.impl == "reference":
+        net = O.make_recurrent_q(d, H, [(H, nA, 0)], True, rng); tgt = O.make_recurrent_q(d, H, [(H, nA, 0)], True, rng)
+        s = rng.normal(size=(T, B, d)).astype(np.float32); sp = rng.normal(size=(T, B, d)).astype(np.float32)
+        a = rng.integers(1, nA + 1, (T, B)).astype(np.int32); r = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+        done = np.zeros((T, B), np.float32); mask = np.ones((T, B), np.int32)
+        opt = O.Adam(1e-4)
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter(); O.batch_train_recurrent(net, tgt, opt, (s, a, r, sp, done, mask), 0.99, True); ts.append(time.perf_counter() - t0)
+        total = float(np.sum(ts[args.warmup:])); v = args.steps / total
+        print(json.dumps({"impl": "reference", "metric": "drqn_gradient_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": drqn_config(args), "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                                                        "sample": f"{args.steps} full recurrent steps, numpy restatement (oracle/recurrent.py)"},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import dqn_b200 as lib
+    layers = [dict(kind=2, act=0, in_=0, out=0), dict(kind=3, act=0, in_=d, out=H), dict(kind=0, act=0, in_=H, out=nA)]
+    math_mode = lib.MATH_3XTF32 if args.math_key == "3xtf32" else lib.MATH_FP32
+    cfg = lib.make_config(layers, (d,), nA, obs_dtype="f32", dueling=True, double_q=True, prioritized_replay=False, batch_size=B, buffer_size=cap,
+                          learning_rate=1e-4, discount=0.99, seed=2, math_mode=math_mode, use_graph=not args.no_graph, trace_length=T, max_episode_length=L)
+    eng = lib.Engine(cfg)
+    net = O.make_recurrent_q(d, H, [(H, nA, 0)], True, rng)
+    eng.set_params(np.concatenate([p.ravel() for p in net.params()]), 0)
+    eng.sync_target()
+    eps = []
+    for _ in range(cap):
+        n = int(rng.integers(32, L + 1))
+        ep = (rng.normal(size=(n, d)).astype(np.float32), rng.integers(1, nA + 1, n).astype(np.int32), rng.uniform(-1, 1, n).astype(np.float32),
+              rng.normal(size=(n, d)).astype(np.float32), np.r_[np.zeros(n - 1), 1].astype(np.uint8))
+        eng.episode_add(*ep)
+        if len(eps) < 16:
+            eps.append(ep)
+    for _ in range(args.warmup):
+        eng.train_step_async()
+    eng.sync()
+    clocks = ClockSampler(0); clocks.start()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.train_step_async()
+    ms = eng.timer_stop()
+    loss, gn = eng.sync()
+    value = args.steps / (ms * 1e-3)
+    h2d = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if i % 8 == 0:
+            ep = eps[(i // 8) % len(eps)]
+            eng.episode_add(*ep)
+            h2d += sum(x.nbytes for x in ep)
+        loss, gn = eng.train_step()
+    e2e = args.steps / (time.perf_counter() - t0)
+    clk = clocks.stop()
+    eng.set_profiling(1)
+    for _ in range(5):
+        eng.train_step_async()
+    eng.sync()
+    prof = eng.get_profile()
+    eng.set_profiling(0)
+    tot = sum(k["ms"] * k["count"] / 5 for k in prof)
+    kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "launches_per_step": k["count"] // 5, "share": round(k["ms"] * k["count"] / 5 / tot, 4)}
+               for k in sorted(prof, key=lambda k: -k["ms"] * k["count"])][:10]
+    cpu = None
+    if not args.no_cpu:
+        tgt = O.make_recurrent_q(d, H, [(H, nA, 0)], True, rng)
+        s = rng.normal(size=(T, B, d)).astype(np.float32); sp = rng.normal(size=(T, B, d)).astype(np.float32)
+        a = rng.integers(1, nA + 1, (T, B)).astype(np.int32); r = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+        opt = O.Adam(1e-4)
+        ts = []
+        for i in range(2 + min(args.cpu_steps, 20)):
+            t1 = time.perf_counter(); O.batch_train_recurrent(net, tgt, opt, (s, a, r, sp, np.zeros((T, B), np.float32), np.ones((T, B), np.int32)), 0.99, True)
+            ts.append(time.perf_counter() - t1)
+        cpu = {"value": 1.0 / float(np.median(ts[2:])), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"median of {len(ts) - 2} full recurrent steps, numpy restatement (oracle/recurrent.py), BLAS threads as available"}
+    lstm = [k for k in prof if k["name"].startswith("lstm_step") or k["name"] == "lstm_bptt_step"]
+    seq_ms = sum(k["ms"] * k["count"] / 5 for k in lstm)
+    print(json.dumps({"metric": "drqn_gradient_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": drqn_config(args),
+                      "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": 8,
+                              "what": "per step: batch_train! + (loss, grad_norm) read back; one whole episode added from host memory every 8 steps; wall clock"},
+                      "gpu_launches": eng.launches_per_step() * args.steps, "clocks": clk,
+                      "roofline": {"kernel": "lstm_step_* (sequential recurrence)", "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                                   "note": f"{seq_ms:.3f} ms of the eager step are the 3 x 32 dependent recurrence launches; no HBM or tensor roofline applies (SURVEY 8d: C4 is latency-bound)"},
+                      "cpu_baseline": cpu, "kernels": kernels, "last_loss": loss, "last_grad_norm": gn}))
+    eng.close()
+
+
 def workload_config(args, world):
     return {"workload": "BASELINE.json configs[2]: synthetic Atari-shaped obs 84x84x4 (u8), Nature-DQN conv + dueling, |A|=6, batch 256/GPU, "
                         f"{args.buffer}-transition PER shard/GPU, double-Q, Adam lr 1e-4",
@@ -127,8 +241,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
+    ap.add_argument("--workload", default="conv", choices=["conv", "drqn"],
+                    help="conv: BASELINE.json configs[2] (the headline, default); drqn: configs[3] (LSTM-128, seq 32, batch 64)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    resolve_math(args)
+    if args.workload == "drqn":
+        return run_drqn(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -142,8 +261,7 @@ def main():
     if world > 1:
         nccl_id = cp.broadcast_bytes(lib.nccl_unique_id() if rank == 0 else None, 128)
     seeds = lib.shard_seeds(0, rank)
-    math_mode = {"auto": lib.MATH_3XTF32, "fp32": lib.MATH_FP32, "3xtf32": lib.MATH_3XTF32}[args.math]
-    args.math = "3xtf32 (tcgen05 kind::tf32, 3-pass split)" if math_mode == lib.MATH_3XTF32 else "fp32 (CUDA-core FMA)"
+    math_mode = lib.MATH_3XTF32 if args.math_key == "3xtf32" else lib.MATH_FP32
     cfg = lib.make_config(util.layer_descs(spec), (84, 84, 4), 6, obs_dtype="u8", batch_size=256, buffer_size=args.buffer, learning_rate=1e-4,
                           discount=0.99, seed=seeds["sampler"], device=local, math_mode=math_mode, use_graph=not args.no_graph, rank=rank, world=world, nccl_id=nccl_id)
     eng = lib.Engine(cfg)
@@ -170,12 +288,12 @@ def main():
     ms = eng.timer_stop()
     loss, gn = eng.sync()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     ms = cp.max_over_ranks(ms)
     launches = eng.launches_per_step() * args.steps
     value = world * args.steps / (ms * 1e-3)
     if args.quick:
         if rank == 0:
+            clocks.stop()
             print(json.dumps({"quick": True, "value": value, "ms_per_step": ms / args.steps, "n_gpus": world, "env": {k: v for k, v in os.environ.items() if k.startswith("DQN_")}, "loss": loss}))
         eng.close()
         cp.close()
@@ -202,6 +320,7 @@ def main():
         eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
         loss, gn = eng.train_step()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None                  # sampled every 10 ms over the device-timed region and the end-to-end region
     e2e_s = cp.max_over_ranks(e2e_s)
     e2e = world * args.steps / e2e_s
 
@@ -233,7 +352,14 @@ def main():
                     "peak_note": f"{peaks['src']} HBM copy bandwidth"}
         step_flops = 26.36e9
         roof["step_tflops_algorithmic"] = step_flops * (args.steps / (ms * 1e-3)) / 1e12
-        roof["traffic_source"] = traffic.get("_file")
+        roof["traffic_source"] = (traffic.get("_file") or "") + ("@" + str(traffic.get("_commit")) if traffic.get("_commit") else "")
+        coll = [k for k in prof if k["name"] == "nccl_allreduce"]
+        if coll:                                                    # a collective is measured against NVLink, not HBM: bus bandwidth of a ring all-reduce
+            b = sum(k["bytes"] for k in coll) / 2.0                 # payload bytes (the Scope records 2 x payload)
+            t = sum(k["ms"] for k in coll) * 1e-3
+            busbw = b * 2.0 * (world - 1) / world / t / 1e9
+            roof["collective"] = {"kernel": "nccl_allreduce", "payload_bytes": b, "busbw": busbw, "peak": 770.0, "unit": "GB/s", "frac": busbw / 770.0,
+                                  "peak_note": "measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)"}
         # the HBM-bound kernels of the step, against the measured copy bandwidth (algorithmic bytes of DESIGN.md section 2)
         roof["hbm_kernels"] = [{"kernel": k["name"], "achieved": k["bytes"] / (k["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                                 "frac": k["bytes"] / (k["ms"] * 1e-3) / 1e9 / peaks["hbm"], "traffic": traffic.get(k["name"], {}).get("dram_bytes")}

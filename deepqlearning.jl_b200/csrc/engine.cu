@@ -146,7 +146,8 @@ struct dqn_engine {
   float* xb_f = nullptr;
   float *w_on_s = nullptr, *w_tg_s = nullptr, *ones = nullptr;
   long long w_scale_lo = 0, w_scale_hi = 0;
-  int tc_split = 0; int tc_tail = 0; int tc_tma = 1; int tc_c1 = 1; int tc_tma_wgrad = 0;
+  int tc_split = 0; int tc_tail = 0; int tc_tma = 1; int tc_c1 = 1; int tc_tma_wgrad = 0; int dgrad_merge = 1;
+  float* wm[DQN_MAX_LAYERS] = {};   // per strided conv layer: weights rearranged for the class-merged dgrad (ConvDgradMergedOp)
   float* colsum_part = nullptr; unsigned int* colsum_ticket = nullptr;
   bool towers_updated = false;
   // recurrent engines (one LSTM as the trunk, SOLVER:239-287): the network batch is trace_length * batch_size rows, time-major
@@ -333,6 +334,19 @@ void forward(E* e, const Pass* ps, int np) {
 
 void enqueue_adam(E* e, long long lo, long long hi, cudaStream_t s);
 
+// rearranged weight copies of the strided conv layers for the class-merged input gradient: the online weights do not change inside a
+// step, so this runs early on the target lane, off the critical path
+void prepare_dgrad_weights(E* e) {
+  if (!e->arena || !e->dgrad_merge || e->cfg.math_mode != DQN_MATH_3XTF32) return;
+  for (size_t l = 1; l < e->convs.size(); ++l) {
+    const ConvL& c = e->convs[l];
+    if (!e->wm[l] || !ConvDgradMergedOp::geometry_ok(c.g)) continue;
+    Scope sc(e, "dgrad_merge_weights", 0, 8.0 * c.w.K * c.g.Cout);
+    dgrad_merge_weights_kernel<<<64, 256, 0, e->ls>>>(e->theta + c.w.off, e->wm[l], c.g.KH, c.g.KW, c.g.S, c.g.Cin, c.g.Cout);
+    CK(cudaGetLastError());
+  }
+}
+
 void backward(E* e, bool conc) {
   const int B = e->B;
   char nm[64];
@@ -488,6 +502,14 @@ void backward(E* e, bool conc) {
       snprintf(nm, sizeof nm, "conv%d_dgrad", l + 1);
       fl = 2.0 * B * c.g.OH * c.g.OW * c.g.Cout * c.w.K;
       by = 4.0 * ((double)B * c.g.OH * c.g.OW * c.g.Cout + (double)c.w.K * c.g.Cout + 2.0 * B * c.g.IH * c.g.IW * c.g.Cin);
+      // strided layers: the S*S parity classes share their source pixels - one contraction over a rearranged copy of the weights
+      if (e->arena && e->dgrad_merge && e->cfg.math_mode == DQN_MATH_3XTF32 && ConvDgradMergedOp::geometry_ok(c.g) && e->wm[l]) {
+        ConvDgradMergedOp mg{};                                  // (its weight copy wm[l] was rebuilt on the target lane, prepare_dgrad_weights)
+        mg.D = e->conv_delta[l]; mg.Wm = e->wm[l]; mg.dX = e->conv_delta[l - 1]; mg.Yprev = e->on.conv_out[l - 1]; mg.act = e->convs[l - 1].w.act; mg.apply_act = 1;
+        mg.nimg = B; mg.g = c.g; mg.vecA = mg.vecB = 1; mg.Ds = mg.D; mg.Ws = mg.Wm; mg.a_single = 0;
+        mg.init();
+        if (tc_conv_dgrad_merged(e, nm, mg, fl, by)) continue;
+      }
       if (!tc_conv_dgrad(e, nm, dg, fl, by)) launch_igemm(e, nm, dg, dg, c.g.S * c.g.S, false, fl, by);
     }
   }
@@ -687,11 +709,13 @@ void enqueue_step(E* e, bool sample) {
   const Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s, tcp};
   if (tcp && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
     const Pass both[2] = {p_on, p_tg};
+    prepare_dgrad_weights(e);
     forward(e, both, 2);
   } else {
     if (conc) order_after(e, e->stream2, e->stream);          // fork: the gathered batch is ready
     {
       Lane lane(e, conc);
+      prepare_dgrad_weights(e);
       forward(e, &p_tg, 1);
     }
     forward(e, &p_on, 1);

@@ -604,6 +604,96 @@ struct ConvDgradOp {
   }
 };
 
+
+// Conv dgrad with the stride-parity classes MERGED into the column dimension (S > 1, KH, KW, IH, IW multiples of S): every class
+// (ph,pw) reads the same source pixels delta[n][a - th][b - tw][:] for its row (n, a, b) - so one contraction with
+//   rows    m  = (n, a, b), a < IH/S, b < IW/S                     (one row per S x S block of input pixels)
+//   k          = (th, tw, co), th < KH/S, tw < KW/S
+//   columns n' = (ph, pw, ci):  dX[n][S a + ph][S b + pw][ci] = sum_k A(m,k) Wm[k][n'],  Wm[k][n'] = W[ph + S th][pw + S tw][ci][co]
+// loads and splits the delta operand ONCE instead of S*S times and has S*S*Cin columns (conv2 of the Nature network: 128 instead of
+// 4 launches' worth of 32).  Wm is a rearranged copy of the layer's weights, rebuilt by dgrad_merge_weights_kernel before the launch.
+struct ConvDgradMergedOp {
+  static constexpr bool HAS_A8 = false;
+  static constexpr bool A_MCONTIG = false, B_KCONTIG = false, Z_IS_CLASS = false;
+  const float* D; const float* Wm; float* dX; const float* Yprev; int act; int apply_act; int nimg; ConvGeom g;
+  int AH, BW, TH, TW;
+  FastDiv fbw, fah, ftw, fcin;
+  int M, N, K;               // M = nimg*AH*BW, N = S*S*Cin, K = TH*TW*Cout
+  int vecA, vecB;
+  const float* Ds; const float* Ws; long long lo_delta; int a_single;     // Ws = Wm for the tensor-core path
+  void init() {
+    AH = g.IH / g.S; BW = g.IW / g.S; TH = g.KH / g.S; TW = g.KW / g.S;
+    fbw.init(BW); fah.init(AH); ftw.init(TW); fcin.init(g.Cin);
+    M = nimg * AH * BW; N = g.S * g.S * g.Cin; K = TH * TW * g.Cout;
+  }
+  static bool geometry_ok(const ConvGeom& g) {
+    return g.S > 1 && g.S <= 4 && g.KH % g.S == 0 && g.KW % g.S == 0 && g.IH % g.S == 0 && g.IW % g.S == 0 && g.Cin % 4 == 0 && g.Cout % 4 == 0 &&
+           (g.IH / g.S) == g.OH + g.KH / g.S - 1 && (g.IW / g.S) == g.OW + g.KW / g.S - 1;
+  }
+  DQN_HD bool tc_ready() const { return Ds && Ws && (g.Cout % 4 == 0) && (N % 4 == 0); }
+  DQN_HD bool tap_ok(const ACtx& c, const KCtx& kc) const { return (unsigned)(c.i0 - kc.t0) < (unsigned)g.OH && (unsigned)(c.i1 - kc.t1) < (unsigned)g.OW; }
+  DQN_HD const float* ptrA(const ACtx& c, const KCtx& kc, int, int k) const { return (c.valid && k < K && tap_ok(c, kc)) ? Ds + c.base + kc.off : nullptr; }
+  DQN_HD const float* ptrB(const KCtx&, int k, int n) const { return (k < K && n < N) ? Ws + (long long)k * N + n : nullptr; }
+  DQN_HD bool interiorA(int, int, int, int) const { return false; }
+  DQN_HD bool interiorB(int n0, int k0, int bn, int bk) const { return n0 + bn <= N && k0 + bk <= K; }
+  DQN_HD const float* ptrA_u(const ACtx& c, const KCtx& kc, int, int) const { return Ds + c.base + kc.off; }
+  DQN_HD const float* ptrB_u(const KCtx&, int k, int n) const { return Ws + ((long long)k * N + n); }
+  DQN_HD void set_class(int) {}
+  DQN_HD ACtx prepA(int m) const {
+    ACtx c; c.valid = m < M; c.base = 0; c.i0 = c.i1 = 0;
+    if (c.valid) {
+      uint32_t t, b, n, a; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, n, a); c.i0 = (int)a; c.i1 = (int)b;
+      c.base = (((long long)n * g.OH + (int)a) * g.OW + (int)b) * g.Cout;
+    }
+    return c;
+  }
+  DQN_HD KCtx prepK(int k) const {
+    KCtx c; c.off = 0; c.offb = 0; c.t0 = c.t1 = c.t2 = 0;
+    if (k < K) {
+      uint32_t t, co, th, tw; g.fCout.divmod((uint32_t)k, t, co); ftw.divmod(t, th, tw); c.t0 = (int)th; c.t1 = (int)tw; c.t2 = (int)co;
+      c.off = (long long)(int)co - (long long)((int)th * g.OW + (int)tw) * g.Cout;
+    }
+    return c;
+  }
+  DQN_HD float4 loadA(const ACtx& c, const KCtx& kc, int, int k) const {
+    if (!c.valid || k >= K || !tap_ok(c, kc)) return make4(0, 0, 0, 0);
+    return ldg4(D + c.base + kc.off);
+  }
+  DQN_HD float4 loadB(const KCtx&, int k, int n) const {
+    if (k >= K || n >= N) return make4(0, 0, 0, 0);
+    return ldg4(Wm + (long long)k * N + n);
+  }
+  DQN_HD long long out_off(int m, int n) const {
+    uint32_t t, b, img, a, cls, ci; fbw.divmod((uint32_t)m, t, b); fah.divmod(t, img, a); fcin.divmod((uint32_t)n, cls, ci);
+    const int ph = (int)cls / g.S, pw = (int)cls - ph * g.S;
+    return (((long long)img * g.IH + a * g.S + ph) * g.IW + b * g.S + pw) * g.Cin + ci;
+  }
+  DQN_HD void store(int m, int n, float v) const {
+    const long long o = out_off(m, n);
+    if (apply_act) v *= act_deriv(Yprev[o], act);
+    dX[o] = v;
+  }
+  DQN_HD bool can_store4() const { return g.Cin % 4 == 0; }
+  DQN_HD void store4(int m, int n, float4 v) const { store4x(m, n, v, epi_aux4(m, n)); }
+  DQN_HD float4 epi_aux4(int m, int n) const { return apply_act ? ldg4(Yprev + out_off(m, n)) : make4(1.f, 1.f, 1.f, 1.f); }
+  DQN_HD void store4x(int m, int n, float4 v, const float4& y) const {
+    if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
+    *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
+  }
+};
+#ifdef __CUDACC__
+// Wm[(th*TW + tw)*Cout + co][(ph*S + pw)*Cin + ci] = W[(ph + S th)*KW + (pw + S tw)][ci][co]   (W: [(kh,kw)][Cin][Cout])
+__global__ void dgrad_merge_weights_kernel(const float* __restrict__ W, float* __restrict__ Wm, int KH, int KW, int S, int Cin, int Cout) {
+  const int TH = KH / S, TW = KW / S, N = S * S * Cin, K = TH * TW * Cout;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)K * N; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e % N), k = (int)(e / N);
+    const int ci = n % Cin, cls = n / Cin, ph = cls / S, pw = cls % S;
+    const int co = k % Cout, tap = k / Cout, th = tap / TW, tw = tap % TW;
+    Wm[e] = W[((long long)((ph + S * th) * KW + (pw + S * tw)) * Cin + ci) * Cout + co];
+  }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // The tiled kernel.  256 threads, BK = 16, register-staged double buffering (one barrier per k-tile).
 constexpr int IGEMM_THREADS = 256;

@@ -12,6 +12,7 @@ bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* op
 bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double flops, double bytes);
 bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double flops, double bytes);
 bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double flops, double bytes);
+bool tc_conv_dgrad_merged(dqn_engine* e, const char* name, const dqn::ConvDgradMergedOp& op, double flops, double bytes);
 bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double flops, double bytes);
 void tc_init(dqn_engine* e);
 void tc_destroy(dqn_engine* e);

@@ -58,7 +58,7 @@ __device__ long long tc_trace[16384];    // per-stage timestamps of CTA 0 (produ
 //               halo), tap = the 16-bit offsets; B = one tap's [Cin][Cout] slab of the weights through a 3-D map {Cout, Cin, tap}
 //   conv wgrad  A = x^T: four im2col boxes of 32 pixels x 32 channels per stage (one per 32 rows of the m tile), no swizzle
 // Out-of-range rows / columns are zero-filled by the TMA unit: no edge-tile code in the producer.
-enum { TMA_DENSE_FWD = 0, TMA_DENSE_DGRAD = 1, TMA_DENSE_WGRAD = 2, TMA_CONV_FWD = 3, TMA_CONV_DGRAD = 4, TMA_CONV_WGRAD = 5 };
+enum { TMA_DENSE_FWD = 0, TMA_DENSE_DGRAD = 1, TMA_DENSE_WGRAD = 2, TMA_CONV_FWD = 3, TMA_CONV_DGRAD = 4, TMA_CONV_WGRAD = 5, TMA_CONV_DGRAD_MERGED = 6 };
 struct TmaMaps {
   CUtensorMap a[4];              // per operand set; dgrad: per k segment (tower)
   CUtensorMap b[4];
@@ -448,7 +448,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         Op op; int m0, n0, zs, kt0, nk;
         if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
-        const int zi = Op::Z_IS_CLASS ? 0 : min(zs / nsplit, 3);
+        const int zi = (Op::Z_IS_CLASS || (tail_s > 1 && t >= tail_t0)) ? 0 : min(zs / nsplit, 3);   // (tail tiles: zs is their k range, one operand set)
         int pw = 0, ph_ = 0, pn = 0;                             // conv forward: first output pixel of the tile -> (ow, oh, image)
         if (tmaps.kind == TMA_CONV_FWD) { pw = m0 % tmaps.ow; const int q = m0 / tmaps.ow; ph_ = q % tmaps.oh; pn = q / tmaps.oh; }
         for (int it = 0; it < nk; ++it) {
@@ -494,6 +494,12 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
                 const int khh = op.ph + th * tmaps.stride, kww = op.pw + tw * tmaps.stride;
                 tma_load_3d(b_hi, &tmaps.b[0], c0, n0, khh * tmaps.kw + kww, bar);
               }
+            } else if (tmaps.kind == TMA_CONV_DGRAD_MERGED) {
+              // rows (n, a, b) over the AH x BW blocks, k = (th, tw, co): the class-wise correlation with every class's columns side by side
+              const int bq = m0 % tmaps.ow, q = m0 / tmaps.ow, aq = q % tmaps.oh, nq = q / tmaps.oh;          // (ow, oh hold BW, AH here)
+              const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;   // (kw holds TW, ntaps TH)
+              tma_load_im2col_4d(a_st, &tmaps.a[0], c0, bq - (tmaps.kw - 1), aq - (tmaps.ntaps - 1), nq, tmaps.kw - 1 - tw, tmaps.ntaps - 1 - th, bar);
+              tma_load_3d(b_hi, &tmaps.b[0], 0, k0, n0 >> 5, bar);
             } else {                                             // conv wgrad: k = output pixel, m = (tap, channel)
               const int pw2 = k0 % tmaps.ow, q2 = k0 / tmaps.ow, ph2 = q2 % tmaps.oh, pn2 = q2 / tmaps.oh;
 #pragma unroll
@@ -930,6 +936,10 @@ struct TmaApi {
   }
 };
 inline TmaApi& tma_api() { static TmaApi a; return a; }
+// conv input gradients through the TMA feed: correct (selftest) but not faster - their act' epilogue (stored-output loads at scattered
+// pixel offsets, six accumulators to drain) dominates: measured conv2 class-merged 48.1 us (TMA) vs 34.7 us (cp.async), conv3 37.6 vs 35.4.
+// Off unless DQN_TC_TMA_DGRAD=1 (the selftest switches it on to keep the path covered).
+inline int& tma_conv_dgrad_enabled() { static int v = 0; return v; }
 inline bool tma_ok16(const void* p, long long ld_floats) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_floats % 4) == 0; }
 
 // row-major fp32 matrix [rows][ld], `cols` valid columns: box bc x br
@@ -998,6 +1008,20 @@ inline bool tma_build(const dqn::ConvFwdOp* ops, int nops, int bn, TmaMaps& tm) 
   tm.cin = ops[0].g.Cin; tm.kw = ops[0].g.KW; tm.stride = ops[0].g.S; tm.oh = ops[0].g.OH; tm.ow = ops[0].g.OW;
   return true;
 }
+inline bool tma_build(const dqn::ConvDgradMergedOp* ops, int nops, int bn, TmaMaps& tm) {
+  if (nops != 1 || !TC_TMA_B || !tma_conv_dgrad_enabled()) return false;
+  const dqn::ConvDgradMergedOp& o = ops[0];
+  const dqn::ConvGeom& g = o.g;
+  if (!o.Ds || !o.Ws || g.Cout % 32 != 0 || o.N % 32 != 0 || o.TH > 16 || o.TW > 16 || (reinterpret_cast<uintptr_t>(o.Ds) & 15) || !tma_api().load()) return false;
+  tm.kind = TMA_CONV_DGRAD_MERGED; tm.cin = g.Cout; tm.kw = o.TW; tm.ntaps = o.TH; tm.oh = o.AH; tm.ow = o.BW; tm.stride = 1;
+  cuuint64_t gd[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)o.nimg};
+  cuuint64_t gs[3] = {(cuuint64_t)g.Cout * 4, (cuuint64_t)g.OW * g.Cout * 4, (cuuint64_t)g.OH * g.OW * g.Cout * 4};
+  int lo[2] = {-(o.TW - 1), -(o.TH - 1)}, up[2] = {o.BW - o.TW - (g.OW - 1), o.AH - o.TH - (g.OH - 1)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (tma_api().im2col(&tm.a[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  return tma_b_mnmajor(&tm.b[0], o.Ws, o.K, o.N, o.N, bn);
+}
 // x [nimg][IH][IW][Cin] as im2col boxes of 32 output pixels x 32 channels (the weight gradient's A operand, k = pixel)
 inline bool tma_a_im2col_wgrad(CUtensorMap* m, const float* p, int nimg, const dqn::ConvGeom& g) {
   if (!tma_api().load() || (reinterpret_cast<uintptr_t>(p) & 15) || g.Cin % 32 != 0 || g.S > 8) return false;
@@ -1018,7 +1042,7 @@ inline bool tma_build(const dqn::ConvWgradOp* ops, int nops, int bn, TmaMaps& tm
 }
 // delta [nimg][OH][OW][Cout] per parity class: a stride-1 correlation with TH x TW taps over the zero-padded delta tensor
 inline bool tma_build(const dqn::ConvDgradOp* ops, int nops, int bn, TmaMaps& tm) {
-  if (nops != 1 || !TC_TMA_B) return false;
+  if (nops != 1 || !TC_TMA_B || !tma_conv_dgrad_enabled()) return false;
   const dqn::ConvDgradOp& o = ops[0];
   const dqn::ConvGeom& g = o.g;
   if (!o.Ds || !o.Ws || g.Cout % 32 != 0 || g.S * g.S > 4 || (reinterpret_cast<uintptr_t>(o.Ds) & 15) || (reinterpret_cast<uintptr_t>(o.Ws) & 15) || !tma_api().load()) return false;
@@ -1127,7 +1151,7 @@ bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz,
     if constexpr (Op::HAS_A8) { a8 = ops[0].a8 != 0; for (int i = 1; i < nops; ++i) a8 = a8 && ops[i].a8 != 0; }
     tc::TmaMaps tm; memset(&tm, 0, sizeof tm);
     // TMA feed wherever the operands are boxes (Dense layers, conv forward over >= 32 input channels); the rest keeps the cp.async loaders
-    const bool tma = e->tc_tma && !a8 && tail_s <= 1 && tc::tma_build(ops, nops, bn, tm);
+    const bool tma = e->tc_tma && !a8 && tail_s <= 1 && tc::tma_build(ops, nops, bn, tm);   // (the tail split keeps the cp.async feed)
     if constexpr (Op::HAS_A8) {
       if (a8) {
         if (bn == 32) tc_launch_v<32, 2, 2, true, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
@@ -1164,6 +1188,7 @@ bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, i
 bool tc_dense_dgrad(dqn_engine* e, const char* name, const dqn::DenseDgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, 1, false, fl, by); }
 bool tc_dense_dgrad2(dqn_engine* e, const char* name, const dqn::DenseDgradOp* ops, int ntow, double fl, double by) { return launch_tc(e, name, ops, ntow, ntow, false, fl, by); }
 bool tc_conv_dgrad(dqn_engine* e, const char* name, const dqn::ConvDgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, op.g.S * op.g.S, false, fl, by); }
+bool tc_conv_dgrad_merged(dqn_engine* e, const char* name, const dqn::ConvDgradMergedOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, 1, false, fl, by); }
 bool tc_dense_wgrad(dqn_engine* e, const char* name, const dqn::DenseWgradOp* ops, int ntow, double fl, double by) { return launch_tc(e, name, ops, ntow, ntow, true, fl, by); }
 bool tc_conv_wgrad(dqn_engine* e, const char* name, const dqn::ConvWgradOp& op, double fl, double by) { return launch_tc(e, name, &op, 1, 1, true, fl, by); }
 
@@ -1184,6 +1209,10 @@ void tc_init(dqn_engine* e) {
   { const char* v = getenv("DQN_TC_TMA"); e->tc_tma = v ? atoi(v) : 1; }
   { const char* v = getenv("DQN_TC_C1"); e->tc_c1 = v ? atoi(v) : 1; }
   { const char* v = getenv("DQN_TC_TMA_WGRAD"); e->tc_tma_wgrad = v ? atoi(v) : 0; }
+  { const char* v = getenv("DQN_DGRAD_MERGE"); e->dgrad_merge = v ? atoi(v) : 1; }
+  { const char* v = getenv("DQN_TC_TMA_DGRAD"); tc::tma_conv_dgrad_enabled() = v ? atoi(v) : 0; }
+  for (size_t l = 1; l < e->convs.size() && l < DQN_MAX_LAYERS; ++l)
+    if (dqn::ConvDgradMergedOp::geometry_ok(e->convs[l].g)) e->wm[l] = dalloc<float>((long long)e->convs[l].w.K * e->convs[l].g.Cout);
   long long off = 0;
   auto take = [&](long long n) { long long o = off; off += (n + 63) / 64 * 64; return o; };
   const bool bytes = e->elem_bytes == 1;
@@ -1206,7 +1235,11 @@ void tc_init(dqn_engine* e) {
   CK(cudaMemcpy(e->ones, &one, sizeof(float), cudaMemcpyHostToDevice));       // {1,0,0,0}
   tc_params_changed(e);
 }
-void tc_destroy(dqn_engine* e) { if (e->arena) cudaFree(e->arena); e->arena = nullptr; }
+void tc_destroy(dqn_engine* e) {
+  if (e->arena) cudaFree(e->arena);
+  e->arena = nullptr;
+  for (auto& p : e->wm) { if (p) cudaFree(p); p = nullptr; }
+}
 
 }  // namespace
 #endif  // TC_KERNEL_ONLY

@@ -151,6 +151,22 @@ template <int BN> static void test_conv(int nimg, int IH, int IW, int Cin, int C
     run_tc<BN>(q, S * S, 1, nullptr, 0, ar.d);
     std::vector<float> got(ref.size()); CKC(cudaMemcpy(got.data(), dDX, got.size() * 4, cudaMemcpyDeviceToHost));
     report("conv_dgrad (A:K  B:K )", got, ref);
+    if (ConvDgradMergedOp::geometry_ok(g)) {       // the same gradient through the class-merged contraction (rearranged weights)
+      const int TH = KH / S, TW = KW / S, Nm = S * S * Cin, Km = TH * TW * Cout;
+      std::vector<float> Wm((size_t)Km * Nm);
+      for (int k = 0; k < Km; ++k) for (int n = 0; n < Nm; ++n) {
+        const int ci = n % Cin, cls = n / Cin, ph = cls / S, pw = cls % S, co = k % Cout, tap = k / Cout, th = tap / TW, tw = tap % TW;
+        Wm[(size_t)k * Nm + n] = W[((size_t)((ph + S * th) * KW + (pw + S * tw)) * Cin + ci) * Cout + co];
+      }
+      float* dWm; CKC(cudaMalloc(&dWm, Wm.size() * 4)); CKC(cudaMemcpy(dWm, Wm.data(), Wm.size() * 4, cudaMemcpyHostToDevice));
+      ConvDgradMergedOp mg{}; mg.D = dD; mg.Wm = dWm; mg.dX = dDX; mg.Yprev = dYp; mg.act = ACT_RELU; mg.apply_act = 1; mg.nimg = nimg; mg.g = g; mg.vecA = mg.vecB = 1;
+      mg.Ds = dD; mg.Ws = dWm; mg.init();
+      CKC(cudaMemset(dDX, 0, X.size() * 4));
+      if (mg.N >= 64) run_tc<64>(mg, 1, 1, nullptr, 0, ar.d); else run_tc<32>(mg, 1, 1, nullptr, 0, ar.d);
+      std::vector<float> got2(ref.size()); CKC(cudaMemcpy(got2.data(), dDX, got2.size() * 4, cudaMemcpyDeviceToHost));
+      report("conv_dgrad merged classes", got2, ref);
+      cudaFree(dWm);
+    }
     cudaFree(dYp);
   }
   cudaFree(dX); cudaFree(dW); cudaFree(dD); cudaFree(dY); cudaFree(dG); cudaFree(dDX); cudaFree(ar.d);
@@ -196,6 +212,41 @@ static void test_conv1_bytes(int nimg, int IH, int IW, int iters) {
   cudaFree(dX); cudaFree(dW); cudaFree(dWs); cudaFree(dY);
 }
 
+// timing of the conv input-gradient contractions at the benchmarked sizes (class-wise and class-merged), with and without the act' epilogue
+static void bench_conv_dgrad(int nimg, int IH, int IW, int Cin, int Cout, int KH, int S, int iters) {
+  ConvGeom g{}; g.IH = IH; g.IW = IW; g.Cin = Cin; g.OH = (IH - KH) / S + 1; g.OW = (IW - KH) / S + 1; g.Cout = Cout; g.KH = KH; g.KW = KH; g.S = S; g.init();
+  const int K = KH * KH * Cin, P = nimg * g.OH * g.OW;
+  float *dW, *dD, *dDX, *dYp, *dWm, *zero;
+  const size_t nx = (size_t)nimg * IH * IW * Cin;
+  CKC(cudaMalloc(&dW, (size_t)(K + 1) * Cout * 4)); CKC(cudaMalloc(&dD, (size_t)P * Cout * 4)); CKC(cudaMalloc(&dDX, nx * 4)); CKC(cudaMalloc(&dYp, nx * 4));
+  CKC(cudaMalloc(&dWm, (size_t)K * Cout * 4)); CKC(cudaMalloc(&zero, 256));
+  CKC(cudaMemset(dW, 0, (size_t)(K + 1) * Cout * 4)); CKC(cudaMemset(dD, 0, (size_t)P * Cout * 4)); CKC(cudaMemset(dYp, 0, nx * 4)); CKC(cudaMemset(dWm, 0, (size_t)K * Cout * 4)); CKC(cudaMemset(zero, 0, 256));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int apply = 1; apply >= 0; --apply) {
+    ConvDgradOp q{}; q.D = dD; q.W = dW; q.dX = dDX; q.Yprev = dYp; q.act = ACT_RELU; q.apply_act = apply; q.nimg = nimg; q.g = g; q.vecA = q.vecB = 1; q.Ds = dD; q.Ws = dW;
+    for (int rep = 0; rep < 2; ++rep) {
+      if (rep) cudaEventRecord(a);
+      for (int i = 0; i < (rep ? iters : 1); ++i) { if (Cin >= 64) launch_tc_raw<64>(q, S * S, 1, nullptr, 0, zero); else launch_tc_raw<32>(q, S * S, 1, nullptr, 0, zero); }
+      if (rep) cudaEventRecord(b);
+      CKC(cudaDeviceSynchronize());
+    }
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("bench conv dgrad class-wise %s %dx%dx%d k%d s%d act'=%d: %.1f us\n", g_last_tma ? "[tma]" : "[cpa]", IH, IW, Cin, KH, S, apply, 1e3 * ms / iters);
+    if (ConvDgradMergedOp::geometry_ok(g)) {
+      ConvDgradMergedOp mg{}; mg.D = dD; mg.Wm = dWm; mg.dX = dDX; mg.Yprev = dYp; mg.act = ACT_RELU; mg.apply_act = apply; mg.nimg = nimg; mg.g = g; mg.vecA = mg.vecB = 1; mg.Ds = dD; mg.Ws = dWm; mg.init();
+      for (int rep = 0; rep < 2; ++rep) {
+        if (rep) cudaEventRecord(a);
+        for (int i = 0; i < (rep ? iters : 1); ++i) launch_tc_raw<64>(mg, 1, 1, nullptr, 0, zero);
+        if (rep) cudaEventRecord(b);
+        CKC(cudaDeviceSynchronize());
+      }
+      cudaEventElapsedTime(&ms, a, b);
+      printf("bench conv dgrad merged     %s %dx%dx%d k%d s%d act'=%d: %.1f us  (M=%d N=%d K=%d)\n", g_last_tma ? "[tma]" : "[cpa]", IH, IW, Cin, KH, S, apply, 1e3 * ms / iters, mg.M, mg.N, mg.K);
+    }
+  }
+  cudaFree(dW); cudaFree(dD); cudaFree(dDX); cudaFree(dYp); cudaFree(dWm); cudaFree(zero);
+}
+
 // timing of one big dense forward (conv2-like and fc1-like shapes) - tuning aid
 template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   Arena ar; ar.init(64 << 20);
@@ -234,9 +285,14 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
 }
 
 int main(int argc, char** argv) {
+  tc::tma_conv_dgrad_enabled() = 1;      // keep the TMA-fed conv input gradients covered (the engine leaves them on the cp.async feed)
   { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
     const int it = argc > 2 ? atoi(argv[2]) : 20;
+    if (argc > 3 && argv[3][0] == 'd') {
+      for (g_feed = 0; g_feed < 2; ++g_feed) { bench_conv_dgrad(256, 20, 20, 32, 64, 4, 2, it); bench_conv_dgrad(256, 9, 9, 64, 64, 3, 1, it); }
+      return 0;
+    }
     if (argc > 3) { test_conv1_bytes(512, 84, 84, it); test_conv1_bytes(256, 84, 84, it); return 0; }
     for (g_feed = 0; g_feed < 2; ++g_feed) {
       printf("== feed: %s\n", g_feed ? "TMA" : "cp.async");

@@ -318,7 +318,7 @@ def test_error_codes_mirror_the_reference_asserts(lib):
     eng.close()
 
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("ref_"))
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
@@ -345,6 +345,13 @@ def test_engine_against_committed_golden_vectors(lib, path):
     assert util.relerr(eng.grads(), g["grads64"]) <= gt
     assert abs(gn - g["grad_norm"]) <= gt * g["grad_norm"]
     assert np.abs(eng.get_priorities() - g["prio1"][:eng.replay_size()[0]]).max() <= 1e-5
+    refp = os.path.join(os.path.dirname(path), "ref_" + base + ".npz")       # outputs of the reference itself (oracle/julia/mint_fixtures.jl), when minted
+    if os.path.exists(refp):
+        r = np.load(refp)
+        assert np.array_equal(eng.targets()[1] - 1, r["best_a"])
+        assert np.abs(eng.q(0) - r["q"]).max() <= QTOL * scale and np.abs(eng.td() - r["td"]).max() <= 2 * QTOL * scale
+        assert abs(loss - float(r["loss"][0])) <= 1e-5 * abs(float(r["loss"][0]))
+        assert util.relerr(eng.grads(), r["grads"]) <= gt
     eng.close()
 
 
