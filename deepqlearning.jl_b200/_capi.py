@@ -97,6 +97,7 @@ SIGNATURES = {
     "dqn_train_step_with_indices": (C.c_int, [_H, _i64p, _f32p, _f32p]),
     "dqn_train_step_async": (C.c_int, [_H]),
     "dqn_sync": (C.c_int, [_H, _f32p, _f32p]),
+    "dqn_step_result": (C.c_int, [_H, C.c_int, _f32p, _f32p]),
     "dqn_q_values": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, _f32p]),
     "dqn_act": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, _i32p, _f32p]),
     "dqn_act_device": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -126,7 +126,13 @@ struct dqn_engine {
   float* ws = nullptr; long long ws_floats = 0;
   // staging for host I/O
   uint8_t* stage = nullptr; long long stage_bytes = 0;
-  float* host_out = nullptr; float* host_out_dev = nullptr;   // mapped pinned: loss, grad_norm, error
+  float* host_out = nullptr; float* host_out_dev = nullptr;   // mapped pinned, two slots of (loss, grad_norm, error, step): step s -> slot s & 1
+  unsigned long long n_launched = 0;                           // gradient steps launched so far (== DevState.step once they finish)
+  cudaEvent_t step_ev[2] = {nullptr, nullptr};                 // recorded behind step s in slot s & 1 (dqn_step_result)
+  cudaStream_t copy_stream = nullptr;                          // dqn_replay_add: host -> staging copies run beside the step in flight
+  uint8_t* add_stage[2] = {nullptr, nullptr}; long long add_stage_bytes[2] = {0, 0};
+  cudaEvent_t add_free[2] = {nullptr, nullptr};                // staging slot consumed by its ingest kernels
+  unsigned long long add_seq = 0;
   long long* idx_h = nullptr;                                  // pinned
   // graph
   cudaGraphExec_t graph_sample = nullptr, graph_idx = nullptr;
@@ -162,6 +168,8 @@ struct dqn_engine {
   int* ep_start_d = nullptr;
   // trunk hand-over to the towers (conv trunk: the last conv layer; LSTM trunk: the hidden states)
   float *trunk_on = nullptr, *trunk_tg = nullptr, *trunk_delta = nullptr; int trunk_act = 0;
+  int fuse_head_all = 1;   // output layers of all three passes + head + their input gradient in one launch (head_fused_kernel)
+  float* hub = nullptr;    // per-sample Huber values of that kernel (deterministic loss reduction)
   int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction
   int a8 = 0;              // 1: the first conv layer (forward and weight gradient) reads the byte batch directly, no fp32 copy of it exists
   int merge_fwd = 0;       // 1: online and target forward share launches layer by layer; measured slower than two lanes on B200 (0.571 vs 0.539 ms/step)
@@ -254,7 +262,7 @@ void order_after(E* e, cudaStream_t later, cudaStream_t earlier) {     // everyt
 // ---- network schedule ---------------------------------------------------------------------------
 // One forward pass: parameters P applied to the rows of X.  Xs: the input batch as fp32 for the tensor-core path (null => fp32
 // CUDA-core kernels only); w1s: the first conv layer's weights pre-scaled by 1/255 when Xs holds raw byte values.
-struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; bool tc; const float* trunk_out = nullptr; };
+struct Pass { const float* P; const void* X; int x_u8; int rows; ActBufs* bufs; const char* tag; const float* Xs; const float* w1s; bool tc; const float* trunk_out = nullptr; bool skip_last = false; };   // skip_last: the output layers are computed by head_fused_kernel
 
 // Layer by layer over all passes.  On the tensor-core path the passes of a layer (online network on [s ; s'], target network on s')
 // and the two towers of a Dense layer share ONE launch: the persistent kernels serialise on the machine anyway, and one launch
@@ -307,6 +315,7 @@ void forward(E* e, const Pass* ps, int np) {
         by[p] += 4.0 * ((double)rows * op.K / (l == 0 ? e->ntow : 1) + (double)(op.K + 1) * op.N + (double)rows * op.N);
       }
     snprintf(nm, sizeof nm, "dense%d_fwd", l + 1);
+    if (l == e->depth - 1 && ps[0].skip_last) continue;
     if (l == e->depth - 1 && l > 0 && e->fuse_heads && e->tow[e->ntow - 1][l].N <= HEADS_MAXN && e->tow[0][l].N <= HEADS_MAXN) {
       // the thin output layers of all passes and towers: one warp per row
       HeadJobs jobs{}; int total = 0;
@@ -347,7 +356,7 @@ void prepare_dgrad_weights(E* e) {
   }
 }
 
-void backward(E* e, bool conc) {
+void backward(E* e, bool conc, bool head_fused = false) {
   const int B = e->B;
   char nm[64];
   const bool trunk = !e->convs.empty() || e->lstm;
@@ -394,7 +403,9 @@ void backward(E* e, bool conc) {
       }
     }
     // input gradients
-    if (l > 0) {
+    if (l > 0 && l == e->depth - 1 && head_fused) {
+      // head_fused_kernel already wrote the gradient into the last hidden layer
+    } else if (l > 0) {
       DenseDgradOp dg[2];
       for (int t = 0; t < e->ntow; ++t) {
         const Mat& w = e->tow[t][l]; const Mat& wp = e->tow[t][l - 1];
@@ -705,8 +716,12 @@ void enqueue_step(E* e, bool sample) {
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
   e->ev_next = 0;
   const bool tcp = e->arena && e->obs_row_bytes % 16 == 0 && (xs != nullptr || e->a8);
-  const Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s, tcp};
-  const Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s, tcp};
+  // thin output layers (N <= 8) behind at least one hidden Dense layer: the whole head is one launch
+  bool head_fused = e->fuse_heads && e->fuse_head_all && e->depth >= 2 && e->cfg.n_actions <= HEADS_MAXN && B <= 65536;
+  for (int t = 0; t < e->ntow; ++t) head_fused = head_fused && e->tow[t][e->depth - 1].N <= HEADS_MAXN && e->tow[t][e->depth - 1].K == e->tow[0][e->depth - 1].K;
+  Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s, tcp};
+  Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s, tcp};
+  p_on.skip_last = p_tg.skip_last = head_fused;
   if (tcp && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
     const Pass both[2] = {p_on, p_tg};
     prepare_dgrad_weights(e);
@@ -733,9 +748,22 @@ void enqueue_step(E* e, bool sample) {
     h.gamma = e->cfg.discount; h.alpha = e->cfg.alpha; h.eps = e->cfg.eps;
     h.inv_world_B = 1.0f / ((float)B * (float)e->cfg.world);
     h.st = e->st;
-    Scope sc(e, "head_loss", 0, B * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
-    head_loss_kernel<<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
-    CK(cudaGetLastError());
+    if (head_fused) {
+      FusedHeadArgs fa{}; fa.h = h; fa.ntow = e->ntow; fa.K = e->tow[0][L].K; fa.hub = e->hub; fa.ticket = e->colsum_ticket + 2;
+      for (int t = 0; t < e->ntow; ++t) {
+        const Mat& w = e->tow[t][L];
+        fa.H_on[t] = e->on.tow_out[t][L - 1]; fa.H_tg[t] = e->tg.tow_out[t][L - 1]; fa.W_on[t] = e->theta + w.off; fa.W_tg[t] = e->theta_t + w.off;
+        fa.out_on[t] = e->on.tow_out[t][L]; fa.out_tg[t] = e->tg.tow_out[t][L]; fa.dH[t] = e->tow_delta[t][L - 1];
+        fa.N[t] = w.N; fa.act_out[t] = w.act; fa.act_hidden[t] = e->tow[t][L - 1].act;
+      }
+      Scope sc(e, "head_fused", 6.0 * B * fa.K * (e->cfg.n_actions + 1), 4.0 * B * fa.K * 5);
+      head_fused_kernel<<<(B + 7) / 8, 256, 0, e->stream>>>(fa);
+      CK(cudaGetLastError());
+    } else {
+      Scope sc(e, "head_loss", 0, B * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
+      head_loss_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(h);
+      CK(cudaGetLastError());
+    }
   }
   // update_priorities! (PER:76-80) needs nothing but the TD errors: on the third lane now, beside the whole reverse pass, instead of
   // 13 us alone at the end of the step (one CTA, twenty dependent tree levels)
@@ -803,17 +831,26 @@ void run_step(E* e, bool sample) {
     enqueue_step(e, sample);
     e->counting = 0; e->launches_per_step = e->launches;
   }
+  e->n_launched += 1;
+  CK(cudaEventRecord(e->step_ev[e->n_launched & 1], e->stream));
 }
 
-void fetch_scalars(E* e, float* loss, float* gn) {
-  CK(cudaStreamSynchronize(e->stream));
-  const int err = reinterpret_cast<int*>(e->host_out)[2];
-  if (loss) *loss = e->host_out[0];
-  if (gn) *gn = e->host_out[1];
+// Scalars of the step launched `back` steps before the latest one (0: the latest; 1: the one before it, which can be read while the
+// latest is still running - the two host slots alternate).
+void fetch_scalars(E* e, float* loss, float* gn, int back = 0) {
+  if (back < 0 || back > 1) fail(DQN_ERR_INVALID, "back must be 0 or 1");
+  if (e->n_launched < (unsigned long long)back + 1) fail(DQN_ERR_STATE, "no such step: %llu launched so far", e->n_launched);
+  const unsigned long long s = e->n_launched - back;
+  if (back == 0) CK(cudaStreamSynchronize(e->stream)); else CK(cudaEventSynchronize(e->step_ev[s & 1]));
+  volatile float* slot = e->host_out + 4 * (s & 1);
+  const int err = reinterpret_cast<volatile int*>(slot)[2];
+  if (loss) *loss = slot[0];
+  if (gn) *gn = slot[1];
   if (err) {
+    CK(cudaStreamSynchronize(e->stream));
     int zero = 0;
     CK(cudaMemcpy(&e->st->error, &zero, sizeof(int), cudaMemcpyHostToDevice));
-    reinterpret_cast<int*>(e->host_out)[2] = 0;
+    reinterpret_cast<int*>(e->host_out)[2] = 0; reinterpret_cast<int*>(e->host_out)[6] = 0;
     if (err & 1) fail(DQN_ERR_STATE, "sum-tree sampler did not reach %d distinct indices", e->B);
     if (err & 2) fail(DQN_ERR_STATE, "non-positive priority (PER:78 @assert all(new_priorities .> 0f0))");
     if (err & 4) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
@@ -868,7 +905,7 @@ void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const u
     CK(cudaGetLastError());
   }
   if (n <= 4096) {
-    tree_update_kernel<<<1, 1024, 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0, nullptr);
+    tree_update_kernel<<<1, (int)std::min<long long>(1024, (n + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0, nullptr);
     CK(cudaGetLastError());
   } else rebuild_tree(e);
   e->cursor = (e->cursor + n) % e->cap;
@@ -1041,16 +1078,22 @@ void allocate(E* e) {
   e->q_s = dalloc<float>((long long)B * nA); e->q_sp_on = dalloc<float>((long long)B * nA); e->q_sp_tg = dalloc<float>((long long)B * nA);
   e->y = dalloc<float>(B); e->td = dalloc<float>(B); e->newp = dalloc<float>(B); e->best_a = dalloc<int>(B);
   e->colsum_part = dalloc<float>(2LL * COLSUM_CTAS * 1024);
-  e->colsum_ticket = dalloc<unsigned int>(2);
+  e->colsum_ticket = dalloc<unsigned int>(4);                 // [0], [1]: column sums per lane; [2]: head_fused_kernel
+  e->hub = dalloc<float>(B);
   e->ws_floats = 16LL << 20;      // 64 MB split-K workspace
   e->ws = dalloc<float>(e->ws_floats);
   e->ws2 = dalloc<float>(e->ws_floats);
   e->lws = e->ws;
-  CK(cudaHostAlloc(&e->host_out, 16, cudaHostAllocMapped));
-  memset(e->host_out, 0, 16);
+  CK(cudaHostAlloc(&e->host_out, 32, cudaHostAllocMapped));
+  memset(e->host_out, 0, 32);
   CK(cudaHostGetDevicePointer(&e->host_out_dev, e->host_out, 0));
   CK(cudaHostAlloc(&e->idx_h, sizeof(long long) * B, cudaHostAllocDefault));
   CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1)); CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&e->step_ev[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->add_free[i], cudaEventDisableTiming));
+  }
 }
 
 void destroy(E* e) {
@@ -1063,7 +1106,7 @@ void destroy(E* e) {
   tc_destroy(e);
   void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
                   e->idx_d, e->xb, e->a_b, e->r_b, e->d_b, e->w_b, e->q_s, e->q_sp_on, e->q_sp_tg, e->y, e->td, e->newp, e->best_a, e->ws, e->ws2,
-                  e->stage, e->flush_buf, e->colsum_part, e->colsum_ticket, e->ep_s, e->ep_sp, e->ep_r, e->ep_a, e->ep_len, e->ep_done, e->ep_start_d,
+                  e->stage, e->flush_buf, e->colsum_part, e->colsum_ticket, e->hub, e->ep_s, e->ep_sp, e->ep_r, e->ep_a, e->ep_len, e->ep_done, e->ep_start_d,
                   e->xproj_on, e->xproj_tg, e->hs_on, e->hs_tg, e->cs_on, e->cs_sp, e->cs_tg, e->gates_s, e->dgates, e->dcell, e->whT, e->h_act, e->c_act,
                   e->lstm ? e->trunk_delta : nullptr};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -1077,6 +1120,12 @@ void destroy(E* e) {
   if (e->t0) cudaEventDestroy(e->t0);
   if (e->t1) cudaEventDestroy(e->t1);
   if (e->copy_done) cudaEventDestroy(e->copy_done);
+  for (int i = 0; i < 2; ++i) {
+    if (e->step_ev[i]) cudaEventDestroy(e->step_ev[i]);
+    if (e->add_free[i]) cudaEventDestroy(e->add_free[i]);
+    if (e->add_stage[i]) cudaFree(e->add_stage[i]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (auto ev : e->evs) cudaEventDestroy(ev);
   if (e->stream3) cudaStreamDestroy(e->stream3);
   if (e->stream2) cudaStreamDestroy(e->stream2);
@@ -1182,6 +1231,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_FUSE_HEAD_ALL"); e->fuse_head_all = v ? atoi(v) : 0; }   // one launch for output layers + loss + dH: measured slower (0.452 vs 0.415 ms/step) - it joins the three passes early
     build_topology(e);
     allocate(e);
     tc_init(e);
@@ -1263,25 +1313,35 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
     const long long rb = h->obs_row_bytes;
     const long long chunk = std::max<long long>(1, std::min<long long>(n, (256LL << 20) / std::max<long long>(1, 2 * rb)));
     const long long per = 2 * rb + 4 + 4 + 1 + 4;
-    ensure_stage(h, chunk * per + 64 * 6 + chunk * 8);
+    const long long need = chunk * per + 64 * 6 + chunk * 8;
+    // The host -> device copies go to one of two staging areas on their own stream, so they run beside whatever step is still in
+    // flight on the engine's stream; only the ingest kernels (and the sum-tree refresh) are ordered behind that step.  The call
+    // returns when the copies are done - the caller's buffers are free again - with the ingest still in flight.
     for (long long t0 = 0; t0 < n; t0 += chunk) {
       const long long c = std::min(chunk, n - t0);
-      uint8_t* p = h->stage;
+      const int slot = (int)(h->add_seq++ & 1);
+      if (h->add_stage_bytes[slot] < need) {
+        if (h->add_stage[slot]) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->add_stage[slot])); h->add_stage[slot] = nullptr; h->add_stage_bytes[slot] = 0; }
+        CK(cudaMalloc(&h->add_stage[slot], need)); h->add_stage_bytes[slot] = need;
+      }
+      uint8_t* p = h->add_stage[slot];
       auto carve = [&](long long bytes) { uint8_t* q = p; p += (bytes + 63) / 64 * 64; return q; };
       uint8_t* ds = carve(c * rb); uint8_t* dsp = carve(c * rb);
       int* da = (int*)carve(c * 4); float* dr = (float*)carve(c * 4); float* dtd = (float*)carve(c * 4); uint8_t* dd = carve(c);
       long long* slots = (long long*)carve(c * 8);
-      CK(cudaMemcpyAsync(ds, (const uint8_t*)s + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(dsp, (const uint8_t*)sp + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(da, a + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(dr, r + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(dtd, td0 + t0, c * 4, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(dd, done + t0, c, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaEventRecord(h->copy_done, h->stream));             // the caller's buffers are free again once the copies are done ...
+      CK(cudaStreamWaitEvent(h->copy_stream, h->add_free[slot], 0));      // the ingest that last read this area has finished
+      CK(cudaMemcpyAsync(ds, (const uint8_t*)s + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaMemcpyAsync(dsp, (const uint8_t*)sp + t0 * rb, c * rb, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaMemcpyAsync(da, a + t0, c * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaMemcpyAsync(dr, r + t0, c * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaMemcpyAsync(dtd, td0 + t0, c * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaMemcpyAsync(dd, done + t0, c, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(h->copy_done, h->copy_stream));
+      CK(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
       ingest_device(h, ds, da, dr, dsp, dd, dtd, c, slots);
-      if (t0 + c < n) CK(cudaStreamSynchronize(h->stream));   // the staging area is reused by the next chunk
+      CK(cudaEventRecord(h->add_free[slot], h->stream));
     }
-    if (n > 0) CK(cudaEventSynchronize(h->copy_done));         // ... the ingest kernels and the sum-tree refresh stay in flight
+    if (n > 0) CK(cudaEventSynchronize(h->copy_done));
   });
 }
 
@@ -1421,6 +1481,7 @@ int dqn_train_step_with_indices(dqn_engine_t* h, const int64_t* idx, float* loss
 }
 int dqn_train_step_async(dqn_engine_t* h) { return guard(h, [&] { run_step(h, true); }); }
 int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm); }); }
+int dqn_step_result(dqn_engine_t* h, int back, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm, back); }); }
 
 int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* q_out) {
   return guard(h, [&] {

@@ -17,7 +17,7 @@ struct DevState {
   float loss;                     // loss_val SOLVER:223-224
   int error;                      // sticky error flags raised by kernels (bit 0: sampler did not converge,
                                   //   bit 1: non-positive priority PER:78, bit 2: td0+eps <= 0 PER:66, bit 3: bad action)
-  int pad;
+  unsigned int step;              // gradient steps finished so far: step s publishes its scalars to host slot s & 1
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -260,8 +260,11 @@ __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long l
   if (end_of_step && j == 0) {
     st->b1p *= beta1; st->b2p *= beta2;
     if (advance_sampler) st->sample_call += 1;
-    if (publish) {      // scalars of the finished step -> mapped pinned host words (loss, grad_norm, error flags)
+    const unsigned int s = ++st->step;
+    if (publish) {      // scalars of the finished step -> mapped pinned host words (loss, grad_norm, error flags, step), two slots:
+      publish += 4 * (s & 1);           // the host may read step s while step s+1 runs (dqn_step_result)
       publish[0] = st->loss; publish[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(publish)[2] = st->error;
+      reinterpret_cast<unsigned int*>(publish)[3] = s;
     }
   }
 }
@@ -394,48 +397,53 @@ __device__ __forceinline__ void dueling_q(const float* V, const float* A, int ro
   }
 }
 
+// per-sample part of the head: returns huber(w td); q_* are this sample's three Q rows after the dueling combine
+__device__ __forceinline__ float head_sample(const HeadArgs& h, int i, const float* q_s_row, const float* q_on_row, const float* q_tg_row,
+                                             float v_on_s, const float* a_on_s, float* dv_out, float* da_out) {
+  const int nA = h.nA;
+  for (int k = 0; k < nA; ++k) h.q_sp_on[(long long)i * nA + k] = q_on_row[k];
+  int best = 0;
+  for (int k = 1; k < nA; ++k) if (q_on_row[k] > q_on_row[best]) best = k;          // first maximal index (Julia argmax)
+  for (int k = 0; k < nA; ++k) h.q_sp_tg[(long long)i * nA + k] = q_tg_row[k];
+  float qsp;
+  if (h.double_q) qsp = q_tg_row[best];
+  else { best = 0; for (int k = 1; k < nA; ++k) if (q_tg_row[k] > q_tg_row[best]) best = k; qsp = q_tg_row[best]; }
+  // y = r + ((1 - d) * gamma) * q'
+  const float y = __fadd_rn(h.r_b[i], __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.d_b[i]), h.gamma), qsp));
+  for (int k = 0; k < nA; ++k) h.q_s[(long long)i * nA + k] = q_s_row[k];
+  int a = h.a_b[i] - 1;
+  if (a < 0 || a >= nA) { atomicOr(&h.st->error, 8); a = min(max(a, 0), nA - 1); }   // never index q[] out of range
+  const float td = __fsub_rn(q_s_row[a], y);
+  const float w = h.w_b[i];
+  const float x = __fmul_rn(w, td);
+  const float ax = fabsf(x), quad = fminf(ax, 1.f), lin = __fsub_rn(ax, quad);
+  const float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), lin);
+  const float g = __fmul_rn(__fmul_rn(w, fminf(fmaxf(x, -1.f), 1.f)), h.inv_world_B);
+  if (h.dueling) {
+    dv_out[0] = g * act_deriv(v_on_s, h.act_v);
+    const float gm = __fdiv_rn(g, (float)nA);
+    for (int k = 0; k < nA; ++k) da_out[k] = ((k == a ? g : 0.f) - gm) * act_deriv(a_on_s[k], h.act_a);
+  } else {
+    for (int k = 0; k < nA; ++k) da_out[k] = (k == a ? g : 0.f) * act_deriv(a_on_s[k], h.act_a);
+  }
+  h.y[i] = y; h.best_a[i] = best + 1; h.td[i] = td;
+  h.newp[i] = pow_f32(__fadd_rn(fabsf(td), h.eps), h.alpha);
+  return hub;
+}
+
 __global__ void head_loss_kernel(HeadArgs h) {
   __shared__ float red[32];
   float hub = 0.f;
   // one thread per sample; the recurrent step has trace_length * batch_size rows (> 1024): threads stride over them
   for (int i = threadIdx.x; i < h.B; i += blockDim.x) {
-    float q[HEAD_MAX_ACTIONS];
+    float q[HEAD_MAX_ACTIONS], qo[HEAD_MAX_ACTIONS], qt[HEAD_MAX_ACTIONS], da[HEAD_MAX_ACTIONS], dv = 0.f;
     const int nA = h.nA;
-    // s' online / target
-    dueling_q(h.V_on, h.A_on, h.B + i, nA, h.dueling, q);
-    for (int k = 0; k < nA; ++k) h.q_sp_on[(long long)i * nA + k] = q[k];
-    int best = 0;
-    for (int k = 1; k < nA; ++k) if (q[k] > q[best]) best = k;          // first maximal index (Julia argmax)
-    dueling_q(h.V_tg, h.A_tg, i, nA, h.dueling, q);
-    for (int k = 0; k < nA; ++k) h.q_sp_tg[(long long)i * nA + k] = q[k];
-    float qsp;
-    if (h.double_q) qsp = q[best];
-    else { best = 0; for (int k = 1; k < nA; ++k) if (q[k] > q[best]) best = k; qsp = q[best]; }
-    // y = r + ((1 - d) * gamma) * q'
-    const float y = __fadd_rn(h.r_b[i], __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.d_b[i]), h.gamma), qsp));
-    // s online
+    dueling_q(h.V_on, h.A_on, h.B + i, nA, h.dueling, qo);
+    dueling_q(h.V_tg, h.A_tg, i, nA, h.dueling, qt);
     dueling_q(h.V_on, h.A_on, i, nA, h.dueling, q);
-    for (int k = 0; k < nA; ++k) h.q_s[(long long)i * nA + k] = q[k];
-    int a = h.a_b[i] - 1;
-    if (a < 0 || a >= nA) { atomicOr(&h.st->error, 8); a = min(max(a, 0), nA - 1); }   // never index q[] out of range
-    const float td = __fsub_rn(q[a], y);
-    const float w = h.w_b[i];
-    const float x = __fmul_rn(w, td);
-    const float ax = fabsf(x), quad = fminf(ax, 1.f), lin = __fsub_rn(ax, quad);
-    hub += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), lin);
-    const float g = __fmul_rn(__fmul_rn(w, fminf(fmaxf(x, -1.f), 1.f)), h.inv_world_B);
-    if (h.dueling) {
-      h.dV[i] = g * act_deriv(h.V_on[i], h.act_v);
-      const float gm = __fdiv_rn(g, (float)nA);
-      for (int k = 0; k < nA; ++k) {
-        const float d = (k == a ? g : 0.f) - gm;
-        h.dA[(long long)i * nA + k] = d * act_deriv(h.A_on[(long long)i * nA + k], h.act_a);
-      }
-    } else {
-      for (int k = 0; k < nA; ++k) h.dA[(long long)i * nA + k] = (k == a ? g : 0.f) * act_deriv(h.A_on[(long long)i * nA + k], h.act_a);
-    }
-    h.y[i] = y; h.best_a[i] = best + 1; h.td[i] = td;
-    h.newp[i] = pow_f32(__fadd_rn(fabsf(td), h.eps), h.alpha);
+    hub += head_sample(h, i, q, qo, qt, h.dueling ? h.V_on[i] : 0.f, h.A_on + (long long)i * nA, &dv, da);
+    if (h.dueling) h.dV[i] = dv;
+    for (int k = 0; k < nA; ++k) h.dA[(long long)i * nA + k] = da[k];
   }
   // loss = sum(huber) / B  (block reduction; fp32)
   float s = hub;
@@ -683,6 +691,110 @@ __global__ void __launch_bounds__(256) heads_dgrad_kernel(const HeadGradJobs job
 #pragma unroll
   for (int n = 0; n < HEADS_MAXN; ++n) if (n < jb.N) s = fmaf(__ldg(d + n), __ldg(wr + n), s);
   jb.dX[i] = s * act_deriv(jb.Y[i], jb.act);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole head in ONE launch (feed-forward step, thin output layers): for sample i one warp computes the output layers of both towers
+// on the three rows that matter (online s, online s', target s') - lanes stride over k, a butterfly per output, exactly the sums of
+// heads_fwd_kernel - then the per-sample head (dueling combine, Double-Q argmax, target, IS-Huber, dQ seed, priority) and the gradient
+// into the last hidden layer (heads_dgrad_kernel's formula).  Replaces four launches of 7-13 us each that sat one behind the other in
+// the middle of the step (heads_fwd x2, head_loss, heads_dgrad).  The loss is reduced deterministically: per-sample values to a buffer,
+// the last CTA to finish (ticket) adds them in index order.
+struct FusedHeadArgs {
+  HeadArgs h;
+  const float* H_on[2]; const float* H_tg[2];   // last hidden layer outputs per tower: online [2B][K], target [B][K]
+  const float* W_on[2]; const float* W_tg[2];   // output layers, augmented [K+1][N]
+  float* out_on[2]; float* out_tg[2];           // V / A outputs kept for the diagnostics ([2B][N], [B][N])
+  float* dH[2];                                 // gradient into the last hidden layer [B][K], times act'(H)
+  int N[2], act_out[2], act_hidden[2], K, ntow;
+  float* hub; unsigned int* ticket;
+};
+__device__ __forceinline__ void head_rowdot(const float* __restrict__ x, const float* __restrict__ W, int K, int N, int act, int lane, float* out) {
+  float acc[HEADS_MAXN];
+#pragma unroll
+  for (int n = 0; n < HEADS_MAXN; ++n) acc[n] = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < K; k += 32) {
+    const float xv = __ldg(x + k);
+    const float* wr = W + (long long)k * N;
+#pragma unroll
+    for (int n = 0; n < HEADS_MAXN; ++n) if (n < N) acc[n] = fmaf(xv, __ldg(wr + n), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < HEADS_MAXN; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    out[n] = n < N ? act_apply(acc[n] + __ldg(W + (long long)K * N + n), act) : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) head_fused_kernel(const FusedHeadArgs a) {
+  const HeadArgs& h = a.h;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  __shared__ int last;
+  if (i < h.B) {
+    float o_s[2][HEADS_MAXN], o_sp[2][HEADS_MAXN], o_tg[2][HEADS_MAXN];
+    for (int t = 0; t < a.ntow; ++t) {
+      head_rowdot(a.H_on[t] + (long long)i * a.K, a.W_on[t], a.K, a.N[t], a.act_out[t], lane, o_s[t]);
+      head_rowdot(a.H_on[t] + (long long)(h.B + i) * a.K, a.W_on[t], a.K, a.N[t], a.act_out[t], lane, o_sp[t]);
+      head_rowdot(a.H_tg[t] + (long long)i * a.K, a.W_tg[t], a.K, a.N[t], a.act_out[t], lane, o_tg[t]);
+      if (lane < a.N[t]) {
+        a.out_on[t][(long long)i * a.N[t] + lane] = o_s[t][lane];
+        a.out_on[t][(long long)(h.B + i) * a.N[t] + lane] = o_sp[t][lane];
+        a.out_tg[t][(long long)i * a.N[t] + lane] = o_tg[t][lane];
+      }
+    }
+    const int nA = h.nA, ta = a.ntow - 1;                        // advantage (or only) tower
+    float q[HEADS_MAXN], qo[HEADS_MAXN], qt[HEADS_MAXN], da[HEADS_MAXN], dv = 0.f;
+    if (h.dueling) {                                             // Q = (V + A) - mean(A), the mean summed in index order (DUEL:8-11)
+      float ms = o_s[1][0], mo = o_sp[1][0], mt = o_tg[1][0];
+      for (int k = 1; k < nA; ++k) { ms = __fadd_rn(ms, o_s[1][k]); mo = __fadd_rn(mo, o_sp[1][k]); mt = __fadd_rn(mt, o_tg[1][k]); }
+      ms = __fdiv_rn(ms, (float)nA); mo = __fdiv_rn(mo, (float)nA); mt = __fdiv_rn(mt, (float)nA);
+      for (int k = 0; k < nA; ++k) {
+        q[k] = __fsub_rn(__fadd_rn(o_s[0][0], o_s[1][k]), ms); qo[k] = __fsub_rn(__fadd_rn(o_sp[0][0], o_sp[1][k]), mo); qt[k] = __fsub_rn(__fadd_rn(o_tg[0][0], o_tg[1][k]), mt);
+      }
+    } else {
+      for (int k = 0; k < nA; ++k) { q[k] = o_s[0][k]; qo[k] = o_sp[0][k]; qt[k] = o_tg[0][k]; }
+    }
+    float hub = 0.f;
+    if (lane == 0) {
+      hub = head_sample(h, i, q, qo, qt, h.dueling ? o_s[0][0] : 0.f, o_s[ta], &dv, da);
+      a.hub[i] = hub;
+      if (h.dueling) h.dV[i] = dv;
+      for (int k = 0; k < nA; ++k) h.dA[(long long)i * nA + k] = da[k];
+    }
+    dv = __shfl_sync(0xffffffffu, dv, 0);
+#pragma unroll
+    for (int k = 0; k < HEADS_MAXN; ++k) da[k] = __shfl_sync(0xffffffffu, k < nA ? da[k] : 0.f, 0);
+    // gradient into the last hidden layer: dH[j] = (sum_n d[n] W[j][n]) act'(H[j])
+    for (int t = 0; t < a.ntow; ++t) {
+      const float* W = a.W_on[t]; const float* Hr = a.H_on[t] + (long long)i * a.K; float* o = a.dH[t] + (long long)i * a.K;
+      const int N = a.N[t];
+      for (int j = lane; j < a.K; j += 32) {
+        float sacc = 0.f;
+        if (h.dueling && t == 0) sacc = fmaf(dv, __ldg(W + j), 0.f);
+        else {
+#pragma unroll
+          for (int n = 0; n < HEADS_MAXN; ++n) if (n < N) sacc = fmaf(da[n], __ldg(W + (long long)j * N + n), sacc);
+        }
+        o[j] = sacc * act_deriv(Hr[j], a.act_hidden[t]);
+      }
+    }
+  }
+  // deterministic loss: the last CTA sums the per-sample values in index order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int k = threadIdx.x; k < h.B; k += 32) s += __ldcg(a.hub + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) { h.st->loss = __fdiv_rn(s, (float)h.B); h.st->gradmax_bits = 0u; *a.ticket = 0u; }
+  }
 }
 #endif  // __CUDACC__
 

@@ -223,6 +223,12 @@ class Engine:
         self._ck(lib.dqn_sync(self.h, C.byref(loss), C.byref(gn)))
         return loss.value, gn.value
 
+    def step_result(self, back=0):
+        """(loss, grad_norm) of the step launched `back` (0 or 1) steps before the latest; back=1 does not wait for the latest."""
+        loss, gn = C.c_float(), C.c_float()
+        self._ck(lib.dqn_step_result(self.h, back, C.byref(loss), C.byref(gn)))
+        return loss.value, gn.value
+
     def q_values(self, obs, which=_capi.NET_ONLINE):
         obs = np.ascontiguousarray(obs, self.obs_np)
         n = obs.size // self.obs_elems

@@ -161,6 +161,10 @@ int dqn_train_step(dqn_engine_t* h, float* loss, float* grad_norm);        /* sa
 int dqn_train_step_with_indices(dqn_engine_t* h, const int64_t* idx, float* loss, float* grad_norm);
 int dqn_train_step_async(dqn_engine_t* h);                                 /* enqueue only */
 int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm);              /* wait, fetch the last step's scalars */
+/* (loss_val, grad_norm) of the step launched `back` steps before the latest one: back = 0 is dqn_sync; back = 1 waits only for the
+ * step before the latest, so a caller that logs the scalars (SOLVER:147-166 is their only use) can add the next transitions and
+ * launch the next step while this one runs:  add_k; async_k; result(back=1) -> step k-1. */
+int dqn_step_result(dqn_engine_t* h, int back, float* loss, float* grad_norm);
 
 /* ---- acting: policy.qnetwork(obatch) (POLICY:38-64, SOLVER:83) ------------------------------------ */
 int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* q_out);   /* q_out (n, n_actions) row-major == (|A|, n) column-major */

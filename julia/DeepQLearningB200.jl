@@ -32,7 +32,8 @@ mutable struct Config     # dqn_config_t (field order and types must match inclu
     math_mode::Int32; use_graph::Int32; rank::Int32; world::Int32
     nccl_id::NTuple{128,UInt8}
     max_act_rows::Int32
-    reserved::NTuple{7,Int32}
+    trace_length::Int32; max_episode_length::Int32
+    reserved::NTuple{5,Int32}
     Config() = new()
 end
 
@@ -60,6 +61,8 @@ function layer_desc(l)
         kw, kh, cin, cout = size(l.weight)
         all(==(0), l.pad) || error("DeepQLearningB200: only pad = 0 convolutions")
         LayerDesc(1, act_code(l.σ), cin, cout, kh, kw, l.stride[1])
+    elseif l isa Flux.Recur && l.cell isa Flux.LSTMCell        # Flux.LSTM(in, out): the recurrent engine (src/solver.jl:239-287)
+        LayerDesc(3, 0, size(l.cell.Wi, 2), size(l.cell.Wh, 2), 0, 0, 0)
     else
         LayerDesc(2, 0, 0, 0, 0, 0, 0)      # flattenbatch / identity closures
     end
@@ -88,6 +91,9 @@ function Engine(solver, env, qnetwork::Chain; discount, n_actions, obs_size, dev
     cfg.batch_size, cfg.buffer_size = solver.batch_size, solver.buffer_size
     cfg.learning_rate, cfg.discount = solver.learning_rate, Float32(discount)
     cfg.math_mode, cfg.seed = math_mode, seed
+    if solver.recurrence
+        cfg.trace_length, cfg.max_episode_length = solver.trace_length, solver.max_episode_length
+    end
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:dqn_engine_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h)
     rc == 0 || throw(EngineError(rc, unsafe_string(ccall((:dqn_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
@@ -137,6 +143,46 @@ function q_values(e::Engine, obatch::AbstractArray)
     q = Matrix{Float32}(undef, e.n_actions, n)
     check(e, ccall((:dqn_q_values, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Ptr{Float32}), e.h, 0, obatch, n, q))
     return q
+end
+
+# ---- recurrent path: EpisodeReplayBuffer + recurrent batch_train!  (src/episode_replay.jl, src/solver.jl:239-287) --------------------
+# add_episode!(r, ep) :60-66 - the host keeps collecting the running episode exactly as add_exp! :52-58 does and hands it over when it ends
+function add_episode!(e::Engine, ep::Vector)
+    s = reduce(hcat, [vec(Float32.(x.s)) for x in ep]); sp = reduce(hcat, [vec(Float32.(x.sp)) for x in ep])
+    check(e, ccall((:dqn_episode_add, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Int64),
+                   e.h, s, Int32[x.a for x in ep], Float32[x.r for x in ep], sp, UInt8[x.done for x in ep], length(ep)))
+end
+# resetstate!(policy)  src/policy.jl:32-34: the acting hidden state goes back to state0 (q_values carries it between calls)
+resetstate!(e::Engine) = check(e, ccall((:dqn_policy_reset, LIB), Cint, (Ptr{Cvoid},), e.h))
+
+# ---- vectorised acting / batched evaluation: argmax + epsilon-greedy on the device for n lanes  (src/solver.jl:83, src/policy.jl:38-46)
+function act(e::Engine, obatch::AbstractArray; eps=0f0, call=0)
+    n = size(obatch)[end]
+    a = Vector{Int32}(undef, n)
+    check(e, ccall((:dqn_act, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Float32, UInt64, Ptr{Int32}, Ptr{Float32}), e.h, obatch, n, eps, call, a, C_NULL))
+    return a
+end
+
+# ---- all GPUs of the box from this one Julia process (dqn_group_*): ndev engines, one NCCL communicator inside -----------------------
+mutable struct Group
+    g::Ptr{Cvoid}
+    ranks::Vector{Engine}
+end
+function Group(cfg::Config, ndev::Integer, batch_size, n_actions)
+    g = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:dqn_group_create, LIB), Cint, (Ref{Config}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), cfg, ndev, C_NULL, g)
+    rc == 0 || throw(EngineError(rc, unsafe_string(ccall((:dqn_group_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+    ranks = [Engine(ccall((:dqn_group_engine, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Cint), g[], r), batch_size, n_actions,
+                    ccall((:dqn_num_params, LIB), Int64, (Ptr{Cvoid},), ccall((:dqn_group_engine, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Cint), g[], r))) for r in 0:ndev-1]
+    grp = Group(g[], ranks)
+    finalizer(x -> ccall((:dqn_group_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.g), grp)
+    return grp
+end
+function batch_train!(grp::Group)          # one data-parallel step: every shard samples its own batch, one gradient all-reduce
+    loss = Ref{Float32}(0); gn = Ref{Float32}(0)
+    rc = ccall((:dqn_group_train_step, LIB), Cint, (Ptr{Cvoid}, Ref{Float32}, Ref{Float32}), grp.g, loss, gn)
+    rc == 0 || throw(EngineError(rc, unsafe_string(ccall((:dqn_group_last_error, LIB), Cstring, (Ptr{Cvoid},), grp.g))))
+    return loss[], gn[]
 end
 
 end # module

@@ -57,8 +57,10 @@ def raw(tag, path, name):
 
 
 # names of the tensor-core launches of one eager step, in launch order (scripts/one_step.py, math mode 1, single lane)
-STEP_ORDER = ["conv1_fwd_target", "conv2_fwd_target", "conv3_fwd_target", "dense1_fwd_target", "conv1_fwd_online", "conv2_fwd_online", "conv3_fwd_online",
+# round 2: the first conv layer's forward has its own kernel (c1::conv1_fwd_kernel); the generic tcgen05 kernel takes the rest
+STEP_ORDER = ["conv2_fwd_target", "conv3_fwd_target", "dense1_fwd_target", "conv2_fwd_online", "conv3_fwd_online",
               "dense1_fwd_online", "dense1_wgrad", "dense1_dgrad", "conv3_wgrad", "conv3_dgrad", "conv2_wgrad", "conv2_dgrad", "conv1_wgrad"]
+C1_ORDER = ["conv1_fwd_target", "conv1_fwd_online"]
 
 
 def traffic(tag, path, name):
@@ -70,16 +72,26 @@ def traffic(tag, path, name):
     ik, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     ur, uw = unit.get(rows[1][ir], 1.0), unit.get(rows[1][iw], 1.0)
-    out, tc = {}, 0
+    out, tc, c1 = {}, 0, 0
+    extra = [m for m in ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") if m in hdr]
     for r in rows[2:]:
         b = float(r[ir]) * ur + float(r[iw]) * uw
-        if "tc_gemm_kernel" in r[ik]:
+        if "conv1_fwd_kernel" in r[ik]:
+            if c1 < len(C1_ORDER):
+                out[C1_ORDER[c1]] = {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80], **{m.split(".")[0]: float(r[hdr.index(m)]) for m in extra}}
+            c1 += 1
+        elif "tc_gemm_kernel" in r[ik]:
             if tc < len(STEP_ORDER):
-                out[STEP_ORDER[tc]] = {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80]}
+                out[STEP_ORDER[tc]] = {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80], **{m.split(".")[0]: float(r[hdr.index(m)]) for m in extra}}
             tc += 1
         else:
             key = "gather_rows" if "gather_rows" in r[ik] else ("adam" if "adam" in r[ik] else r[ik].split("(")[0])
             out.setdefault(key, {"dram_bytes": b, "ncu_us": float(r[it]), "kernel": r[ik][:80]})
+    try:
+        out["_commit"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+    except Exception:
+        pass
     dst = os.path.join(ROOT, "profiles", f"{tag}_traffic_{name}.json")
     json.dump(out, open(dst, "w"), indent=1)
     print(dst)

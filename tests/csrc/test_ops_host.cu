@@ -113,6 +113,18 @@ static void test_conv(int nimg, int IH, int IW, int Cin, int Cout, int KH, int K
     }
     for (size_t i = 0; i < acc.size(); ++i) RX[i] = (float)(acc[i] * act_deriv(Yp[i], ACT_RELU));
     cmp("conv_dgrad", dX, RX, 1e-3f);
+    if (ConvDgradMergedOp::geometry_ok(g)) {       // the stride-parity classes merged into the column dimension, over rearranged weights
+      const int TH = KH / S, TW = KW / S, Nm = S * S * Cin, Km = TH * TW * Cout;
+      std::vector<float> Wm((size_t)Km * Nm), dX2(X.size(), 123.f);
+      for (int k = 0; k < Km; ++k) for (int n = 0; n < Nm; ++n) {
+        const int ci = n % Cin, cls = n / Cin, ph = cls / S, pw = cls % S, co = k % Cout, tap = k / Cout, th = tap / TW, tw = tap % TW;
+        Wm[(size_t)k * Nm + n] = W[((size_t)((ph + S * th) * KW + (pw + S * tw)) * Cin + ci) * Cout + co];
+      }
+      ConvDgradMergedOp mg{}; mg.D = D.data(); mg.Wm = Wm.data(); mg.dX = dX2.data(); mg.Yprev = Yp.data(); mg.act = ACT_RELU; mg.apply_act = 1; mg.nimg = nimg; mg.g = g;
+      mg.vecA = mg.vecB = 1; mg.init();
+      igemm_host(mg);
+      cmp("conv_dgrad merged classes", dX2, RX, 1e-3f);
+    }
   }
 }
 
@@ -140,6 +152,8 @@ int main() {
   test_dense(4, 16, 6, ACT_SIGMOID, true);       // u8 observations
   test_conv(2, 20, 20, 4, 8, 8, 8, 4, true);     // conv1-like, u8 input
   test_conv(2, 9, 9, 8, 12, 4, 4, 2, false);     // conv2-like, stride 2
+  test_conv(2, 10, 10, 8, 12, 4, 4, 2, false);   // conv2 geometry family (even extents): also the class-merged input gradient
+  test_conv(1, 12, 12, 4, 8, 6, 6, 3, false);    // stride 3, nine classes merged
   test_conv(2, 7, 7, 8, 8, 3, 3, 1, false);      // conv3-like
   test_conv(1, 12, 11, 3, 5, 4, 3, 2, false);    // odd everything (scalar paths, uneven parity classes)
   test_conv(1, 10, 10, 4, 4, 3, 3, 2, false);    // KH % S != 0

@@ -286,6 +286,32 @@ def test_train_step_with_indices_equals_sampled_step(lib):
     eng.close(); eng2.close()
 
 
+def test_one_step_ahead_loop_equals_the_serial_loop(lib):
+    """add; step; read  vs  add_{k+1}; launch_{k+1}; read_k (dqn_step_result back=1, copies on their own stream): the same
+    transitions enter the ring at the same point of the device order, so every (loss, grad_norm) and the final state are BIT-identical."""
+    spec, net, tgt, buf, eng = setup_pair(lib, "conv_small")
+    spec2, net2, tgt2, buf2, eng2 = setup_pair(lib, "conv_small")
+    K = 12
+    batches = [util.random_transitions(spec, 5, seed=100 + k) for k in range(K)]
+    serial, ahead = [], []
+    for s, a, r, sp, done in batches:
+        eng.replay_add(s, a, r, sp, done, np.abs(r))
+        serial.append(eng.train_step())
+    for k, (s, a, r, sp, done) in enumerate(batches):
+        eng2.replay_add(s, a, r, sp, done, np.abs(r))
+        eng2.train_step_async()
+        if k:
+            ahead.append(eng2.step_result(1))
+    ahead.append(eng2.step_result(0))
+    assert serial == ahead
+    assert eng2.step_result(1) == serial[-2]                # the slot of the step before the latest is still intact
+    assert np.array_equal(eng.get_params(0), eng2.get_params(0))
+    assert np.array_equal(eng.sample_indices(7), eng2.sample_indices(7))
+    with pytest.raises(lib.DQNError):
+        eng2.step_result(2)
+    eng.close(); eng2.close()
+
+
 @pytest.mark.parametrize("name,dueling", [("c1_gridworld", True), ("conv_small", True), ("conv_small", False), ("testmdp", True)])
 def test_acting_q_values(lib, name, dueling):
     spec, net, tgt, buf, eng = setup_pair(lib, name, dueling)
@@ -387,14 +413,15 @@ def test_env_switches_keep_parity(lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     for tag, env in (("default", {}), ("merge", {"DQN_MERGE_FWD": "1"}), ("one_lane", {"DQN_STREAMS": "0"}), ("tiled_heads", {"DQN_FUSE_HEADS": "0"}), ("no_a8", {"DQN_NO_A8": "1"}),
-                     ("tail_split", {"DQN_TC_TAIL": "1"}), ("cp_async_feed", {"DQN_TC_TMA": "0"}), ("generic_conv1", {"DQN_TC_C1": "0"}), ("tma_wgrad", {"DQN_TC_TMA_WGRAD": "1"})):
+                     ("tail_split", {"DQN_TC_TAIL": "1"}), ("cp_async_feed", {"DQN_TC_TMA": "0"}), ("generic_conv1", {"DQN_TC_C1": "0"}), ("tma_wgrad", {"DQN_TC_TMA_WGRAD": "1"}),
+                     ("single_head_kernel", {"DQN_FUSE_HEAD_ALL": "1"}), ("classwise_dgrad", {"DQN_DGRAD_MERGE": "0"}), ("tma_dgrad", {"DQN_TC_TMA_DGRAD": "1"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, **env})
         line = [x for x in r.stdout.splitlines() if x.startswith("RES")]
         assert line, (tag, r.stdout[-500:], r.stderr[-1500:])
         outs[tag] = [float(x) for x in line[0].split()[1:]]
     ref = outs["default"]
     assert outs["one_lane"] == ref, outs                                    # same kernels, same order of operations: bit-identical
-    for tag in ("merge", "tiled_heads", "tail_split", "no_a8", "cp_async_feed", "generic_conv1", "tma_wgrad"):   # different summation order in a few contractions
+    for tag in ("merge", "tiled_heads", "tail_split", "no_a8", "cp_async_feed", "generic_conv1", "tma_wgrad", "single_head_kernel", "classwise_dgrad", "tma_dgrad"):   # different summation order in a few contractions
         for a, b in zip(outs[tag], ref):
             assert abs(a - b) <= 2e-5 * abs(b), (tag, outs)
 
