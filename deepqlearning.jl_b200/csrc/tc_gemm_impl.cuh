@@ -42,8 +42,10 @@ namespace tc {
 #ifdef TC_TRACE
 __device__ long long tc_trace[16384];    // per-stage timestamps of CTA 0 (producer warp 0, one converter warp, MMA warp 0): tuning aid of the selftest
 #define TRACE(st, ev) do { if (blockIdx.x == 0 && lane == 0 && (st) < 1000) tc_trace[(st) * 16 + (ev)] = clock64(); } while (0)
+#define ETRACE(ch, ev) do { if (blockIdx.x == 0 && lane == 0) tc_trace[16000 + (ch) * 4 + (ev)] = clock64(); } while (0)   // epilogue of tile 0, per chunk
 #else
 #define TRACE(st, ev) do { } while (0)
+#define ETRACE(ch, ev) do { } while (0)
 #endif
 
 // ---- TMA feed (FEED_TMA launches): the operand stages are moved by cp.async.bulk.tensor, one elected producer thread instead of
@@ -151,6 +153,9 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
 #ifndef TC_MAX_STAGES
 #define TC_MAX_STAGES 12
 #endif
+#ifndef TC_TMA64_NBUF
+#define TC_TMA64_NBUF 2            // accumulator sets of the TMA-fed BN = 64 tiles (2: three accumulators per set, see DB64 below)
+#endif
   static constexpr int FIT = (227 * 1024 - TAIL) / STAGE_BYTES;
   static constexpr int STAGES = (FIT > TC_MAX_STAGES ? TC_MAX_STAGES : FIT) / NGRP * NGRP;    // a group's slots keep their parity around the ring
   static_assert(STAGES <= 16, "barrier arrays");
@@ -159,8 +164,13 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
   // TMA feed (its idle loader warps become issuers): six issuing warps = product x k-step parity, each with an accumulator of its own
   // (R = 2 interleave for all three products) - a thread can issue one tcgen05 instruction per ~75 cycles, so four MMAs + commit per
   // stage and warp (375 cycles + the barrier wait) left the tensor pipe idle a third of the time (stage trace)
-  static constexpr int NMMA_W = TMA ? 6 : 3;
-  static constexpr int NACC = TMA ? 6 : R + 2;
+  // TMA feed, BN = 64 with two accumulator sets (DB64): six accumulators of 64 columns fill TMEM with ONE set, so the next tile's first
+  // MMA waited for the whole epilogue (~5500 cycles, a quarter of a 16-stage tile in the stage trace).  Three accumulators per set
+  // instead: main product over two (even / odd k steps, one issuing warp each), both correction products in the third, issued by
+  // ONE warp (8 MMAs per stage) so that their order - and the rounding - is fixed.
+  static constexpr bool DB64 = TMA && BN == 64 && NBUF == 2;
+  static constexpr int NMMA_W = DB64 ? 3 : (TMA ? 6 : 3);
+  static constexpr int NACC = DB64 ? 3 : (TMA ? 6 : R + 2);
   static constexpr int ACC_COLS = NBUF * NACC * BN;
   static constexpr int AST_FIT = (512 - ACC_COLS) / 64;
   static constexpr int AST = TMA ? 2 : 4;                              // A-operand stages resident in TMEM
@@ -438,7 +448,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
   // TMA feed: warps 4 and 5 (idle loaders) are MMA issuers 4 and 5; they run the issuer code at the end of this chain
-  const bool tma_issuer = TMA && (warp == 4 || warp == 5);
+  const bool tma_issuer = TMA && !L::DB64 && (warp == 4 || warp == 5);
   if (TMA && warp < LOAD_WARPS && !tma_issuer) {
     reg_dec<56>();
     // ================= TMA producer (warp 0: one thread, one or two instructions per stage) + B copiers (warps 1-2, cp.async) =================
@@ -799,7 +809,9 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #pragma unroll
             for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
           }
+          if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 0);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 1);
 #pragma unroll
           for (int a = 1; a < NACC; ++a) {                       // sum the accumulators with round-to-nearest adds
             if (!TMA && a == R && !a_lo) continue;
@@ -814,6 +826,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
             for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
           }
         }
+        if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 2);
         if (m < op.M) {
           if (vec && n0 + c0 + 15 < op.N) {
 #pragma unroll
@@ -835,6 +848,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
             }
           }
         }
+        if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 3);
       }
       tc_fence_before();                                       // this warp's tcgen05.ld are complete (wait::ld) and ordered before the arrive
       __syncwarp();
@@ -843,7 +857,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       ++etr;
       if (++buf == NBUF) { buf = 0; aph ^= 1; }
     }
-  } else if (!TMA && warp >= MMA_WARP0 + NMMA) {
+  } else if ((!TMA || L::DB64) && warp >= MMA_WARP0 + NMMA) {
     reg_dec<40>();                                             // idle warp that completes the MMA warpgroup
   } else {
     if (tma_issuer) reg_dec<56>(); else reg_dec<40>();         // (warps 4-5 share a warpgroup with the producer warps: same setmaxnreg)
@@ -852,10 +866,11 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
     // TMA feed: six warps, role = product + 3 * (k-step parity): two MMAs each per stage, every role its own accumulator.
     constexpr uint32_t idesc = make_idesc2(BM, BN, false, B_MN);   // A comes from TMEM: K-major by construction
     const int role = tma_issuer ? warp : warp - MMA_WARP0;     // TMA feed: warps 28-31 -> 0-3, warps 4-5 -> 4-5
-    const int prod = TMA ? role % 3 : role, half = TMA ? role / 3 : 0;
+    // DB64: role 0 = main product, even k steps; role 1 = main product, odd k steps; role 2 = both correction products
+    const int prod = L::DB64 ? (role == 2 ? 1 : 0) : (TMA ? role % 3 : role), half = L::DB64 ? (role == 1 ? 1 : 0) : (TMA ? role / 3 : 0);
     const uint64_t dbase = make_desc(0, L::B_LBO, L::B_SBO, L::B_LTYPE) + (uint64_t)((sbase + L::A_BYTES + (prod == 2 ? L::B_BYTES : 0)) >> 4);
     const uint32_t a_base = tmem + ACOL0 + (prod == 1 ? 32u : 0u);
-    const bool active = prod != 1 || a_lo;                     // a single-plane A (raw bytes) has no A_lo B_hi product
+    const bool active = L::DB64 || prod != 1 || a_lo;          // a single-plane A (raw bytes) has no A_lo B_hi product
     int s = 0; uint32_t ph = 0;
     int as = 0;
     int mtr = 0; (void)mtr;
@@ -867,7 +882,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       if (role == 0) TRACE(mtr, 11);
       tc_fence_after();
       // TMA feed: accumulator (prod, half) at column (2 prod + half) BN; cp.async feed: main accumulators 0..R-1, then one per correction
-      const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN) + (TMA ? (uint32_t)((2 * prod + half) * BN) : (prod == 0 ? 0u : (uint32_t)((R + prod - 1) * BN)));
+      const uint32_t acc = tmem + (uint32_t)(buf * NACC * BN) + (L::DB64 ? (uint32_t)(role * BN) : TMA ? (uint32_t)((2 * prod + half) * BN) : (prod == 0 ? 0u : (uint32_t)((R + prod - 1) * BN)));
       for (int it = 0; it < nk; ++it) {
         if (role == 0) TRACE(mtr, 8);
         mbar_wait(bar_full + 8 * s, ph);
@@ -879,7 +894,14 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
           const uint32_t more = it > 0 ? 1u : 0u;
 #ifndef TC_EXP_NOMMA
           if (active) {
-            if (TMA) {
+            if (L::DB64 && role == 2) {                          // A_lo B_hi (A from the lo half of the TMEM stage) and A_hi B_lo, k step by k step
+              const uint64_t d_lo = d0 + (uint64_t)(L::B_BYTES >> 4);
+#pragma unroll
+              for (int j = 0; j < BK / 8; ++j) {
+                if (a_lo) umma_tf32_ts(acc, a_t + j * 8, d0 + (uint64_t)(j * (L::B_KSTEP >> 4)), idesc, j > 0 ? 1u : more);
+                umma_tf32_ts(acc, a_t - 32 + j * 8, d_lo + (uint64_t)(j * (L::B_KSTEP >> 4)), idesc, (a_lo || j > 0) ? 1u : more);
+              }
+            } else if (TMA) {
 #pragma unroll
               for (int q = 0; q < BK / 16; ++q) {
                 const int j = half + 2 * q;                       // this role's k steps of the stage
@@ -1160,7 +1182,7 @@ bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz,
     }
     if (!a8 && tma) {
       if (bn == 32) tc_launch_v<32, 2, 2, false, Op, true>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
-      else tc_launch_v<64, 2, 1, false, Op, true>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
+      else tc_launch_v<64, 2, TC_TMA64_NBUF, false, Op, true>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
     } else if (!a8) {
       if (bn == 32) tc_launch_v<32, 2, 2, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);
       else tc_launch_v<64, 2, 1, false, Op>(e, ops, nops, nsplit, ws_stride, MT, NT, ntiles, tail_t0, tail_s, tm);

@@ -37,7 +37,7 @@ static int g_nsm = 148;
 static int g_feed = 0;            // 0: cp.async loaders, 1: TMA producer (where the operands are boxes; other launches fall back and say so)
 template <int BN, bool TMA, class Op>
 static void launch_tc_feed(const Op& op, int nz, int nsplit, float* ws, long long ws_stride, const float* zero, const tc::TmaMaps& tm) {
-  constexpr int R = BN == 32 ? 2 : TEST_R, NBUF = BN == 32 ? 2 : (TEST_R == 1 ? 2 : 1);
+  constexpr int R = BN == 32 ? 2 : TEST_R, NBUF = BN == 32 ? 2 : (TMA ? TC_TMA64_NBUF : (TEST_R == 1 ? 2 : 1));     // as launch_tc instantiates them
   using L = tc::Lay<BN, R, NBUF, Op::A_MCONTIG, !Op::B_KCONTIG, false, TMA>;
   static bool attr = false;
   if (!attr) { CKC(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, R, NBUF, false, Op, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM)); attr = true; }
@@ -277,6 +277,8 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
       for (int j = 0; j < 15; ++j) { if (j == 3 || j == 8 || j == 12) printf(" |"); printf(" %6lld", tr[it * 16 + j] ? tr[it * 16 + j] - t0 : -1); }
       printf("\n");
     }
+    printf("  epilogue of tile 0, per 16-column chunk: ld-issued ld-done summed stored\n");
+    for (int c = 0; c < 4; ++c) { printf("   c%d:", c); for (int k = 0; k < 4; ++k) printf(" %6lld", tr[16000 + c * 4 + k] ? tr[16000 + c * 4 + k] - t0 : -1); printf("\n"); }
     std::vector<long long> z(16384, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 16384));
   }
 #endif
