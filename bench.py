@@ -221,6 +221,107 @@ def run_drqn(args):
     eng.close()
 
 
+def mlp_config(args):
+    return {"workload": "BASELINE.json configs[1]: synthetic vector obs (dim 128, Float32), |A|=16, 3x256 Dense MLP + dueling (two towers), batch 256, "
+                        f"{args.buffer}-transition PER buffer, double-Q, Adam lr 1e-4",
+            "batch_per_gpu": 256, "buffer_per_gpu": args.buffer, "parallelism": "dp1",
+            "l2": "latency-bound by nature (0.82 GFLOP, 9.6 MB per step: SURVEY 8d); the gathered rows come from a 1 GB store, everything else lives in L2",
+            "math": args.math}
+
+
+def run_mlp(args):
+    """configs[1]: the PER step on the MLP.  Device-resident steps/s, end-to-end steps/s (4 transitions added from pinned host memory and the
+    scalars read back every step, one step ahead like the conv workload), CPU restatement beside it."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import util
+    spec = util.SPECS["c2_mlp"]
+    if args.impl == "reference":
+        from oracle.cpu_baseline import CpuBaseline
+        cb = CpuBaseline(spec["layers"], spec["obs"], spec["nA"], 256, args.buffer, False)
+        ts = cb.time_steps(args.steps, args.warmup)
+        total = float(np.sum(ts)); v = args.steps / total
+        print(json.dumps({"impl": "reference", "metric": "mlp_gradient_steps_per_sec", "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": mlp_config(args), "cpu_baseline": {"value": v, "unit": UNIT, "cores": cb.threads, "kind": "port", "sample": f"{args.steps} full steps"},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import dqn_b200 as lib
+    import oracle as O
+    math_mode = lib.MATH_3XTF32 if args.math_key == "3xtf32" else lib.MATH_FP32
+    cfg = lib.make_config(util.layer_descs(spec), (128,), 16, obs_dtype="f32", batch_size=256, buffer_size=args.buffer, learning_rate=1e-4, discount=0.99,
+                          seed=2, math_mode=math_mode, use_graph=not args.no_graph)
+    eng = lib.Engine(cfg)
+    eng.set_params(O.flat_params(util.make_oracle_net(spec, True, seed=1)), 0)
+    eng.sync_target()
+    eng.replay_fill_synthetic(args.buffer, seed=1000)
+    for _ in range(args.warmup):
+        eng.train_step_async()
+    eng.sync()
+    clocks = ClockSampler(0); clocks.start()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.train_step_async()
+    ms = eng.timer_stop()
+    loss, gn = eng.sync()
+    value = args.steps / (ms * 1e-3)
+    rng = np.random.default_rng(5)
+    s_h = lib._capi.pinned_empty((TRAIN_FREQ, 128), np.float32); sp_h = lib._capi.pinned_empty((TRAIN_FREQ, 128), np.float32)
+    s_h[...] = rng.normal(size=s_h.shape); sp_h[...] = rng.normal(size=sp_h.shape)
+    a_h = rng.integers(1, 17, TRAIN_FREQ).astype(np.int32); r_h = rng.uniform(-1, 1, TRAIN_FREQ).astype(np.float32)
+    d_h = np.zeros(TRAIN_FREQ, np.uint8); td_h = np.abs(r_h)
+    h2d = int(s_h.nbytes + sp_h.nbytes + a_h.nbytes + r_h.nbytes + d_h.nbytes + td_h.nbytes)
+    for _ in range(args.warmup):
+        eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h); eng.train_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
+        loss, gn = eng.train_step()
+    e2e_sync = args.steps / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.replay_add(s_h, a_h, r_h, sp_h, d_h, td_h)
+        eng.train_step_async()
+        if k:
+            loss, gn = eng.step_result(1)
+    loss, gn = eng.step_result(0)
+    e2e = args.steps / (time.perf_counter() - t0)
+    clk = clocks.stop()
+    eng.set_profiling(1)
+    for _ in range(5):
+        eng.train_step_async()
+    eng.sync()
+    prof = eng.get_profile()
+    eng.set_profiling(0)
+    tot = sum(k["ms"] * k["count"] / 5 for k in prof)
+    kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] * k["count"] / 5 / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"] * k["count"])][:10]
+    adam = next((k for k in prof if k["name"].startswith("adam")), None)
+    peaks = load_peaks()
+    roof = None
+    if adam:
+        ach = adam["bytes"] / (adam["ms"] * 1e-3) / 1e9
+        roof = {"kernel": "adam", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                "note": "9.3 MB of optimizer state per launch: L2-resident and launch-latency-bound at this size; the step as a whole is latency-bound (SURVEY 8d), "
+                        f"eager per-kernel sum {tot:.3f} ms"}
+    cpu = None
+    if not args.no_cpu:
+        from oracle.cpu_baseline import CpuBaseline
+        cb = CpuBaseline(spec["layers"], spec["obs"], spec["nA"], 256, args.buffer, False)
+        ts = cb.time_steps(args.cpu_steps, 3)
+        cpu = {"value": 1.0 / float(np.median(ts)), "unit": UNIT, "cores": cb.threads, "kind": "port",
+               "sample": f"median of {args.cpu_steps} full steps after 3 warm-ups (B=256, O(N) sampling over N={args.buffer})",
+               "label": "Flux-equivalent CPU restatement (torch-CPU); Julia is not installed in this image"}
+    print(json.dumps({"metric": "mlp_gradient_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": mlp_config(args),
+                      "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "sync_value": e2e_sync,
+                              "what": f"per step: add_exp! x{TRAIN_FREQ} from pinned host memory + batch_train! + (loss, grad_norm) read back; wall clock; one step ahead (sync_value: strictly serial)"},
+                      "gpu_launches": eng.launches_per_step() * args.steps, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+                      "last_loss": loss, "last_grad_norm": gn}))
+    eng.close()
+
+
 def workload_config(args, world):
     return {"workload": "BASELINE.json configs[2]: synthetic Atari-shaped obs 84x84x4 (u8), Nature-DQN conv + dueling, |A|=6, batch 256/GPU, "
                         f"{args.buffer}-transition PER shard/GPU, double-Q, Adam lr 1e-4",
@@ -241,13 +342,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
-    ap.add_argument("--workload", default="conv", choices=["conv", "drqn"],
-                    help="conv: BASELINE.json configs[2] (the headline, default); drqn: configs[3] (LSTM-128, seq 32, batch 64)")
+    ap.add_argument("--workload", default="conv", choices=["conv", "drqn", "mlp"],
+                    help="conv: BASELINE.json configs[2] (the headline, default); drqn: configs[3] (LSTM-128, seq 32, batch 64); mlp: configs[1]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     resolve_math(args)
     if args.workload == "drqn":
         return run_drqn(args)
+    if args.workload == "mlp":
+        return run_mlp(args)
     if args.impl == "reference":
         return run_reference(args)
 
