@@ -168,6 +168,7 @@ struct dqn_engine {
   int* ep_start_d = nullptr;
   // trunk hand-over to the towers (conv trunk: the last conv layer; LSTM trunk: the hidden states)
   float *trunk_on = nullptr, *trunk_tg = nullptr, *trunk_delta = nullptr; int trunk_act = 0;
+  int lstm_seq = 1;        // recurrent engines: the whole recurrence of a pass in one cluster launch (lstm_seq_*_kernel); 0 = one launch per time step
   int fuse_head_all = 1;   // output layers of all three passes + head + their input gradient in one launch (head_fused_kernel)
   float* hub = nullptr;    // per-sample Huber values of that kernel (deterministic loss reduction)
   int fuse_heads = 1;      // thin output layers (N <= 8) by heads_fwd_kernel / heads_dgrad_kernel instead of the tiled contraction
@@ -600,6 +601,7 @@ void enqueue_step_recurrent(E* e, bool sample) {
     CK(cudaGetLastError());
   }
   const bool conc = e->use_streams && !e->profiling;
+  const bool seq = e->lstm_seq && lstm_seq_supported(H);      // the whole recurrence in one cluster launch per pass (lstm.cuh)
   e->ev_next = 0;
   // ---- target network over s' (lane 2) beside the online network over s and s' (two chains per launch)
   if (conc) order_after(e, e->stream2, e->stream);
@@ -608,6 +610,13 @@ void enqueue_step_recurrent(E* e, bool sample) {
     lstm_xproj(e, e->theta_t, xs + (long long)TB * d, TB, e->xproj_tg, "lstm_xproj_target");
     lstm_broadcast(e, e->hs_tg, e->theta_t + e->h0_off, Bep);
     lstm_broadcast(e, e->cs_tg + 2 * blk, e->theta_t + e->c0_off, Bep);
+    if (seq) {
+      LstmSeqFwdArgs a{};
+      a.xproj[0] = e->xproj_tg; a.h0[0] = e->theta_t + e->h0_off; a.c0[0] = e->theta_t + e->c0_off; a.hs[0] = e->hs_tg + blk; a.cs[0] = nullptr; a.gates[0] = nullptr;
+      a.Wh = e->theta_t + e->wh.off; a.B = Bep; a.H = H; a.T = T;
+      Scope sc(e, "lstm_seq_target", 2.0 * TB * 4.0 * H * H, 4.0 * TB * 10.0 * H);
+      CK(lstm_seq_fwd_launch(a, 1, e->ls));
+    } else
     for (int t = 0; t < T; ++t) {
       LstmFwdArgs a{};
       a.xproj[0] = e->xproj_tg + (long long)t * Bep * N4; a.h_prev[0] = e->hs_tg + t * blk; a.h_out[0] = e->hs_tg + (t + 1) * blk;
@@ -621,6 +630,16 @@ void enqueue_step_recurrent(E* e, bool sample) {
   lstm_xproj(e, e->theta, xs, 2 * TB, e->xproj_on, "lstm_xproj_online");
   lstm_broadcast(e, e->hs_on, e->theta + e->h0_off, Bep);
   lstm_broadcast(e, e->cs_on, e->theta + e->c0_off, Bep);
+  if (seq) {
+    // chain 0: the s pass (states and gates kept for BPTT); chain 1: the s' pass
+    LstmSeqFwdArgs a{};
+    a.xproj[0] = e->xproj_on; a.xproj[1] = e->xproj_on + (long long)TB * N4;
+    a.h0[0] = a.h0[1] = e->theta + e->h0_off; a.c0[0] = a.c0[1] = e->theta + e->c0_off;
+    a.hs[0] = e->hs_on + blk; a.hs[1] = e->hs_on + (T + 1) * blk; a.cs[0] = e->cs_on + blk; a.cs[1] = nullptr; a.gates[0] = e->gates_s; a.gates[1] = nullptr;
+    a.Wh = e->theta + e->wh.off; a.B = Bep; a.H = H; a.T = T;
+    Scope sc(e, "lstm_seq_online", 2.0 * 2 * TB * 4.0 * H * H, 4.0 * 2 * TB * 10.0 * H);
+    CK(lstm_seq_fwd_launch(a, 2, e->ls));
+  } else
   for (int t = 0; t < T; ++t) {
     LstmFwdArgs a{};
     // chain 0: the s pass (states kept for BPTT); chain 1: the s' pass.  Block 0 of hs_on / cs_on is state0, block t+1 the s pass after step t,
@@ -649,12 +668,20 @@ void enqueue_step_recurrent(E* e, bool sample) {
     h.gamma = e->cfg.discount; h.alpha = e->cfg.alpha; h.eps = e->cfg.eps;
     h.inv_world_B = 1.0f / ((float)TB * (float)e->cfg.world);
     h.st = e->st;
+    h.part = e->hub; h.ticket = e->colsum_ticket + 3;
     Scope sc(e, "head_loss", 0, TB * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
-    head_loss_kernel<<<1, std::min(1024, (TB + 31) / 32 * 32), 0, e->stream>>>(h);
+    head_loss_kernel<<<(TB + 127) / 128, 128, 0, e->stream>>>(h);
     CK(cudaGetLastError());
   }
   backward(e, conc);                                           // the towers: weight gradients + the gradient into the hidden states (trunk_delta)
   // ---- BPTT through the cell
+  if (seq) {
+    LstmSeqBwdArgs a{};
+    a.dh_out = e->trunk_delta; a.Wh = e->theta + e->wh.off; a.gates = e->gates_s; a.cs = e->cs_on + blk; a.c0 = e->theta + e->c0_off; a.dgates = e->dgates;
+    a.B = Bep; a.H = H; a.T = T;
+    Scope sc(e, "lstm_seq_bptt", 2.0 * TB * 4.0 * H * H, 4.0 * TB * 14.0 * H);
+    CK(lstm_seq_bwd_launch(a, e->stream));
+  } else {
   {
     Scope sc(e, "lstm_transpose", 0, 8.0 * H * N4);
     transpose_kernel<<<dim3((N4 + 31) / 32, (H + 31) / 32), dim3(32, 8), 0, e->stream>>>(e->theta + e->wh.off, e->whT, H, N4);
@@ -668,6 +695,7 @@ void enqueue_step_recurrent(E* e, bool sample) {
     Scope sc(e, "lstm_bptt_step", 2.0 * Bep * 4.0 * H * H, 4.0 * Bep * 14.0 * H);
     lstm_bwd_step_kernel<<<dim3((H + 31) / 32, (Bep + LSTM_TB - 1) / LSTM_TB), dim3(32, LSTM_TB), LSTM_TB * N4 * sizeof(float), e->stream>>>(a);
     CK(cudaGetLastError());
+  }
   }
   if (conc) order_after(e, e->stream2, e->stream);
   {
@@ -1231,6 +1259,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_STREAMS"); e->use_streams = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_LSTM_SEQ"); e->lstm_seq = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_FUSE_HEAD_ALL"); e->fuse_head_all = v ? atoi(v) : 0; }   // one launch for output layers + loss + dH: measured slower (0.452 vs 0.415 ms/step) - it joins the three passes early
     build_topology(e);
     allocate(e);

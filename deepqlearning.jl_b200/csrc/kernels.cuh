@@ -53,15 +53,36 @@ __device__ __forceinline__ float pow_f32(float x, float y) { return (float)pow((
 // Sum-tree.  tree[1] root, children of k at 2k, 2k+1, leaves at P + i.  Internal nodes are always
 // recomputed as fl(left + right) - the tree is a pure function of its leaves (bit-exact vs oracle/sumtree.py).
 constexpr int TREE_TOP = 1024;            // nodes 1..1023 (the first 10 levels) are staged in shared memory by the sampler
+// One binary step of the descent: children (l, r) of the current node.
+__device__ __forceinline__ void tree_step(float& v, int& node, float l, float r) {
+  const bool left = (v < l) || (r == 0.f);
+  if (!left) v = __fsub_rn(v, l);
+  node = 2 * node + (left ? 0 : 1);
+}
+// Root-to-leaf descent.  Below the staged top every level would be one dependent L2 round trip (11 of them at P = 2^20); internal nodes
+// are always fl(left + right) of their children (tree_update / tree_level kernels), so the children AND grandchildren sums of a node
+// can be rebuilt bit-exactly from its eight great-grandchildren - one 32-byte load serves three levels.
 __device__ __forceinline__ int tree_descend(const float* __restrict__ tree, const float* __restrict__ top, int P, float u) {
   float v = __fmul_rn(u, top ? top[1] : tree[1]);
   int node = 1;
   while (node < P) {
-    const float2 ch = (top && 2 * node + 1 < TREE_TOP) ? *reinterpret_cast<const float2*>(top + 2 * node)
-                                                        : *reinterpret_cast<const float2*>(tree + 2 * node);
-    const bool left = (v < ch.x) || (ch.y == 0.f);
-    if (!left) v = __fsub_rn(v, ch.x);
-    node = 2 * node + (left ? 0 : 1);
+    if (top && 2 * node + 1 < TREE_TOP) {
+      const float2 ch = *reinterpret_cast<const float2*>(top + 2 * node);
+      tree_step(v, node, ch.x, ch.y);
+    } else if (8LL * node < 2LL * P) {                          // three levels from the eight great-grandchildren
+      const float4 a = *reinterpret_cast<const float4*>(tree + 8LL * node), b = *reinterpret_cast<const float4*>(tree + 8LL * node + 4);
+      const float g0 = __fadd_rn(a.x, a.y), g1 = __fadd_rn(a.z, a.w), g2 = __fadd_rn(b.x, b.y), g3 = __fadd_rn(b.z, b.w);
+      const int n0 = node;
+      tree_step(v, node, __fadd_rn(g0, g1), __fadd_rn(g2, g3));
+      const bool hi = node != 2 * n0;
+      tree_step(v, node, hi ? g2 : g0, hi ? g3 : g1);
+      const int q = node - 4 * n0;                              // grandchild 0..3
+      const float l = q == 0 ? a.x : q == 1 ? a.z : q == 2 ? b.x : b.z, r = q == 0 ? a.y : q == 1 ? a.w : q == 2 ? b.y : b.w;
+      tree_step(v, node, l, r);
+    } else {
+      const float2 ch = *reinterpret_cast<const float2*>(tree + 2 * node);
+      tree_step(v, node, ch.x, ch.y);
+    }
   }
   return node - P;
 }
@@ -382,6 +403,7 @@ struct HeadArgs {
   int B, nA, dueling, double_q, act_v, act_a;
   float gamma, alpha, eps, inv_world_B;      // inv_world_B = 1/(B*world): data-parallel ranks form one batch of B*world
   DevState* st;
+  float* part; unsigned int* ticket;         // several CTAs (recurrent step: trace_length * batch rows): per-CTA partial sums + arrival counter
 };
 constexpr int HEAD_MAX_ACTIONS = 64;
 
@@ -433,9 +455,11 @@ __device__ __forceinline__ float head_sample(const HeadArgs& h, int i, const flo
 
 __global__ void head_loss_kernel(HeadArgs h) {
   __shared__ float red[32];
+  __shared__ bool last;
   float hub = 0.f;
-  // one thread per sample; the recurrent step has trace_length * batch_size rows (> 1024): threads stride over them
-  for (int i = threadIdx.x; i < h.B; i += blockDim.x) {
+  // one thread per sample; grid-stride (one CTA for the feed-forward step; the recurrent step has trace_length * batch_size rows and
+  // runs several CTAs, whose partial sums the last CTA to arrive adds in CTA order: deterministic)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.B; i += gridDim.x * blockDim.x) {
     float q[HEAD_MAX_ACTIONS], qo[HEAD_MAX_ACTIONS], qt[HEAD_MAX_ACTIONS], da[HEAD_MAX_ACTIONS], dv = 0.f;
     const int nA = h.nA;
     dueling_q(h.V_on, h.A_on, h.B + i, nA, h.dueling, qo);
@@ -455,7 +479,24 @@ __global__ void head_loss_kernel(HeadArgs h) {
     s = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) { h.st->loss = __fdiv_rn(s, (float)h.B); h.st->gradmax_bits = 0u; }
+    if (gridDim.x == 1) {
+      if (threadIdx.x == 0) { h.st->loss = __fdiv_rn(s, (float)h.B); h.st->gradmax_bits = 0u; }
+      return;
+    }
+    if (threadIdx.x == 0) {
+      h.part[blockIdx.x] = s;
+      __threadfence();
+      last = atomicAdd(h.ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  if (gridDim.x == 1) return;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned int k = 0; k < gridDim.x; ++k) tot += reinterpret_cast<volatile float*>(h.part)[k];
+    h.st->loss = __fdiv_rn(tot, (float)h.B); h.st->gradmax_bits = 0u;
+    *h.ticket = 0u;
   }
 }
 

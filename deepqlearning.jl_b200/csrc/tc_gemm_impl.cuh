@@ -958,10 +958,11 @@ struct TmaApi {
   }
 };
 inline TmaApi& tma_api() { static TmaApi a; return a; }
-// conv input gradients through the TMA feed: correct (selftest) but not faster - their act' epilogue (stored-output loads at scattered
-// pixel offsets, six accumulators to drain) dominates: measured conv2 class-merged 48.1 us (TMA) vs 34.7 us (cp.async), conv3 37.6 vs 35.4.
-// Off unless DQN_TC_TMA_DGRAD=1 (the selftest switches it on to keep the path covered).
-inline int& tma_conv_dgrad_enabled() { static int v = 0; return v; }
+// conv input gradients through the TMA feed.  With six accumulators per tile they lost to the cp.async feed (their act' epilogue - stored-
+// output loads at scattered pixel offsets - sat in front of the next tile: conv2 class-merged 48.1 vs 34.7 us, conv3 37.6 vs 35.4); with two
+// accumulator sets (DB64) the epilogue is off the main loop and the step is ~1 % faster with them (0.408 vs 0.412 ms).  DQN_TC_TMA_DGRAD=0
+// puts them back on the cp.async feed.
+inline int& tma_conv_dgrad_enabled() { static int v = 1; return v; }
 inline bool tma_ok16(const void* p, long long ld_floats) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_floats % 4) == 0; }
 
 // row-major fp32 matrix [rows][ld], `cols` valid columns: box bc x br
@@ -1232,7 +1233,7 @@ void tc_init(dqn_engine* e) {
   { const char* v = getenv("DQN_TC_C1"); e->tc_c1 = v ? atoi(v) : 1; }
   { const char* v = getenv("DQN_TC_TMA_WGRAD"); e->tc_tma_wgrad = v ? atoi(v) : 0; }
   { const char* v = getenv("DQN_DGRAD_MERGE"); e->dgrad_merge = v ? atoi(v) : 1; }
-  { const char* v = getenv("DQN_TC_TMA_DGRAD"); tc::tma_conv_dgrad_enabled() = v ? atoi(v) : 0; }
+  { const char* v = getenv("DQN_TC_TMA_DGRAD"); tc::tma_conv_dgrad_enabled() = v ? atoi(v) : 1; }
   for (size_t l = 1; l < e->convs.size() && l < DQN_MAX_LAYERS; ++l)
     if (dqn::ConvDgradMergedOp::geometry_ok(e->convs[l].g)) e->wm[l] = dalloc<float>((long long)e->convs[l].w.K * e->convs[l].g.Cout);
   long long off = 0;

@@ -124,6 +124,24 @@ def test_recurrent_step_parity_config4(lib, math_mode):
     eng.close()
 
 
+@pytest.mark.parametrize("H,B,math_mode", [(64, 5, 0), (256, 11, 0), (64, 9, 1)])
+def test_recurrent_step_parity_cluster_kernels(lib, H, B, math_mode):
+    """hidden sizes the one-launch recurrence takes (lstm_seq_*_kernel: clusters of 8 CTAs, 8 batch rows each): partial last cluster,
+    several clusters, both contraction modes around it"""
+    net, tgt, buf, eng = build(lib, 20, H, 5, 7, B, True, True, math_mode, cap=40, L=12, lr=1e-3, seed=13)
+    for call in range(3):
+        check_recurrent_step(lib, net, tgt, buf, eng, call, True, 1e-3)
+    eng.close()
+
+
+def test_recurrent_per_step_kernels_at_config4(lib, monkeypatch):
+    """the fallback (one launch per time step: any hidden size) at the size where the cluster kernels normally run"""
+    monkeypatch.setenv("DQN_LSTM_SEQ", "0")
+    net, tgt, buf, eng = build(lib, 128, 128, 16, 32, 64, True, True, 0, cap=96, L=100, lr=1e-4, n_eps=96, seed=9)
+    check_recurrent_step(lib, net, tgt, buf, eng, 0, True, 1e-4)
+    eng.close()
+
+
 def test_recurrent_acting_carries_hidden_state(lib):
     net, tgt, buf, eng = build(lib, 12, 16, 4, 6, 5, True, True, 0)
     rng = np.random.default_rng(3)
