@@ -469,12 +469,13 @@ def main():
         step_flops = 26.36e9
         roof["step_tflops_algorithmic"] = step_flops * (args.steps / (ms * 1e-3)) / 1e12
         roof["traffic_source"] = (traffic.get("_file") or "") + ("@" + str(traffic.get("_commit")) if traffic.get("_commit") else "")
-        coll = [k for k in prof if k["name"] == "nccl_allreduce"]
+        coll = [k for k in prof if k["name"] in ("nccl_allreduce", "grad_allreduce")]
         if coll:                                                    # a collective is measured against NVLink, not HBM: bus bandwidth of a ring all-reduce
             b = sum(k["bytes"] for k in coll) / 2.0                 # payload bytes (the Scope records 2 x payload)
             t = sum(k["ms"] for k in coll) * 1e-3
             busbw = b * 2.0 * (world - 1) / world / t / 1e9
-            roof["collective"] = {"kernel": "nccl_allreduce", "payload_bytes": b, "busbw": busbw, "peak": 770.0, "unit": "GB/s", "frac": busbw / 770.0,
+            kind = {1: "ncclAllReduce", 2: "peer_allreduce_kernel (own kernel over NVLink peer memory, two-shot, owner computes)"}.get(eng.collective_kind(), "?")
+            roof["collective"] = {"kernel": kind, "payload_bytes": b, "busbw": busbw, "peak": 770.0, "unit": "GB/s", "frac": busbw / 770.0,
                                   "peak_note": "measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)"}
         # the HBM-bound kernels of the step, against the measured copy bandwidth (algorithmic bytes of DESIGN.md section 2)
         roof["hbm_kernels"] = [{"kernel": k["name"], "achieved": k["bytes"] / (k["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",

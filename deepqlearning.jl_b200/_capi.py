@@ -112,6 +112,7 @@ SIGNATURES = {
     "dqn_timer_start": (C.c_int, [_H]),
     "dqn_timer_stop": (C.c_int, [_H, _f32p]),
     "dqn_launches_per_step": (C.c_int, [_H]),
+    "dqn_collective_kind": (C.c_int, [_H]),
     "dqn_set_profiling": (C.c_int, [_H, C.c_int]),
     "dqn_get_profile": (C.c_int, [_H, C.c_char_p, C.c_int64]),
     "dqn_flush_l2": (C.c_int, [_H]),

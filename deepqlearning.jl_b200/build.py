@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdqn_b200.so")
 SOURCES = ["engine.cu"]
-DEPS = ["engine.cu", "igemm.cuh", "kernels.cuh", "tc_gemm.cuh", "tc_gemm_impl.cuh", "conv1_tc.cuh", "lstm.cuh", os.path.join("..", "..", "include", "dqn_b200.h")]
+DEPS = ["engine.cu", "igemm.cuh", "kernels.cuh", "tc_gemm.cuh", "tc_gemm_impl.cuh", "conv1_tc.cuh", "lstm.cuh", "peer_ar.cuh", os.path.join("..", "..", "include", "dqn_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -25,7 +25,9 @@
 #include "../../include/dqn_b200.h"
 #include "igemm.cuh"
 #include "kernels.cuh"
+#include <unistd.h>
 #include "lstm.cuh"
+#include "peer_ar.cuh"
 #include "tc_gemm.cuh"
 
 using namespace dqn;
@@ -56,6 +58,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& why) {
@@ -66,6 +69,7 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { why = "NCCL symbols missing"; return false; }
@@ -139,6 +143,7 @@ struct dqn_engine {
   // nccl
   ncclComm_t comm = nullptr;
   int nccl_ctas = 0;       // CTAs NCCL may use (NCCL_MAX_CTAS) = SMs the persistent grids leave free while a reduction is in flight
+  int ar_ctas = 0;         // CTAs of the reduction launched last
   int sm_reserve = 0;      // SMs currently held back from the persistent tensor-core grids
   // measurement
   cudaEvent_t t0 = nullptr, t1 = nullptr, copy_done = nullptr;
@@ -168,6 +173,9 @@ struct dqn_engine {
   int* ep_start_d = nullptr;
   // trunk hand-over to the towers (conv trunk: the last conv layer; LSTM trunk: the hidden states)
   float *trunk_on = nullptr, *trunk_tg = nullptr, *trunk_delta = nullptr; int trunk_act = 0;
+  // gradient all-reduce over NVLink peer memory (peer_ar.cuh); NCCL stays the fallback (no peer access, world > 8, DQN_PEER_AR=0)
+  int peer_ctas = 16;      // CTAs of a large reduction (DQN_PEER_CTAS, <= PEER_MAXG): bytes in flight over NVLink vs SMs taken from the GEMMs
+  bool peer_ar = false; PeerArArgs peer{}; unsigned long long* peer_flags = nullptr; void* peer_opened[2 * PEER_MAX] = {}; int peer_nopened = 0;
   int lstm_seq = 1;        // recurrent engines: the whole recurrence of a pass in one cluster launch (lstm_seq_*_kernel); 0 = one launch per time step
   int fuse_head_all = 1;   // output layers of all three passes + head + their input gradient in one launch (head_fused_kernel)
   float* hub = nullptr;    // per-sample Huber values of that kernel (deterministic loss reduction)
@@ -357,6 +365,22 @@ void prepare_dgrad_weights(E* e) {
   }
 }
 
+// sum of the gradient elements [off, off + n) over the ranks, in place, on stream s: peer-memory kernel or NCCL
+void allreduce_grad(E* e, long long off, long long n, int bucket, cudaStream_t s) {
+  if (e->peer_ar && (off % 4) == 0 && (n % 4) == 0 && n > 0) {
+    PeerArArgs a = e->peer; a.off = off; a.n = n; a.bucket = bucket;
+    const long long per4 = (n / 4 + a.world - 1) / a.world;
+    const int G = (int)std::max<long long>(1, std::min<long long>(e->peer_ctas, (per4 + 1023) / 1024));     // >= 2 float4 per thread, else fewer CTAs
+    peer_allreduce_kernel<<<G, 512, 0, s>>>(a);
+    CK(cudaGetLastError());
+    e->ar_ctas = G;
+    return;
+  }
+  ncclResult_t r = g_nccl.AllReduce(e->grad + off, e->grad + off, (size_t)n, ncclFloat, ncclSum, e->comm, s);
+  if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  e->ar_ctas = e->nccl_ctas;
+}
+
 void backward(E* e, bool conc, bool head_fused = false) {
   const int B = e->B;
   char nm[64];
@@ -464,9 +488,13 @@ void backward(E* e, bool conc, bool head_fused = false) {
     // layers hold 98 % of the parameters (12.9 of 13.2 MB in config 3), so almost all of the optimizer's HBM traffic leaves the critical path.
     order_after(e, e->stream3, e->stream2);
     if (e->cfg.world > 1) {
-      ncclResult_t r = g_nccl.AllReduce(e->grad + e->tower_off, e->grad + e->tower_off, (size_t)(e->nint - e->tower_off), ncclFloat, ncclSum, e->comm, e->stream3);
-      if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-      e->sm_reserve = e->nccl_ctas;                          // the conv backward below runs beside this reduction: leave its CTAs room
+      cudaStream_t keep = e->ls; e->ls = e->stream3;
+      {
+        Scope sc(e, "allreduce_dense", 0, 2.0 * (e->nint - e->tower_off) * 4);
+        allreduce_grad(e, e->tower_off, e->nint - e->tower_off, 0, e->stream3);
+      }
+      e->ls = keep;
+      e->sm_reserve = e->ar_ctas;                            // the conv backward below runs beside this reduction: leave its CTAs room
     }
     order_after(e, e->stream3, e->stream);
     enqueue_adam(e, e->tower_off, e->nint, e->stream3);
@@ -716,9 +744,8 @@ void enqueue_step_recurrent(E* e, bool sample) {
   }
   if (conc) order_after(e, e->stream, e->stream2);
   if (e->cfg.world > 1) {
-    Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
-    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)e->nint, ncclFloat, ncclSum, e->comm, e->stream);
-    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    Scope sc(e, "grad_allreduce", 0, 2.0 * e->nint * 4);
+    allreduce_grad(e, 0, e->nint, 0, e->stream);
   }
   enqueue_adam(e, 0, e->nint, e->stream);                      // state0 (h0, c0) has a zero gradient: Adam leaves it where it is
   {
@@ -812,12 +839,13 @@ void enqueue_step(E* e, bool sample) {
   if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
     const bool split = conc && !e->convs.empty();          // the Dense bucket is already in flight on the NCCL lane
-    Scope sc(e, "nccl_allreduce", 0, 2.0 * e->nint * 4);
+    Scope sc(e, "grad_allreduce", 0, 2.0 * e->nint * 4);
     const long long n = split ? e->tower_off : e->nint;
     cudaStream_t cs = split ? e->stream3 : e->stream;
     if (split) order_after(e, e->stream3, e->stream);
-    ncclResult_t r = g_nccl.AllReduce(e->grad, e->grad, (size_t)n, ncclFloat, ncclSum, e->comm, cs);
-    if (r != ncclSuccess) fail(DQN_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    cudaStream_t keep = e->ls; e->ls = cs;
+    allreduce_grad(e, 0, n, split ? 1 : 0, cs);
+    e->ls = keep;
     if (split) order_after(e, e->stream, e->stream3);
   }
   if (e->towers_updated) {
@@ -883,6 +911,7 @@ void fetch_scalars(E* e, float* loss, float* gn, int back = 0) {
     if (err & 2) fail(DQN_ERR_STATE, "non-positive priority (PER:78 @assert all(new_priorities .> 0f0))");
     if (err & 4) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
     if (err & 8) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+    if (err & 16) fail(DQN_ERR_NCCL, "gradient all-reduce over peer memory: a rank did not arrive within the spin limit");
   }
 }
 
@@ -1130,6 +1159,8 @@ void destroy(E* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->graph_sample) cudaGraphExecDestroy(e->graph_sample);
   if (e->graph_idx) cudaGraphExecDestroy(e->graph_idx);
+  for (int i = 0; i < e->peer_nopened; ++i) if (e->peer_opened[i]) cudaIpcCloseMemHandle(e->peer_opened[i]);
+  if (e->peer_flags) cudaFree(e->peer_flags);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   tc_destroy(e);
   void* ptrs[] = {e->theta, e->theta_t, e->adam_m, e->adam_v, e->grad, e->store_s, e->store_sp, e->done, e->act, e->rew, e->tree, e->st,
@@ -1232,6 +1263,62 @@ int dqn_nccl_unique_id(uint8_t id_out[DQN_NCCL_ID_BYTES]) {
   return DQN_OK;
 }
 
+// Peer-memory all-reduce set-up (peer_ar.cuh): every rank publishes its gradient vector and its flag block - as CUDA IPC handles between
+// processes, as plain pointers between the engines of one process (dqn_group_create) - through one ncclAllGather on the communicator
+// that exists anyway, and maps its peers'.  Any failure leaves NCCL in charge.
+struct PeerInfo { long long pid; unsigned long long grad, flags; int dev, pad; cudaIpcMemHandle_t hgrad, hflags; };
+void peer_setup(E* e) {
+  const char* v = getenv("DQN_PEER_AR");
+  const int W = e->cfg.world;
+  if ((v && atoi(v) == 0) || W > PEER_MAX || !g_nccl.AllGather) return;
+  { const char* c = getenv("DQN_PEER_CTAS"); if (c) e->peer_ctas = std::max(1, std::min(PEER_MAXG, atoi(c))); }
+  e->peer_flags = dalloc<unsigned long long>(PEER_FLAGS);
+  PeerInfo mine{};
+  mine.pid = (long long)getpid(); mine.grad = (unsigned long long)e->grad; mine.flags = (unsigned long long)e->peer_flags; mine.dev = e->cfg.device;
+  bool ok = cudaIpcGetMemHandle(&mine.hgrad, e->grad) == cudaSuccess && cudaIpcGetMemHandle(&mine.hflags, e->peer_flags) == cudaSuccess;
+  cudaGetLastError();
+  mine.pad = ok ? 1 : 0;
+  PeerInfo* d_all = dalloc<PeerInfo>(W + 1);
+  CK(cudaMemcpy(d_all + W, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  ncclResult_t r = g_nccl.AllGather(d_all + W, d_all, sizeof(PeerInfo), ncclChar, e->comm, e->stream);
+  if (r != ncclSuccess) { cudaFree(d_all); return; }
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<PeerInfo> all(W);
+  CK(cudaMemcpy(all.data(), d_all, sizeof(PeerInfo) * W, cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  PeerArArgs a{};
+  a.world = W; a.rank = e->cfg.rank; a.st = e->st;
+  for (int p = 0; p < W && ok; ++p) {
+    if (!all[p].pad) { ok = false; break; }
+    if (p == e->cfg.rank) { a.grad[p] = e->grad; a.flags[p] = e->peer_flags; continue; }
+    if (all[p].pid == mine.pid) {                              // same process: the pointers are valid here once peer access is on
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, e->cfg.device, all[p].dev) != cudaSuccess || !can) { ok = false; break; }
+      cudaError_t pe = cudaDeviceEnablePeerAccess(all[p].dev, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+      cudaGetLastError();
+      a.grad[p] = reinterpret_cast<float*>(all[p].grad); a.flags[p] = reinterpret_cast<unsigned long long*>(all[p].flags);
+    } else {
+      void* g = nullptr; void* f = nullptr;
+      if (cudaIpcOpenMemHandle(&g, all[p].hgrad, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      e->peer_opened[e->peer_nopened++] = g;
+      if (cudaIpcOpenMemHandle(&f, all[p].hflags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      e->peer_opened[e->peer_nopened++] = f;
+      a.grad[p] = reinterpret_cast<float*>(g); a.flags[p] = reinterpret_cast<unsigned long long*>(f);
+    }
+  }
+  cudaGetLastError();
+  // every rank must take the same path: agree through one more reduction (sum of the ok flags == world)
+  float* d_ok = dalloc<float>(1);
+  const float mine_ok = ok ? 1.f : 0.f;
+  CK(cudaMemcpy(d_ok, &mine_ok, sizeof(float), cudaMemcpyHostToDevice));
+  r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclFloat, ncclSum, e->comm, e->stream);
+  float tot = 0.f;
+  if (r == ncclSuccess) { CK(cudaStreamSynchronize(e->stream)); CK(cudaMemcpy(&tot, d_ok, sizeof(float), cudaMemcpyDeviceToHost)); }
+  cudaFree(d_ok);
+  if ((int)(tot + 0.5f) == W) { e->peer = a; e->peer_ar = true; }
+}
+
 int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return DQN_ERR_INVALID; }
   *out = nullptr;
@@ -1282,6 +1369,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
         CK(cudaStreamSynchronize(cs));
       }
     }
+    if (cfg->world > 1) peer_setup(e);
     CK(cudaStreamSynchronize(e->stream));
     *out = e;
     return DQN_OK;
@@ -1726,6 +1814,7 @@ int dqn_timer_stop(dqn_engine_t* h, float* ms) {
   return guard(h, [&] { CK(cudaEventRecord(h->t1, h->stream)); CK(cudaEventSynchronize(h->t1)); CK(cudaEventElapsedTime(ms, h->t0, h->t1)); });
 }
 int dqn_launches_per_step(const dqn_engine_t* h) { return h ? h->launches_per_step : 0; }
+int dqn_collective_kind(const dqn_engine_t* h) { return !h || h->cfg.world <= 1 ? 0 : (h->peer_ar ? 2 : 1); }
 int dqn_set_profiling(dqn_engine_t* h, int on) {
   return guard(h, [&] {
     CK(cudaStreamSynchronize(h->stream));

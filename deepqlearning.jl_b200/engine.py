@@ -296,6 +296,10 @@ class Engine:
     def launches_per_step(self):
         return int(lib.dqn_launches_per_step(self.h))
 
+    def collective_kind(self):
+        """0: none (world 1), 1: NCCL, 2: the engine's own all-reduce over NVLink peer memory"""
+        return int(lib.dqn_collective_kind(self.h))
+
     def set_profiling(self, on):
         self._ck(lib.dqn_set_profiling(self.h, int(on)))
 

@@ -195,6 +195,8 @@ int dqn_get_activation(dqn_engine_t* h, int stage, int tower, float* out, int64_
 int dqn_timer_start(dqn_engine_t* h);                            /* CUDA event on the engine's stream */
 int dqn_timer_stop(dqn_engine_t* h, float* ms);                  /* second event, synchronise, elapsed */
 int dqn_launches_per_step(const dqn_engine_t* h);                /* kernels of ours launched by one dqn_train_step */
+int dqn_collective_kind(const dqn_engine_t* h);                  /* gradient all-reduce of this engine: 0 none (world 1), 1 NCCL, 2 the engine's own
+                                                                  * kernel over NVLink peer memory (peer_ar.cuh) */
 int dqn_set_profiling(dqn_engine_t* h, int on);                  /* eager launches bracketed by events */
 int dqn_get_profile(dqn_engine_t* h, char* buf, int64_t buflen); /* "name ms count bytes flops\n" per kernel */
 int dqn_flush_l2(dqn_engine_t* h);                               /* writes a buffer larger than L2 */

@@ -134,6 +134,15 @@ function batch_train!(e::Engine)
     return loss[], gn[]
 end
 
+# One step ahead: the scalars are only logged (src/solver.jl:147-166), so the host may launch step k+1 before it reads step k's:
+#   add_exp!(...); batch_train_async!(e); loss_k, gn_k = step_result(e, 1)
+batch_train_async!(e::Engine) = check(e, ccall((:dqn_train_step_async, LIB), Cint, (Ptr{Cvoid},), e.h))
+function step_result(e::Engine, back::Integer = 0)
+    loss = Ref{Float32}(0); gn = Ref{Float32}(0)
+    check(e, ccall((:dqn_step_result, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Float32}, Ref{Float32}), e.h, back, loss, gn))
+    return loss[], gn[]
+end
+
 # Flux.loadparams!(target_q, Flux.params(active_q))   src/solver.jl:142-145
 sync_target!(e::Engine) = check(e, ccall((:dqn_sync_target, LIB), Cint, (Ptr{Cvoid},), e.h))
 

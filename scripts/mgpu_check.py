@@ -16,7 +16,10 @@ import util                  # noqa: E402
 cp = lib.ControlPlane(2)
 rank, world = cp.rank, cp.world
 ok = True
-for name, mode in (("testmdp", 0), ("conv_small", 0), ("conv_small", 1)):
+finals = {}
+for name, mode, ar in (("testmdp", 0, "peer"), ("conv_small", 0, "peer"), ("conv_small", 1, "peer"), ("conv_small", 1, "nccl")):
+    # ar: the engine's own all-reduce over NVLink peer memory (default when the ranks can map each other's memory) or NCCL (DQN_PEER_AR=0)
+    os.environ["DQN_PEER_AR"] = "1" if ar == "peer" else "0"
     spec = util.SPECS[name]
     B = spec["B"]
     nccl_id = cp.broadcast_bytes(lib.nccl_unique_id() if rank == 0 else None, 128)     # a ncclUniqueId is single-use: one per communicator
@@ -50,7 +53,17 @@ for name, mode in (("testmdp", 0), ("conv_small", 0), ("conv_small", 1)):
     tsum = cp.sum_over_ranks(float(np.abs(theta).sum()))
     same = abs(tsum / world - float(np.abs(theta).sum())) <= 1e-9 * tsum
     gmax = cp.max_over_ranks(gn)
-    print(f"[rank {rank}] {name} mode {mode}: grad rel err vs combined-batch oracle {err:.2e}, params identical across ranks {same}, grad_norm {gn:.6e} (max {gmax:.6e})", flush=True)
+    kind = eng.collective_kind()
+    ok = ok and kind == (2 if ar == "peer" else 1)
+    for _ in range(6):                                   # more steps through the captured graph (two buckets per step, fresh epochs every step)
+        eng.train_step()
+    th2 = eng.get_params(0)
+    t2 = cp.sum_over_ranks(float(np.abs(th2).sum()))
+    same = same and abs(t2 / world - float(np.abs(th2).sum())) <= 1e-9 * t2 and bool(np.isfinite(th2).all())
+    finals[(name, mode, ar)] = th2
+    if ar == "nccl" and world == 2:                      # a sum of two terms has one rounding whichever way it is ordered: both reductions agree exactly
+        same = same and np.array_equal(th2, finals[(name, mode, "peer")])
+    print(f"[rank {rank}] {name} mode {mode} all-reduce {ar} (kind {kind}): grad rel err vs combined-batch oracle {err:.2e}, params identical across ranks {same}, grad_norm {gn:.6e} (max {gmax:.6e})", flush=True)
     ok = ok and err < 2e-4 and same and gmax == gn
     eng.close()
 cp.barrier()
