@@ -137,6 +137,13 @@ struct dqn_engine {
   uint8_t* add_stage[2] = {nullptr, nullptr}; long long add_stage_bytes[2] = {0, 0};
   cudaEvent_t add_free[2] = {nullptr, nullptr};                // staging slot consumed by its ingest kernels
   unsigned long long add_seq = 0;
+  // dqn_replay_add's ingest kernels run on their own lane: behind the priority update of the step in flight (which publishes a tree
+  // epoch in device memory; an external event node in the captured graph cost 8 us per step) instead of behind the whole step, so a
+  // caller that runs one step ahead never leaves the GPU idle between steps.  Every other call joins the lane first (guard).
+  cudaStream_t ingest_stream = nullptr; cudaEvent_t ingest_done = nullptr, main_mark = nullptr;
+  int ingest_lane = 1;                                         // DQN_INGEST_LANE=0: ingest on the main stream, behind the whole step in flight
+  bool ingest_pending = false;                                 // ingest work the main stream has not been ordered behind yet
+  bool main_dirty = true;                                      // main-stream work since the last step that the ingest lane is not ordered behind
   long long* idx_h = nullptr;                                  // pinned
   // graph
   cudaGraphExec_t graph_sample = nullptr, graph_idx = nullptr;
@@ -750,7 +757,7 @@ void enqueue_step_recurrent(E* e, bool sample) {
   enqueue_adam(e, 0, e->nint, e->stream);                      // state0 (h0, c0) has a zero gradient: Adam leaves it where it is
   {
     Scope sc(e, "end_of_step", 0, 12);
-    tree_update_kernel<<<1, 32, 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, 0, 0, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
+    tree_update_kernel<<<1, 32, 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, 0, 0, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev, 1);
     CK(cudaGetLastError());
   }
 }
@@ -828,8 +835,10 @@ void enqueue_step(E* e, bool sample) {
     cudaStream_t keep = e->ls; e->ls = e->stream3;
     {
       Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
+      // (publishes the tree epoch: from here on the step touches neither the replay rows nor the tree - new transitions may be ingested
+      //  beside its reverse pass, dqn_replay_add)
       tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream3>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
-                                                                                  1, e->st, 0, e->cfg.adam_beta1, e->cfg.adam_beta2, 0, nullptr);
+                                                                                  1, e->st, 0, e->cfg.adam_beta1, e->cfg.adam_beta2, 0, nullptr, 1);
       CK(cudaGetLastError());
     }
     e->ls = keep;
@@ -860,7 +869,7 @@ void enqueue_step(E* e, bool sample) {
   } else {
     Scope sc(e, "sumtree_update", 0, B * 12.0 * 21);
     tree_update_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, e->idx_d, e->newp, e->cfg.prioritized_replay ? B : 0,
-                                                                               1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev);
+                                                                               1, e->st, 1, e->cfg.adam_beta1, e->cfg.adam_beta2, sample ? 1 : 0, e->host_out_dev, 1);
     CK(cudaGetLastError());
   }
 }
@@ -889,6 +898,7 @@ void run_step(E* e, bool sample) {
   }
   e->n_launched += 1;
   CK(cudaEventRecord(e->step_ev[e->n_launched & 1], e->stream));
+  e->main_dirty = e->lstm;      // the ingest lane is ordered behind this step through tree_free (feed-forward steps record it)
 }
 
 // Scalars of the step launched `back` steps before the latest one (0: the latest; 1: the one before it, which can be read while the
@@ -911,6 +921,7 @@ void fetch_scalars(E* e, float* loss, float* gn, int back = 0) {
     if (err & 2) fail(DQN_ERR_STATE, "non-positive priority (PER:78 @assert all(new_priorities .> 0f0))");
     if (err & 4) fail(DQN_ERR_STATE, "td_err + eps <= 0 (PER:66 @assert)");
     if (err & 8) fail(DQN_ERR_INVALID, "action index outside 1..n_actions");
+    if (err & 32) fail(DQN_ERR_STATE, "ingest lane: the step in flight never published its tree epoch");
     if (err & 16) fail(DQN_ERR_NCCL, "gradient all-reduce over peer memory: a rank did not arrive within the spin limit");
   }
 }
@@ -949,7 +960,9 @@ void set_curr_size(E* e) {
 }
 
 // n transitions already on the device (Flux layout) -> ring
-void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const uint8_t* sp, const uint8_t* d, const float* td0, long long n, long long* slots) {
+void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const uint8_t* sp, const uint8_t* d, const float* td0, long long n, long long* slots,
+                   cudaStream_t st = nullptr) {
+  if (!st || n > 4096) st = e->stream;                       // (a bulk add rebuilds the whole tree: main stream only)
   const int C = e->hwc ? e->cfg.obs_c : 1;
   const int HW = e->hwc ? e->cfg.obs_h * e->cfg.obs_w : (int)e->obs_elems;
   if (n > e->cap) fail(DQN_ERR_INVALID, "adding %lld transitions to a buffer of %lld", n, e->cap);
@@ -957,12 +970,12 @@ void ingest_device(E* e, const uint8_t* s, const int* a, const float* r, const u
   for (long long t0 = 0; t0 < n; t0 += 32768) {
     const long long cnt = std::min<long long>(32768, n - t0);
     dim3 grid((unsigned)std::min<long long>((e->obs_elems + 255) / 256, 64), (unsigned)cnt);
-    ingest_kernel<<<grid, 256, 0, e->stream>>>(s, sp, a, r, d, td0, t0, e->cursor, e->cap, C, HW, e->elem_bytes, e->store_s, e->store_sp,
+    ingest_kernel<<<grid, 256, 0, st>>>(s, sp, a, r, d, td0, t0, e->cursor, e->cap, C, HW, e->elem_bytes, e->store_s, e->store_sp,
                                                e->act, e->rew, e->done, e->tree, e->P, slots, e->cfg.alpha, e->cfg.eps, e->cfg.n_actions, new_size, e->st);
     CK(cudaGetLastError());
   }
   if (n <= 4096) {
-    tree_update_kernel<<<1, (int)std::min<long long>(1024, (n + 31) / 32 * 32), 0, e->stream>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0, nullptr);
+    tree_update_kernel<<<1, (int)std::min<long long>(1024, (n + 31) / 32 * 32), 0, st>>>(e->tree, e->P, slots, nullptr, (int)n, 0, e->st, 0, 1.0, 1.0, 0, nullptr);
     CK(cudaGetLastError());
   } else rebuild_tree(e);
   e->cursor = (e->cursor + n) % e->cap;
@@ -1147,6 +1160,9 @@ void allocate(E* e) {
   CK(cudaHostAlloc(&e->idx_h, sizeof(long long) * B, cudaHostAllocDefault));
   CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1)); CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ingest_done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->main_mark, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CK(cudaEventCreateWithFlags(&e->step_ev[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->add_free[i], cudaEventDisableTiming));
@@ -1185,6 +1201,8 @@ void destroy(E* e) {
     if (e->add_stage[i]) cudaFree(e->add_stage[i]);
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->ingest_stream) { cudaStreamSynchronize(e->ingest_stream); cudaStreamDestroy(e->ingest_stream); }
+  for (cudaEvent_t ev : {e->ingest_done, e->main_mark}) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->evs) cudaEventDestroy(ev);
   if (e->stream3) cudaStreamDestroy(e->stream3);
   if (e->stream2) cudaStreamDestroy(e->stream2);
@@ -1206,10 +1224,15 @@ void gather_params(E* e, const float* dev, float* flat) {
   for (long long i = 0; i < e->nflux; ++i) flat[i] = h[(size_t)e->perm[(size_t)i]];
 }
 
-template <class F> int guard(E* e, F&& f) {
+// ro: the call enqueues nothing on the main stream that touches the replay state (scalar fetches; dqn_replay_add, which has its own lane)
+template <class F> int guard(E* e, F&& f, bool ro = false) {
   try {
     if (!e) return DQN_ERR_INVALID;
     CK(cudaSetDevice(e->cfg.device));
+    if (!ro) {
+      if (e->ingest_pending) { CK(cudaStreamWaitEvent(e->stream, e->ingest_done, 0)); e->ingest_pending = false; }
+      e->main_dirty = true;
+    }
     f();
     return DQN_OK;
   } catch (const Err& x) {
@@ -1347,6 +1370,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_LSTM_SEQ"); e->lstm_seq = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_INGEST_LANE"); e->ingest_lane = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_FUSE_HEAD_ALL"); e->fuse_head_all = v ? atoi(v) : 0; }   // one launch for output layers + loss + dH: measured slower (0.452 vs 0.415 ms/step) - it joins the three passes early
     build_topology(e);
     allocate(e);
@@ -1434,11 +1458,19 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
     // The host -> device copies go to one of two staging areas on their own stream, so they run beside whatever step is still in
     // flight on the engine's stream; only the ingest kernels (and the sum-tree refresh) are ordered behind that step.  The call
     // returns when the copies are done - the caller's buffers are free again - with the ingest still in flight.
+    // Small adds (the per-env-step case) are ingested on their own lane, ordered behind the priority update of the step in flight only;
+    // a bulk add goes to the main stream like every other call.
+    const bool lane = h->ingest_lane && chunk <= 4096 && n <= 4096;
+    if (!lane) {
+      if (h->ingest_pending) { CK(cudaStreamWaitEvent(h->stream, h->ingest_done, 0)); h->ingest_pending = false; }
+      h->main_dirty = true;
+    }
+    cudaStream_t is = lane ? h->ingest_stream : h->stream;
     for (long long t0 = 0; t0 < n; t0 += chunk) {
       const long long c = std::min(chunk, n - t0);
       const int slot = (int)(h->add_seq++ & 1);
       if (h->add_stage_bytes[slot] < need) {
-        if (h->add_stage[slot]) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->add_stage[slot])); h->add_stage[slot] = nullptr; h->add_stage_bytes[slot] = 0; }
+        if (h->add_stage[slot]) { CK(cudaStreamSynchronize(h->stream)); CK(cudaStreamSynchronize(h->ingest_stream)); CK(cudaFree(h->add_stage[slot])); h->add_stage[slot] = nullptr; h->add_stage_bytes[slot] = 0; }
         CK(cudaMalloc(&h->add_stage[slot], need)); h->add_stage_bytes[slot] = need;
       }
       uint8_t* p = h->add_stage[slot];
@@ -1454,12 +1486,21 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
       CK(cudaMemcpyAsync(dtd, td0 + t0, c * 4, cudaMemcpyHostToDevice, h->copy_stream));
       CK(cudaMemcpyAsync(dd, done + t0, c, cudaMemcpyHostToDevice, h->copy_stream));
       CK(cudaEventRecord(h->copy_done, h->copy_stream));
-      CK(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
-      ingest_device(h, ds, da, dr, dsp, dd, dtd, c, slots);
-      CK(cudaEventRecord(h->add_free[slot], h->stream));
+      if (lane) {
+        if (h->main_dirty) {                                  // main-stream work of earlier calls (fills, priority updates, reads): all of it first
+          CK(cudaEventRecord(h->main_mark, h->stream)); CK(cudaStreamWaitEvent(is, h->main_mark, 0)); h->main_dirty = false;
+        }
+        // the step in flight (if any) must have gathered its rows and refreshed its priorities: it says so in device memory (tree epoch)
+        epoch_wait_kernel<<<1, 32, 0, is>>>(h->st, (unsigned int)h->n_launched);
+        CK(cudaGetLastError());
+      }
+      CK(cudaStreamWaitEvent(is, h->copy_done, 0));
+      ingest_device(h, ds, da, dr, dsp, dd, dtd, c, slots, is);
+      CK(cudaEventRecord(h->add_free[slot], is));
+      if (lane) { CK(cudaEventRecord(h->ingest_done, is)); h->ingest_pending = true; }
     }
     if (n > 0) CK(cudaEventSynchronize(h->copy_done));
-  });
+  }, /*ro=*/true);
 }
 
 int dqn_replay_add_device(dqn_engine_t* h, const void* s, const int32_t* a, const float* r, const void* sp, const uint8_t* done,
@@ -1597,8 +1638,8 @@ int dqn_train_step_with_indices(dqn_engine_t* h, const int64_t* idx, float* loss
   });
 }
 int dqn_train_step_async(dqn_engine_t* h) { return guard(h, [&] { run_step(h, true); }); }
-int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm); }); }
-int dqn_step_result(dqn_engine_t* h, int back, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm, back); }); }
+int dqn_sync(dqn_engine_t* h, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm); }, /*ro=*/true); }
+int dqn_step_result(dqn_engine_t* h, int back, float* loss, float* grad_norm) { return guard(h, [&] { fetch_scalars(h, loss, grad_norm, back); }, /*ro=*/true); }
 
 int dqn_q_values(dqn_engine_t* h, int which, const void* obs, int64_t n, float* q_out) {
   return guard(h, [&] {

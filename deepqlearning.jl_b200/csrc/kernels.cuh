@@ -18,6 +18,8 @@ struct DevState {
   int error;                      // sticky error flags raised by kernels (bit 0: sampler did not converge,
                                   //   bit 1: non-positive priority PER:78, bit 2: td0+eps <= 0 PER:66, bit 3: bad action)
   unsigned int step;              // gradient steps finished so far: step s publishes its scalars to host slot s & 1
+  unsigned int tree_epoch;        // s once step s has gathered its rows and refreshed its priorities: from then on it touches neither the
+  unsigned int pad;               //   replay rows nor the tree, and new transitions may be ingested beside the rest of it (epoch_wait_kernel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -259,7 +261,7 @@ __global__ void scale_block_kernel(const float* __restrict__ w, float* __restric
 // sampling-call counter) so that a captured graph advances its own state.
 __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long long* __restrict__ idx, const float* __restrict__ newp,
                                    int n, int write_leaves, DevState* st, int end_of_step, double beta1, double beta2,
-                                   int advance_sampler, float* __restrict__ publish) {
+                                   int advance_sampler, float* __restrict__ publish, int publish_epoch = 0) {
   const int j = threadIdx.x;
   if (write_leaves) {
     for (int t = j; t < n; t += blockDim.x) {
@@ -278,6 +280,10 @@ __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long l
       __syncthreads();
     }
   }
+  if (publish_epoch && j == 0) {          // (all levels are written: the barrier above closed the last one)
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->tree_epoch), "r"(st->step + 1u) : "memory");
+  }
   if (end_of_step && j == 0) {
     st->b1p *= beta1; st->b2p *= beta2;
     if (advance_sampler) st->sample_call += 1;
@@ -287,6 +293,20 @@ __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long l
       publish[0] = st->loss; publish[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(publish)[2] = st->error;
       reinterpret_cast<unsigned int*>(publish)[3] = s;
     }
+  }
+}
+
+// First kernel of an ingest on the ingest lane: returns once step `expected` (the one in flight when dqn_replay_add was called) has
+// published its tree epoch.  One warp, sleeping between polls: it shares an SM with a persistent GEMM CTA without taking anything from it.
+__global__ void epoch_wait_kernel(DevState* st, unsigned int expected) {
+  if (threadIdx.x != 0) return;
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->tree_epoch) : "memory");
+    if (v >= expected) break;
+    if (clock64() - t0 > 4000000000LL) { atomicOr(&st->error, 32); break; }
+    __nanosleep(200);
   }
 }
 

@@ -286,10 +286,14 @@ def test_train_step_with_indices_equals_sampled_step(lib):
     eng.close(); eng2.close()
 
 
-def test_one_step_ahead_loop_equals_the_serial_loop(lib):
+@pytest.mark.parametrize("ingest_lane", ["1", "0"])
+def test_one_step_ahead_loop_equals_the_serial_loop(lib, monkeypatch, ingest_lane):
     """add; step; read  vs  add_{k+1}; launch_{k+1}; read_k (dqn_step_result back=1, copies on their own stream): the same
     transitions enter the ring at the same point of the device order, so every (loss, grad_norm) and the final state are BIT-identical."""
+    # ingest lane on: the transitions of step k+1 are written into the ring beside the reverse pass of step k (behind its tree epoch);
+    # off: behind the whole step.  Same order of effects either way.
     spec, net, tgt, buf, eng = setup_pair(lib, "conv_small")
+    monkeypatch.setenv("DQN_INGEST_LANE", ingest_lane)
     spec2, net2, tgt2, buf2, eng2 = setup_pair(lib, "conv_small")
     K = 12
     batches = [util.random_transitions(spec, 5, seed=100 + k) for k in range(K)]
