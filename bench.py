@@ -391,6 +391,7 @@ def main():
     ms = eng.timer_stop()
     loss, gn = eng.sync()
     barrier()
+    ms_by_rank = cp.gather_over_ranks(ms / args.steps)
     ms = cp.max_over_ranks(ms)
     launches = eng.launches_per_step() * args.steps
     value = world * args.steps / (ms * 1e-3)
@@ -494,7 +495,8 @@ def main():
 
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "ms_per_step": ms / args.steps, "ms_per_step_by_rank": [round(v, 5) for v in ms_by_rank],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": workload_config(args, world),
                           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                                   "what": f"per step: add_exp! x{TRAIN_FREQ} from pinned host memory + batch_train! + (loss, grad_norm) read back; wall clock",

@@ -51,6 +51,16 @@ class ControlPlane:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t[0])
 
+    def gather_over_ranks(self, x):
+        """list of every rank's value, in rank order, on every rank"""
+        if self.dist is None:
+            return [float(x)]
+        import torch
+        t = torch.zeros(self.world, dtype=torch.float64)
+        t[self.rank] = float(x)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
     def close(self):
         if self.dist is not None and self.dist.is_initialized():
             self.dist.destroy_process_group()

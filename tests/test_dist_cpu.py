@@ -33,6 +33,7 @@ def _worker(rank, world, port, out):
     assert got == bytes(range(128))
     cp.barrier()
     assert cp.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+    assert cp.gather_over_ranks(3.0 * rank) == [3.0 * r for r in range(world)]
     seeds = d.shard_seeds(0, rank)
     assert seeds["weights"] == 1 and seeds["replay"] == 1000 + rank
 
