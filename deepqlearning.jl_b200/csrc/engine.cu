@@ -783,7 +783,10 @@ void enqueue_step(E* e, bool sample) {
   for (int t = 0; t < e->ntow; ++t) head_fused = head_fused && e->tow[t][e->depth - 1].N <= HEADS_MAXN && e->tow[t][e->depth - 1].K == e->tow[0][e->depth - 1].K;
   Pass p_on{e->theta, e->xb, e->elem_bytes == 1, 2 * B, &e->on, "online", xs, e->w_on_s, tcp};
   Pass p_tg{e->theta_t, e->xb + (long long)B * e->obs_row_bytes, e->elem_bytes == 1, B, &e->tg, "target", xs ? xs + (long long)B * e->obs_elems : nullptr, e->w_tg_s, tcp};
-  p_on.skip_last = p_tg.skip_last = head_fused;
+  // fuse_head_all: 0 = separate kernels (default); 2 = output layers on their passes' own lanes (heads_fwd_kernel), then loss + gradient
+  // into the last hidden layer in one launch; 1 = the output layers in that launch as well (joins the three passes early)
+  const bool head_fwd_in_pass = head_fused && e->fuse_head_all == 2;
+  p_on.skip_last = p_tg.skip_last = head_fused && !head_fwd_in_pass;
   if (tcp && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
     const Pass both[2] = {p_on, p_tg};
     prepare_dgrad_weights(e);
@@ -811,14 +814,14 @@ void enqueue_step(E* e, bool sample) {
     h.inv_world_B = 1.0f / ((float)B * (float)e->cfg.world);
     h.st = e->st;
     if (head_fused) {
-      FusedHeadArgs fa{}; fa.h = h; fa.ntow = e->ntow; fa.K = e->tow[0][L].K; fa.hub = e->hub; fa.ticket = e->colsum_ticket + 2;
+      FusedHeadArgs fa{}; fa.h = h; fa.ntow = e->ntow; fa.K = e->tow[0][L].K; fa.hub = e->hub; fa.ticket = e->colsum_ticket + 2; fa.fwd_done = head_fwd_in_pass ? 1 : 0;
       for (int t = 0; t < e->ntow; ++t) {
         const Mat& w = e->tow[t][L];
         fa.H_on[t] = e->on.tow_out[t][L - 1]; fa.H_tg[t] = e->tg.tow_out[t][L - 1]; fa.W_on[t] = e->theta + w.off; fa.W_tg[t] = e->theta_t + w.off;
         fa.out_on[t] = e->on.tow_out[t][L]; fa.out_tg[t] = e->tg.tow_out[t][L]; fa.dH[t] = e->tow_delta[t][L - 1];
         fa.N[t] = w.N; fa.act_out[t] = w.act; fa.act_hidden[t] = e->tow[t][L - 1].act;
       }
-      Scope sc(e, "head_fused", 6.0 * B * fa.K * (e->cfg.n_actions + 1), 4.0 * B * fa.K * 5);
+      Scope sc(e, head_fwd_in_pass ? "head_loss_dgrad" : "head_fused", 6.0 * B * fa.K * (e->cfg.n_actions + 1), 4.0 * B * fa.K * 5);
       head_fused_kernel<<<(B + 7) / 8, 256, 0, e->stream>>>(fa);
       CK(cudaGetLastError());
     } else {
@@ -843,7 +846,7 @@ void enqueue_step(E* e, bool sample) {
     }
     e->ls = keep;
   }
-  backward(e, conc);
+  backward(e, conc, head_fused);
   e->sm_reserve = 0;
   if (conc) order_after(e, e->stream, e->stream2);            // all weight gradients are in
   if (e->cfg.world > 1) {
@@ -1371,6 +1374,8 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_LSTM_SEQ"); e->lstm_seq = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_INGEST_LANE"); e->ingest_lane = v ? atoi(v) : 1; }
+    // (measured, ms/step: 0 separate kernels 0.401; 2 loss + dgrad in one launch 0.413; 1 output layers as well 0.430 - a warp per sample
+    //  is too little parallelism for the 256 x 1024 gradient that heads_dgrad_kernel spreads over 262 144 threads)
     { const char* v = getenv("DQN_FUSE_HEAD_ALL"); e->fuse_head_all = v ? atoi(v) : 0; }   // one launch for output layers + loss + dH: measured slower (0.452 vs 0.415 ms/step) - it joins the three passes early
     build_topology(e);
     allocate(e);

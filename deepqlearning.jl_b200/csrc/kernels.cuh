@@ -769,6 +769,7 @@ struct FusedHeadArgs {
   float* dH[2];                                 // gradient into the last hidden layer [B][K], times act'(H)
   int N[2], act_out[2], act_hidden[2], K, ntow;
   float* hub; unsigned int* ticket;
+  int fwd_done;                                 // the output layers were already computed (heads_fwd_kernel on each pass's own lane): out_* are inputs
 };
 __device__ __forceinline__ void head_rowdot(const float* __restrict__ x, const float* __restrict__ W, int K, int N, int act, int lane, float* out) {
   float acc[HEADS_MAXN];
@@ -795,6 +796,17 @@ __global__ void __launch_bounds__(256) head_fused_kernel(const FusedHeadArgs a) 
   __shared__ int last;
   if (i < h.B) {
     float o_s[2][HEADS_MAXN], o_sp[2][HEADS_MAXN], o_tg[2][HEADS_MAXN];
+    if (a.fwd_done) {
+      for (int t = 0; t < a.ntow; ++t) {
+#pragma unroll
+        for (int n = 0; n < HEADS_MAXN; ++n) {
+          const bool in = n < a.N[t];
+          o_s[t][n] = in ? a.out_on[t][(long long)i * a.N[t] + n] : 0.f;
+          o_sp[t][n] = in ? a.out_on[t][(long long)(h.B + i) * a.N[t] + n] : 0.f;
+          o_tg[t][n] = in ? a.out_tg[t][(long long)i * a.N[t] + n] : 0.f;
+        }
+      }
+    } else
     for (int t = 0; t < a.ntow; ++t) {
       head_rowdot(a.H_on[t] + (long long)i * a.K, a.W_on[t], a.K, a.N[t], a.act_out[t], lane, o_s[t]);
       head_rowdot(a.H_on[t] + (long long)(h.B + i) * a.K, a.W_on[t], a.K, a.N[t], a.act_out[t], lane, o_sp[t]);
