@@ -452,7 +452,7 @@ def main():
     barrier()
     if rank == 0:
         tot = sum(k["ms"] * 1 for k in prof)
-        kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"])][:12]
+        kernels = [{"name": k["name"], "ms": round(k["ms"], 5), "share": round(k["ms"] / tot, 4)} for k in sorted(prof, key=lambda k: -k["ms"])]
         top = max(prof, key=lambda k: k["ms"])
         traffic = load_traffic()
         tr = traffic.get(top["name"], {}).get("dram_bytes")

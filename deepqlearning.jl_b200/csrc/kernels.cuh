@@ -305,7 +305,7 @@ __global__ void epoch_wait_kernel(DevState* st, unsigned int expected) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->tree_epoch) : "memory");
     if (v >= expected) break;
-    if (clock64() - t0 > 4000000000LL) { atomicOr(&st->error, 32); break; }
+    if (clock64() - t0 > 240000000000LL) { atomicOr(&st->error, 32); break; }   // ~2 min: the step in flight may itself be waiting for a peer rank
     __nanosleep(200);
   }
 }

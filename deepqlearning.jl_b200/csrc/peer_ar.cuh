@@ -11,7 +11,8 @@
 //   kernel has started, stream order put every weight-gradient kernel before it) gates the pulls, done[p][c] (CTA c of peer p has
 //   pushed its part, fenced at system scope) gates the kernel's exit - what follows in the stream (Adam) sees the complete sum.
 //   Epochs come from the device-side step counter, so a captured CUDA graph replays the kernel unchanged.
-// Spins are bounded: a peer that never arrives raises the sticky error bit 16 (DQN_ERR_NCCL at the next scalar fetch) instead of hanging.
+// Spins are bounded (~2 min): a peer that never arrives raises the sticky error bit 16 (DQN_ERR_NCCL at the next scalar fetch) instead of
+// hanging for ever.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,7 +25,7 @@ constexpr int PEER_MAXG = 64;          // CTAs of one reduction
 constexpr int PEER_READY = 0;          // flag block: ready[PEER_MAX], then done[PEER_MAX][PEER_MAXG]
 constexpr int PEER_DONE = PEER_MAX;
 constexpr int PEER_FLAGS = PEER_MAX + PEER_MAX * PEER_MAXG;
-constexpr long long PEER_SPIN_CLOCKS = 6000000000LL;   // ~3 s at 1.9 GHz
+constexpr long long PEER_SPIN_CLOCKS = 240000000000LL; // ~2 min at 1.9 GHz: a last resort against a dead peer, far beyond any host-side skew between ranks
 
 struct PeerArArgs {
   float* grad[PEER_MAX];                 // every rank's gradient vector as mapped in this process (own entry: the local pointer)
