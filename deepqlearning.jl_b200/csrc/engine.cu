@@ -528,17 +528,29 @@ void backward(E* e, bool conc, bool head_fused = false) {
     const bool split_bias = tma_wgrad || (e->arena && (c.w.K % 128 == 0) && c.w.K <= 256 && (c.g.Cout % 4 == 0) && c.g.Cout <= 1024);   // worth a launch only when it saves >= 1/3 of the tiles
     if (split_bias) { wg_tc.M = c.w.K; wg_tc.no_bias = 1; }
     if (wg.a_single && e->a8) { wg_tc.a8 = 1; wg_tc.Xs = nullptr; }     // first layer: the byte batch itself is the operand
+    bool bias_by_colsum = false;
     {
       if (conc) order_after(e, e->stream2, e->stream);
       Lane lane(e, conc);
       if (!tc_conv_wgrad(e, nm, wg_tc, fl, by)) launch_igemm(e, nm, wg, wg, 1, true, fl, by);
-      else if (split_bias) {
+      else bias_by_colsum = split_bias;
+      // the first layer has no input gradient: its column sums go to the (idle) main lane and run beside the weight-gradient contraction
+      // instead of behind it and its reduction on the tail of the step
+      if (bias_by_colsum && !(conc && l == 0)) {
         snprintf(nm, sizeof nm, "conv%d_bgrad", l + 1);
         Scope sc(e, nm, 0, 4.0 * wg.K * wg.N);
         colsum_kernel<<<COLSUM_CTAS, 256, 0, e->ls>>>(e->conv_delta[l], (long long)wg.K, wg.N, e->grad + c.w.off + (long long)c.w.K * c.g.Cout,
                                                      e->colsum_part + (e->ls == e->stream ? 0 : COLSUM_CTAS * 1024), e->colsum_ticket + (e->ls == e->stream ? 0 : 1));
         CK(cudaGetLastError());
+        bias_by_colsum = false;
       }
+    }
+    if (bias_by_colsum) {
+      snprintf(nm, sizeof nm, "conv%d_bgrad", l + 1);
+      Scope sc(e, nm, 0, 4.0 * wg.K * wg.N);
+      colsum_kernel<<<COLSUM_CTAS, 256, 0, e->stream>>>(e->conv_delta[l], (long long)wg.K, wg.N, e->grad + c.w.off + (long long)c.w.K * c.g.Cout,
+                                                       e->colsum_part, e->colsum_ticket);
+      CK(cudaGetLastError());
     }
     if (l > 0) {
       ConvDgradOp dg{};

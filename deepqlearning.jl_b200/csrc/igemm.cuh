@@ -834,30 +834,47 @@ igemm_kernel(Op opa, Op opb, int nsplit, float* __restrict__ ws, long long ws_st
   }
 }
 
-// out[i] = sum_s ws[(z*nsplit + s)][i], s ascending (deterministic), for the split-K weight gradients
+// out[i] = sum_s ws[(z*nsplit + s)][i] (deterministic: fixed order), the epilogue of every split-K contraction.
+// sub = 1: one thread per four columns, the splits added in ascending order.  sub = 4 (small outputs with many splits - the conv weight
+// gradients: 8 CTAs x 64 dependent-ish loads was 11.6 us on the tail of the step): four adjacent lanes share an output, each adds a
+// contiguous quarter of the splits in ascending order, the quarters meet as (q0 + q1) + (q2 + q3) by two butterfly shuffles.
 template <class Op>
-__global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __restrict__ ws, long long ws_stride, int m_off = 0, int rows = -1) {
+__global__ void splitk_reduce_kernel(Op opa, Op opb, int nsplit, const float* __restrict__ ws, long long ws_stride, int m_off = 0, int rows = -1, int sub = 1) {
   const int zi = blockIdx.y;
   Op op = zi == 0 ? opa : opb;
   if (Op::Z_IS_CLASS) op.set_class(0);                    // only single-class dgrads are ever split
   // rows [m_off, m_off + rows) of the output (the tail tiles of a launch, see tc_gemm_impl.cuh); default: all of it
   const long long total = (long long)(rows < 0 ? op.M : rows) * op.N;
   if (op.can_store4()) {                     // N % 4 == 0: four columns per thread, vector epilogue (also writes the split planes)
-    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const int q = (int)(gt % sub);
+    const int k0 = (int)((long long)q * nsplit / sub), k1 = (int)((long long)(q + 1) * nsplit / sub);
+    // (the loop bound is uniform over the `sub` lanes of an output and the shuffles are predicated per output group, not per warp)
+    for (long long i = (gt / sub) * 4; i - (long long)((threadIdx.x & 31) / sub) * 4 < total; i += (nth / sub) * 4) {
+      const bool valid = i < total;
       float4 s = make4(0, 0, 0, 0);
-      int k = 0;
-      for (; k + 8 <= nsplit; k += 8) {        // eight independent loads in flight (small grids are latency bound), added in ascending order
-        float4 p[8];
+      if (valid) {
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {          // eight independent loads in flight (small grids are latency bound), added in ascending order
+          float4 p[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) p[j] = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k + j)) * ws_stride + i));
+          for (int j = 0; j < 8; ++j) p[j] = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k + j)) * ws_stride + i));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s.x += p[j].x; s.y += p[j].y; s.z += p[j].z; s.w += p[j].w; }
+          for (int j = 0; j < 8; ++j) { s.x += p[j].x; s.y += p[j].y; s.z += p[j].z; s.w += p[j].w; }
+        }
+        for (; k < k1; ++k) {
+          const float4 p = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i));
+          s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+        }
       }
-      for (; k < nsplit; ++k) {
-        const float4 p = __ldcg(reinterpret_cast<const float4*>(ws + ((long long)(zi * nsplit + k)) * ws_stride + i));
-        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      if (sub == 4) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+          s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+        }
       }
-      op.store4(m_off + (int)(i / op.N), (int)(i % op.N), s);
+      if (valid && q == 0) op.store4(m_off + (int)(i / op.N), (int)(i % op.N), s);
     }
     return;
   }

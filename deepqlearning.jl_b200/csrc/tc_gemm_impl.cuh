@@ -1197,9 +1197,10 @@ bool launch_tc(dqn_engine* e, const char* name, const Op* ops, int nops, int nz,
   }
   if (nsplit > 1) {
     Scope sc(e, "splitk_reduce", 0, (double)(nsplit + 1) * ws_stride * nz * 4);
+    const int sub = (nsplit >= 8 && ws_stride / 4 <= 65536) ? 4 : 1;          // small output, many splits: four lanes per output (latency bound otherwise)
     for (int z = 0; z < nz; z += 2) {
-      dim3 g2((unsigned)std::min<long long>((ws_stride / 4 + 255) / 256, 4 * e->nsm), std::min(2, nz - z));
-      splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(ops[z], ops[std::min(z + 1, nops - 1)], nsplit, e->lws + (long long)z * nsplit * ws_stride, ws_stride);
+      dim3 g2((unsigned)std::min<long long>((ws_stride / 4 * sub + 255) / 256, 4 * e->nsm), std::min(2, nz - z));
+      splitk_reduce_kernel<Op><<<g2, 256, 0, e->ls>>>(ops[z], ops[std::min(z + 1, nops - 1)], nsplit, e->lws + (long long)z * nsplit * ws_stride, ws_stride, 0, -1, sub);
       CK(cudaGetLastError());
     }
   }
