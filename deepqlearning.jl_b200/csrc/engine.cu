@@ -183,6 +183,7 @@ struct dqn_engine {
   // gradient all-reduce over NVLink peer memory (peer_ar.cuh); NCCL stays the fallback (no peer access, world > 8, DQN_PEER_AR=0)
   int peer_ctas = 16;      // CTAs of a large reduction (DQN_PEER_CTAS, <= PEER_MAXG): bytes in flight over NVLink vs SMs taken from the GEMMs
   bool peer_ar = false; PeerArArgs peer{}; unsigned long long* peer_flags = nullptr; void* peer_opened[2 * PEER_MAX] = {}; int peer_nopened = 0;
+  int head_small = 1;      // register-resident head kernel for small action sets (DQN_HEAD_SMALL=0: the generic one)
   int lstm_seq = 1;        // recurrent engines: the whole recurrence of a pass in one cluster launch (lstm_seq_*_kernel); 0 = one launch per time step
   int fuse_head_all = 1;   // output layers of all three passes + head + their input gradient in one launch (head_fused_kernel)
   float* hub = nullptr;    // per-sample Huber values of that kernel (deterministic loss reduction)
@@ -838,7 +839,9 @@ void enqueue_step(E* e, bool sample) {
       CK(cudaGetLastError());
     } else {
       Scope sc(e, "head_loss", 0, B * (double)(3 * (e->cfg.n_actions + 1) + 12) * 4);
-      head_loss_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(h);
+      if (e->head_small && B <= 256 && e->cfg.n_actions <= 8) head_loss_small_kernel<8><<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
+      else if (e->head_small && B <= 256 && e->cfg.n_actions <= 32) head_loss_small_kernel<32><<<1, (B + 31) / 32 * 32, 0, e->stream>>>(h);
+      else head_loss_kernel<<<1, std::min(1024, (B + 31) / 32 * 32), 0, e->stream>>>(h);
       CK(cudaGetLastError());
     }
   }
@@ -1385,6 +1388,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_MERGE_FWD"); e->merge_fwd = v ? atoi(v) : 0; }
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_LSTM_SEQ"); e->lstm_seq = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_HEAD_SMALL"); e->head_small = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_INGEST_LANE"); e->ingest_lane = v ? atoi(v) : 1; }
     // (measured, ms/step: 0 separate kernels 0.401; 2 loss + dgrad in one launch 0.413; 1 output layers as well 0.430 - a warp per sample
     //  is too little parallelism for the 256 x 1024 gradient that heads_dgrad_kernel spreads over 262 144 threads)
