@@ -378,13 +378,15 @@ def main():
     barrier = cp.barrier
 
     # ---- device-resident throughput (value) ------------------------------------------------------
+    # (the clock sampler - an nvidia-smi child process - starts BEFORE the barrier: spawning it takes tens of milliseconds on rank 0, and
+    #  ranks that entered the timed loop meanwhile would count that wait inside their first all-reduce)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         eng.train_step_async()
     eng.sync()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     eng.timer_start()
     for _ in range(args.steps):
         eng.train_step_async()
