@@ -316,6 +316,46 @@ def test_one_step_ahead_loop_equals_the_serial_loop(lib, monkeypatch, ingest_lan
     eng.close(); eng2.close()
 
 
+def test_ingest_lane_under_a_mixed_call_sequence(lib, monkeypatch):
+    """A few hundred calls in random order - adds of 1..9 transitions while a step is in flight, steps (async and serial), scalar reads
+    one step late, priority updates, index draws, target syncs, reads of the ring - on an engine with the ingest lane and on one that
+    ingests on the main stream: every returned value and the final state are BIT-identical (the lane only changes what overlaps)."""
+    spec = util.SPECS["conv_small"]
+    engs = []
+    for lane in ("1", "0"):
+        monkeypatch.setenv("DQN_INGEST_LANE", lane)
+        engs.append(setup_pair(lib, "conv_small")[4])
+    rng = np.random.default_rng(77)
+    ops = rng.integers(0, 8, 400)
+    outs = [[], []]
+    for k, op in enumerate(ops):
+        n = int(rng.integers(1, 10))
+        s, a, r, sp, done = util.random_transitions(spec, n, seed=1000 + k)
+        idx = rng.choice(spec["N"], 7, replace=False).astype(np.int64)      # (distinct: duplicate leaves in one update would race)
+        td = rng.uniform(-2, 2, 7).astype(np.float32)
+        for e, out in zip(engs, outs):
+            if op <= 2:
+                e.replay_add(s, a, r, sp, done, np.abs(r))
+            elif op == 3:
+                e.train_step_async()
+            elif op == 4:
+                out.append(e.train_step())
+            elif op == 5:
+                e.update_priorities(idx, td)
+                out.append(tuple(e.sample_indices(k)))
+            elif op == 6:
+                e.sync_target() if k % 3 == 0 else out.append(tuple(e.replay_size()))
+            else:
+                e.train_step_async(); e.replay_add(s, a, r, sp, done, np.abs(r)); e.train_step_async(); out.append(e.step_result(1))
+    for e, out in zip(engs, outs):
+        out.append(e.sync())
+    assert outs[0] == outs[1]
+    assert np.array_equal(engs[0].get_params(0), engs[1].get_params(0)) and np.array_equal(engs[0].get_params(1), engs[1].get_params(1))
+    assert np.array_equal(engs[0].get_tree(), engs[1].get_tree())
+    for e in engs:
+        e.close()
+
+
 @pytest.mark.parametrize("name,dueling", [("c1_gridworld", True), ("conv_small", True), ("conv_small", False), ("testmdp", True)])
 def test_acting_q_values(lib, name, dueling):
     spec, net, tgt, buf, eng = setup_pair(lib, name, dueling)
