@@ -38,12 +38,17 @@ struct Params {
   int patch_pitch;         // bytes per patch row = IW * 4
   int patch_bytes;         // PATCH_ROWS * patch_pitch
   int patch_slot;          // patch_bytes rounded up to 1024
+  // direct mode: the patches come straight from the replay store (no gathered batch on the critical path).  Image n of the pass is
+  // transition idx[n % half_rows]; the first half_rows images read the s store (map 1) and the rest the s' store (map 2) - or the s'
+  // store from the start (sp_first: the target pass).  idx == nullptr: the images are the rows of the gathered batch (map 1).
+  const long long* idx;
+  int half_rows, sp_first;
 };
 
 __host__ __device__ inline int smem_bytes(int patch_slot) { return 2 * B_PLANE + 2 * 2 * patch_slot + 1024 + 512; }
 
 __global__ void __launch_bounds__(C1_THREADS, 1)
-conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const Params p, int ntiles) {
+conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmx2, const Params p, int ntiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -86,8 +91,16 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const Params p, int nt
       if (lane == 0) {
         const uint32_t dst = patch0 + buf * 2 * p.patch_slot, bar = bar_pfull + 8 * buf;
         mbar_expect_tx(bar, (uint32_t)(p.patch_bytes * (two ? 2 : 1)));
-        tma_load_3d(dst, &tmx, 0, oh0 * S, n0, bar);
-        if (two) tma_load_3d(dst + p.patch_slot, &tmx, 0, 0, n0 + 1, bar);
+        const CUtensorMap* ma = &tmx; const CUtensorMap* mb = &tmx;
+        int ia = n0, ib = n0 + 1;
+        if (p.idx) {
+          const int ha = n0 / p.half_rows, hb = (n0 + 1) / p.half_rows;
+          ia = (int)__ldg(p.idx + (n0 - ha * p.half_rows));
+          if ((ha ^ p.sp_first) & 1) ma = &tmx2;
+          if (two) { ib = (int)__ldg(p.idx + (n0 + 1 - hb * p.half_rows)); if ((hb ^ p.sp_first) & 1) mb = &tmx2; }
+        }
+        tma_load_3d(dst, ma, 0, oh0 * S, ia, bar);
+        if (two) tma_load_3d(dst + p.patch_slot, mb, 0, 0, ib, bar);
       }
       __syncwarp();
       if (++buf == 2) { buf = 0; ph ^= 1; }
@@ -235,12 +248,28 @@ inline Params make_params(const dqn::ConvFwdOp& op) {
 #ifndef TC_KERNEL_ONLY
 namespace {
 // first conv layer, forward, on the raw byte batch (DQN_MATH_3XTF32 with byte observations and the Nature-DQN first-layer geometry)
+bool tc_conv1_eligible(dqn_engine* e, const dqn::ConvGeom& g) {
+  return e->cfg.math_mode == DQN_MATH_3XTF32 && e->tc_c1 && e->arena && e->a8 && e->elem_bytes == 1 && g.Cout == c1::COUT && c1::geometry_ok(g);
+}
+// tensor maps of the two observation stores (direct mode: one image = one stored transition)
+void tc_conv1_init(dqn_engine* e) {
+  e->c1_maps_ok = false;
+  if (e->convs.empty() || e->lstm || !tc_conv1_eligible(e, e->convs[0].g) || e->cap > 0x7fffffffLL) return;
+  e->c1_maps_ok = c1::make_map(&e->c1_map_s, e->store_s, (int)e->cap, e->convs[0].g) && c1::make_map(&e->c1_map_sp, e->store_sp, (int)e->cap, e->convs[0].g);
+}
 bool tc_conv1_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, double flops, double bytes) {
   if (e->cfg.math_mode != DQN_MATH_3XTF32 || !e->tc_c1 || !e->arena) return false;
   if (!op.a8 || !op.x_u8 || !op.Ws || op.N != c1::COUT || op.K != c1::K || !c1::geometry_ok(op.g)) return false;
-  CUtensorMap tm;
-  if (!c1::make_map(&tm, op.X, op.nimg, op.g)) return false;
-  const c1::Params p = c1::make_params(op);
+  CUtensorMap tm, tm2;
+  c1::Params p = c1::make_params(op);
+  if (e->c1_direct_now) {                      // this step's passes read the replay store through the sampled indices (engine.cu: enqueue_step)
+    if (!e->c1_maps_ok) return false;
+    tm = e->c1_map_s; tm2 = e->c1_map_sp;
+    p.idx = e->idx_d; p.half_rows = e->B; p.sp_first = (op.X != (const void*)e->xb) ? 1 : 0;
+  } else {
+    if (!c1::make_map(&tm, op.X, op.nimg, op.g)) return false;
+    tm2 = tm;
+  }
   const int smem = c1::smem_bytes(p.patch_slot);
   if (smem > 227 * 1024) return false;
   static unsigned long long attr_set[4] = {0, 0, 0, 0};
@@ -251,7 +280,7 @@ bool tc_conv1_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, dou
   }
   const int ntiles = (op.M + tc::BM - 1) / tc::BM;
   Scope sc(e, name, flops, bytes);
-  c1::conv1_fwd_kernel<<<std::min(ntiles, e->nsm), c1::C1_THREADS, smem, e->ls>>>(tm, p, ntiles);
+  c1::conv1_fwd_kernel<<<std::min(ntiles, e->nsm), c1::C1_THREADS, smem, e->ls>>>(tm, tm2, p, ntiles);
   CK(cudaGetLastError());
   return true;
 }

@@ -6,6 +6,7 @@
 //   Bellman target, IS-Huber, dQ, td, new priorities) -> reverse pass -> [NCCL all-reduce] -> fused Adam +
 //   max|g| -> sum-tree refresh -> publish (loss, grad_norm).
 // There is no CPU fallback anywhere in this file: every numerical result is produced by a kernel launch.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -183,6 +184,9 @@ struct dqn_engine {
   // gradient all-reduce over NVLink peer memory (peer_ar.cuh); NCCL stays the fallback (no peer access, world > 8, DQN_PEER_AR=0)
   int peer_ctas = 16;      // CTAs of a large reduction (DQN_PEER_CTAS, <= PEER_MAXG): bytes in flight over NVLink vs SMs taken from the GEMMs
   bool peer_ar = false; PeerArArgs peer{}; unsigned long long* peer_flags = nullptr; void* peer_opened[2 * PEER_MAX] = {}; int peer_nopened = 0;
+  // first conv layer straight from the replay store: its TMA patch loads take the sampled indices, so the row gather leaves the critical
+  // path (it still runs, on the third lane, for the weight-gradient operand).  DQN_C1_DIRECT=0: gather first, as before.
+  int c1_direct = 1; bool c1_maps_ok = false, c1_direct_now = false; CUtensorMap c1_map_s, c1_map_sp;
   int head_small = 1;      // register-resident head kernel for small action sets (DQN_HEAD_SMALL=0: the generic one)
   int lstm_seq = 1;        // recurrent engines: the whole recurrence of a pass in one cluster launch (lstm_seq_*_kernel); 0 = one launch per time step
   int fuse_head_all = 1;   // output layers of all three passes + head + their input gradient in one launch (head_fused_kernel)
@@ -591,22 +595,28 @@ void enqueue_adam(E* e, long long lo, long long hi, cudaStream_t s) {
   e->ls = keep;
 }
 
-void enqueue_gather(E* e) {       // observation rows of the sampled transitions -> batch (and its tensor-core operand planes)
+void enqueue_gather(E* e, cudaStream_t gs = nullptr) {       // observation rows of the sampled transitions -> batch (and its tensor-core operand planes)
+  if (!gs) gs = e->stream;
+  cudaStream_t keep_ls = e->ls; e->ls = gs;
   const long long rb = e->obs_row_bytes;
   const long long per = (rb % 16 == 0) ? 256LL * 4 * 16 : 256LL * 4;
   dim3 grid((unsigned)((rb + per - 1) / per), 2 * e->B);
-  Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
-  gather_rows_kernel<<<grid, 256, 0, e->stream>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0 && e->elem_bytes == 1) ? e->xb_f : nullptr, 0, e->elem_bytes == 1);
-  CK(cudaGetLastError());
+  {
+    Scope sc(e, "gather_rows", 0, 4.0 * e->B * rb);
+    gather_rows_kernel<<<grid, 256, 0, gs>>>(e->store_s, e->store_sp, e->idx_d, e->B, rb, e->xb, (rb % 16 == 0 && e->elem_bytes == 1) ? e->xb_f : nullptr, 0, e->elem_bytes == 1);
+    CK(cudaGetLastError());
+  }
+  e->ls = keep_ls;
 }
-void enqueue_batch_prep(E* e) {   // get_batch (PER:89-104) for indices given by the caller
+void enqueue_batch_prep(E* e, cudaStream_t gs = nullptr) {   // get_batch (PER:89-104) for indices given by the caller
   {
     Scope sc(e, "batch_meta", 0, e->B * 40.0);
     batch_meta_kernel<<<(e->B + 255) / 256, 256, 0, e->stream>>>(e->idx_d, e->B, e->tree, e->P, e->act, e->rew, e->done, e->st,
                                                                 e->cfg.beta, e->a_b, e->r_b, e->d_b, e->w_b);
     CK(cudaGetLastError());
   }
-  enqueue_gather(e);
+  if (gs) order_after(e, gs, e->stream);
+  enqueue_gather(e, gs);
 }
 size_t sample_smem(int B) { int HT = 1; while (HT < 4 * B) HT <<= 1; return 2 * HT * sizeof(int) + TREE_TOP * sizeof(float); }
 
@@ -778,6 +788,9 @@ void enqueue_step_recurrent(E* e, bool sample) {
 void enqueue_step(E* e, bool sample) {
   if (e->lstm) { enqueue_step_recurrent(e, sample); return; }
   const int B = e->B;
+  // first conv layer straight from the replay store (conv1_tc.cuh, direct mode): the gather leaves the critical path for the third lane
+  const bool direct = e->c1_direct && e->c1_maps_ok && e->use_streams && !e->profiling && !e->merge_fwd && !e->convs.empty() && tc_conv1_eligible(e, e->convs[0].g);
+  e->ev_next = 0;
   if (sample) {
     {
       Scope sc(e, "sumtree_sample", 0, B * 8.0 * 22);
@@ -785,11 +798,11 @@ void enqueue_step(E* e, bool sample) {
                                                                             e->act, e->rew, e->done, e->cfg.beta, e->a_b, e->r_b, e->d_b, e->w_b);
       CK(cudaGetLastError());
     }
-    enqueue_gather(e);
-  } else enqueue_batch_prep(e);
+    if (direct) order_after(e, e->stream3, e->stream);
+    enqueue_gather(e, direct ? e->stream3 : nullptr);
+  } else enqueue_batch_prep(e, direct ? e->stream3 : nullptr);
   const float* xs = (e->arena && e->obs_row_bytes % 16 == 0) ? (e->elem_bytes == 1 ? e->xb_f : (const float*)e->xb) : nullptr;
   const bool conc = e->use_streams && !e->profiling;          // profiling wants clean per-kernel times: one lane
-  e->ev_next = 0;
   const bool tcp = e->arena && e->obs_row_bytes % 16 == 0 && (xs != nullptr || e->a8);
   // thin output layers (N <= 8) behind at least one hidden Dense layer: the whole head is one launch
   bool head_fused = e->fuse_heads && e->fuse_head_all && e->depth >= 2 && e->cfg.n_actions <= HEADS_MAXN && B <= 65536;
@@ -800,6 +813,7 @@ void enqueue_step(E* e, bool sample) {
   // into the last hidden layer in one launch; 1 = the output layers in that launch as well (joins the three passes early)
   const bool head_fwd_in_pass = head_fused && e->fuse_head_all == 2;
   p_on.skip_last = p_tg.skip_last = head_fused && !head_fwd_in_pass;
+  e->c1_direct_now = direct;
   if (tcp && e->cfg.math_mode == DQN_MATH_3XTF32 && e->merge_fwd) {   // tensor-core path: both networks layer by layer in shared launches
     const Pass both[2] = {p_on, p_tg};
     prepare_dgrad_weights(e);
@@ -814,6 +828,8 @@ void enqueue_step(E* e, bool sample) {
     forward(e, &p_on, 1);
     if (conc) order_after(e, e->stream, e->stream2);          // join before the head needs Q_target(s')
   }
+  e->c1_direct_now = false;
+  if (direct) order_after(e, e->stream, e->stream3);          // the gathered batch (first layer's weight-gradient operand) is complete
   {
     HeadArgs h{};
     const int L = e->depth - 1;
@@ -1389,6 +1405,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     { const char* v = getenv("DQN_FUSE_HEADS"); e->fuse_heads = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_LSTM_SEQ"); e->lstm_seq = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_HEAD_SMALL"); e->head_small = v ? atoi(v) : 1; }
+    { const char* v = getenv("DQN_C1_DIRECT"); e->c1_direct = v ? atoi(v) : 1; }
     { const char* v = getenv("DQN_INGEST_LANE"); e->ingest_lane = v ? atoi(v) : 1; }
     // (measured, ms/step: 0 separate kernels 0.401; 2 loss + dgrad in one launch 0.413; 1 output layers as well 0.430 - a warp per sample
     //  is too little parallelism for the 256 x 1024 gradient that heads_dgrad_kernel spreads over 262 144 threads)
@@ -1396,6 +1413,7 @@ int dqn_engine_create(const dqn_config_t* cfg, dqn_engine_t** out) {
     build_topology(e);
     allocate(e);
     tc_init(e);
+    tc_conv1_init(e);
     if (cfg->world > 1) {
       std::string why;
       if (!g_nccl.load(why)) fail(DQN_ERR_NCCL, "%s", why.c_str());

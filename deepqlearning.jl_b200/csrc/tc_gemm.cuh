@@ -5,6 +5,8 @@
 #include "igemm.cuh"
 struct dqn_engine;
 namespace {
+bool tc_conv1_eligible(dqn_engine* e, const dqn::ConvGeom& g);
+void tc_conv1_init(dqn_engine* e);
 bool tc_conv1_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp& op, double flops, double bytes);
 bool tc_conv_fwd(dqn_engine* e, const char* name, const dqn::ConvFwdOp* ops, int nops, double flops, double bytes);
 bool tc_dense_fwd(dqn_engine* e, const char* name, const dqn::DenseFwdOp* ops, int nops, double flops, double bytes);

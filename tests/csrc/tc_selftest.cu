@@ -192,12 +192,12 @@ static void test_conv1_bytes(int nimg, int IH, int IW, int iters) {
   const c1::Params pr = c1::make_params(op);
   const int smem = c1::smem_bytes(pr.patch_slot), ntiles = (P + 127) / 128, grid = ntiles < g_nsm ? ntiles : g_nsm;
   CKC(cudaFuncSetAttribute(c1::conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, pr, ntiles);
+  c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, tm, pr, ntiles);
   CKC(cudaGetLastError()); CKC(cudaDeviceSynchronize());
   if (iters > 0) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
-    for (int i = 0; i < iters; ++i) c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, pr, ntiles);
+    for (int i = 0; i < iters; ++i) c1::conv1_fwd_kernel<<<grid, c1::C1_THREADS, smem>>>(tm, tm, pr, ntiles);
     cudaEventRecord(b); CKC(cudaEventSynchronize(b));
     float ms; cudaEventElapsedTime(&ms, a, b);
     const double us = 1e3 * ms / iters;

@@ -458,13 +458,14 @@ def test_env_switches_keep_parity(lib):
     outs = {}
     for tag, env in (("default", {}), ("merge", {"DQN_MERGE_FWD": "1"}), ("one_lane", {"DQN_STREAMS": "0"}), ("tiled_heads", {"DQN_FUSE_HEADS": "0"}), ("no_a8", {"DQN_NO_A8": "1"}),
                      ("tail_split", {"DQN_TC_TAIL": "1"}), ("cp_async_feed", {"DQN_TC_TMA": "0"}), ("generic_conv1", {"DQN_TC_C1": "0"}), ("tma_wgrad", {"DQN_TC_TMA_WGRAD": "1"}),
-                     ("single_head_kernel", {"DQN_FUSE_HEAD_ALL": "1"}), ("head_loss_dgrad_kernel", {"DQN_FUSE_HEAD_ALL": "2"}), ("classwise_dgrad", {"DQN_DGRAD_MERGE": "0"}), ("cp_async_dgrad", {"DQN_TC_TMA_DGRAD": "0"}), ("generic_head", {"DQN_HEAD_SMALL": "0"})):
+                     ("single_head_kernel", {"DQN_FUSE_HEAD_ALL": "1"}), ("head_loss_dgrad_kernel", {"DQN_FUSE_HEAD_ALL": "2"}), ("classwise_dgrad", {"DQN_DGRAD_MERGE": "0"}), ("cp_async_dgrad", {"DQN_TC_TMA_DGRAD": "0"}), ("generic_head", {"DQN_HEAD_SMALL": "0"}), ("gather_first", {"DQN_C1_DIRECT": "0"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, **env})
         line = [x for x in r.stdout.splitlines() if x.startswith("RES")]
         assert line, (tag, r.stdout[-500:], r.stderr[-1500:])
         outs[tag] = [float(x) for x in line[0].split()[1:]]
     ref = outs["default"]
     assert outs["one_lane"] == ref, outs                                    # same kernels, same order of operations: bit-identical
+    assert outs["gather_first"] == ref, outs                                # first layer from the gathered batch instead of the store: same bytes
     assert outs["generic_head"] == ref, outs                                # the register-resident head is the generic one, operation for operation
     for tag in ("merge", "tiled_heads", "tail_split", "no_a8", "cp_async_feed", "generic_conv1", "tma_wgrad", "single_head_kernel", "head_loss_dgrad_kernel", "classwise_dgrad", "cp_async_dgrad"):   # different summation order in a few contractions
         for a, b in zip(outs[tag], ref):
