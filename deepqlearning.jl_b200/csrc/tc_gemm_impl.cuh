@@ -67,6 +67,7 @@ struct TmaMaps {
   int kind;                      // TMA_*
   int seg_k;                     // dgrad: k where the second segment starts (0: one segment)
   int cin, kw, stride, oh, ow;   // conv: decode of (pixel, k stage) into im2col coordinates (dgrad: cin = Cout of the layer, the k channels)
+  int a_rows;                    // rows of the A tile that TMA loads (128, or 64: warps 4-7 feed rows 64..127 with cp.async, see the kernel)
   int ntaps;                     // conv wgrad: KH * KW
   int a_slabs;                   // 1: MN-major A staged as four [32 k][32 m] slabs (conv wgrad) instead of one dense [32 k][128 m] tile
 };
@@ -90,6 +91,7 @@ constexpr int GW = 8;            // warps per converter group
 constexpr int CONV_WARPS = GW * NGRP;
 constexpr int EPI_WARPS = 4;
 constexpr int NMMA = 3;
+constexpr int AH_WARP0 = 4, AH_THREADS = 128;   // TMA feed, BN = 64: warps 4-7 feed rows 64..127 of the A tile (cp.async) beside the TMA producer
 constexpr int CONV_WARP0 = LOAD_WARPS, EPI_WARP0 = CONV_WARP0 + CONV_WARPS, MMA_WARP0 = EPI_WARP0 + EPI_WARPS;
 constexpr int THREADS = 1024;
 static_assert(MMA_WARP0 + NMMA <= THREADS / 32 && CONV_WARP0 % 4 == 0 && EPI_WARP0 % 4 == 0 && MMA_WARP0 % 4 == 0, "warpgroup-aligned roles");
@@ -152,6 +154,9 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
   static constexpr int TAIL = 1024 + 512;                              // alignment slack + barriers / tmem address
 #ifndef TC_MAX_STAGES
 #define TC_MAX_STAGES 12
+#endif
+#ifndef TC_PSPLIT
+#define TC_PSPLIT 1                // TMA feed: two producer threads on alternate stages
 #endif
 #ifndef TC_TMA64_NBUF
 #define TC_TMA64_NBUF 2            // accumulator sets of the TMA-fed BN = 64 tiles (2: three accumulators per set, see DB64 below)
@@ -372,7 +377,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   const bool a_lo = !opa.a_single;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, TMA ? (L::TMA_B ? 1 : 1 + TMA_BLD) : LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, L::NMMA_W); }
+    const int helpers = (TMA && !A_MN && L::DB64 && tmaps.a_rows == BM / 2) ? AH_THREADS : 0;     // cp.async arrivals of the A-half feeders
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_landed + 8 * s, TMA ? (L::TMA_B ? 1 : 1 + TMA_BLD) + helpers : LOADERS); mbar_init(bar_full + 8 * s, GW); mbar_init(bar_empty + 8 * s, L::NMMA_W); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, L::NMMA_W); mbar_init(bar_acce + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -447,12 +453,18 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
   };
 
   constexpr int B_CH = BN * (BK / 4);                          // 16-byte chunks of B per stage
+  constexpr bool PSPLIT = TMA && L::TMA_B && (TC_PSPLIT != 0);
   // TMA feed: warps 4 and 5 (idle loaders) are MMA issuers 4 and 5; they run the issuer code at the end of this chain
   const bool tma_issuer = TMA && !L::DB64 && (warp == 4 || warp == 5);
   if (TMA && warp < LOAD_WARPS && !tma_issuer) {
     reg_dec<56>();
     // ================= TMA producer (warp 0: one thread, one or two instructions per stage) + B copiers (warps 1-2, cp.async) =================
-    if (warp == 0) {
+    if (warp == 0 || (PSPLIT && warp == 1)) {
+      // (two producer threads when both operands are boxes, on ALTERNATE stages: the issue of a cp.async.bulk.tensor blocks its thread
+      //  until the TMA unit takes it (~4.2 cycles per box row of the requests ahead), and a single thread then adds its own loop overhead
+      //  - barrier poll, coordinates - to every stage; with two threads one request is always queued behind the one in progress)
+      constexpr bool doA = true, doB = true;
+      unsigned int gstage = 0;
       int is = 0; uint32_t iph = 0;
       int ptr_ = 0; (void)ptr_;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -464,35 +476,37 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
         for (int it = 0; it < nk; ++it) {
           const int k0 = (kt0 + it) * BK;
           const uint32_t a_st = sbase + is * L::STAGE_BYTES, b_hi = a_st + L::A_BYTES, bar = bar_landed + 8 * is;
-          TRACE(ptr_, 0);
-          mbar_wait(bar_empty + 8 * is, iph ^ 1);                // slot free (first pass returns immediately)
-          TRACE(ptr_, 1);
-          if (lane == 0) {
-            uint32_t a_bytes = BM * BK * 4;
+          const bool mine = !PSPLIT || (int)(gstage & 1u) == warp;
+          ++gstage;
+          if (warp == 0) TRACE(ptr_, 0);
+          if (mine) mbar_wait(bar_empty + 8 * is, iph ^ 1);      // slot free (first pass returns immediately)
+          if (warp == 0) TRACE(ptr_, 1);
+          if (mine && lane == 0) {
+            uint32_t a_bytes = (uint32_t)tmaps.a_rows * BK * 4;   // (rows 64..127 may come from the A-half feeders: their bytes are not transaction bytes)
             if (tmaps.kind == TMA_CONV_WGRAD) {                  // only the 32-row slabs that lie inside the filter are loaded
               int live = 0;
 #pragma unroll
               for (int j = 0; j < 4; ++j) live += ((m0 + 32 * j) / tmaps.cin < tmaps.ntaps) ? 1 : 0;
               a_bytes = (uint32_t)(live * 4096);
             }
-            mbar_expect_tx(bar, a_bytes + (uint32_t)(L::TMA_B ? BN * BK * 4 : 0));
+            mbar_expect_tx(bar, (doA ? a_bytes : 0u) + (uint32_t)((L::TMA_B && doB) ? BN * BK * 4 : 0));
             if (tmaps.kind == TMA_CONV_FWD) {                    // k stage -> (tap row, tap column, first channel); one tap's 32 channels per stage
               // im2col-mode coordinates (measured, scripts/ubench/tma_probe.cu): {c, w, h, n} is the first base pixel in input coordinates
               // (ow*S, oh*S), the box walks base pixels by the map's traversal strides, wraps rows and images, zero-fills past the batch;
               // the 16-bit offsets are the filter tap
               const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;
-              tma_load_im2col_4d(a_st, &tmaps.a[zi], c0, pw * tmaps.stride, ph_ * tmaps.stride, pn, tw, th, bar);
-              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (doA) tma_load_im2col_4d(a_st, &tmaps.a[zi], c0, pw * tmaps.stride, ph_ * tmaps.stride, pn, tw, th, bar);
+              if (L::TMA_B && doB) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             } else if (tmaps.kind == TMA_DENSE_FWD) {
-              tma_load_2d(a_st, &tmaps.a[zi], k0, m0, bar);
-              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (doA) tma_load_2d(a_st, &tmaps.a[zi], k0, m0, bar);
+              if (L::TMA_B && doB) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             } else if (tmaps.kind == TMA_DENSE_WGRAD) {
-              tma_load_2d(a_st, &tmaps.a[zi], m0, k0, bar);
-              if (L::TMA_B) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (doA) tma_load_2d(a_st, &tmaps.a[zi], m0, k0, bar);
+              if (L::TMA_B && doB) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             } else if (tmaps.kind == TMA_DENSE_DGRAD) {          // k segments (towers) have their own delta / weight matrices
               const int sg = (tmaps.seg_k > 0 && k0 >= tmaps.seg_k) ? 1 : 0, kk = k0 - sg * tmaps.seg_k;
-              tma_load_2d(a_st, &tmaps.a[sg], kk, m0, bar);
-              if (L::TMA_B) tma_load_2d(b_hi, &tmaps.b[sg], kk, n0, bar);
+              if (doA) tma_load_2d(a_st, &tmaps.a[sg], kk, m0, bar);
+              if (L::TMA_B && doB) tma_load_2d(b_hi, &tmaps.b[sg], kk, n0, bar);
             } else if (tmaps.kind == TMA_CONV_DGRAD) {
               if constexpr (Op::Z_IS_CLASS) {
                 // class (ph, pw): row m = input pixel (n, a, b) of the class, k = (th, tw, co): source delta[n][a - th][b - tw][co].
@@ -500,32 +514,60 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
                 const int zc = zs / nsplit;
                 const int bq = m0 % op.BW, q = m0 / op.BW, aq = q % op.AH, nq = q / op.AH;
                 const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / op.TW, tw = tap - th * op.TW;
-                tma_load_im2col_4d(a_st, &tmaps.a[zc], c0, bq - (op.TW - 1), aq - (op.TH - 1), nq, op.TW - 1 - tw, op.TH - 1 - th, bar);
+                if (doA) tma_load_im2col_4d(a_st, &tmaps.a[zc], c0, bq - (op.TW - 1), aq - (op.TH - 1), nq, op.TW - 1 - tw, op.TH - 1 - th, bar);
                 const int khh = op.ph + th * tmaps.stride, kww = op.pw + tw * tmaps.stride;
-                tma_load_3d(b_hi, &tmaps.b[0], c0, n0, khh * tmaps.kw + kww, bar);
+                if (doB) tma_load_3d(b_hi, &tmaps.b[0], c0, n0, khh * tmaps.kw + kww, bar);
               }
             } else if (tmaps.kind == TMA_CONV_DGRAD_MERGED) {
               // rows (n, a, b) over the AH x BW blocks, k = (th, tw, co): the class-wise correlation with every class's columns side by side
               const int bq = m0 % tmaps.ow, q = m0 / tmaps.ow, aq = q % tmaps.oh, nq = q / tmaps.oh;          // (ow, oh hold BW, AH here)
               const int tap = k0 / tmaps.cin, c0 = k0 - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;   // (kw holds TW, ntaps TH)
-              tma_load_im2col_4d(a_st, &tmaps.a[0], c0, bq - (tmaps.kw - 1), aq - (tmaps.ntaps - 1), nq, tmaps.kw - 1 - tw, tmaps.ntaps - 1 - th, bar);
-              tma_load_3d(b_hi, &tmaps.b[0], 0, k0, n0 >> 5, bar);
+              if (doA) tma_load_im2col_4d(a_st, &tmaps.a[0], c0, bq - (tmaps.kw - 1), aq - (tmaps.ntaps - 1), nq, tmaps.kw - 1 - tw, tmaps.ntaps - 1 - th, bar);
+              if (doB) tma_load_3d(b_hi, &tmaps.b[0], 0, k0, n0 >> 5, bar);
             } else {                                             // conv wgrad: k = output pixel, m = (tap, channel)
               const int pw2 = k0 % tmaps.ow, q2 = k0 / tmaps.ow, ph2 = q2 % tmaps.oh, pn2 = q2 / tmaps.oh;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int mm = m0 + 32 * j, tap = mm / tmaps.cin, c0 = mm - tap * tmaps.cin, th = tap / tmaps.kw, tw = tap - th * tmaps.kw;
                 // rows past the last tap are never stored: leave their slab alone (and out of the byte count)
-                if (tap < tmaps.ntaps) tma_load_im2col_4d(a_st + j * 4096, &tmaps.a[zi], c0, pw2 * tmaps.stride, ph2 * tmaps.stride, pn2, tw, th, bar);
+                if (tap < tmaps.ntaps) if (doA) tma_load_im2col_4d(a_st + j * 4096, &tmaps.a[zi], c0, pw2 * tmaps.stride, ph2 * tmaps.stride, pn2, tw, th, bar);
               }
-              tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
+              if (doB) tma_load_3d(b_hi, &tmaps.b[zi], 0, k0, n0 >> 5, bar);
             }
           }
           __syncwarp();
-          TRACE(ptr_, 2);
+          if (warp == 0) TRACE(ptr_, 2);
           ++ptr_;
           if (++is == STAGES) { is = 0; iph ^= 1; }
         }
+      }
+    } else if (!A_MN && L::DB64 && warp >= AH_WARP0 && tmaps.a_rows == BM / 2) {
+      // ================= A-half feeders (warps 4-7): rows 64..127 of the A tile through cp.async, functor addresses, SWIZZLE_128B layout =================
+      if constexpr (!A_MN) {
+        const int h = tid - AH_WARP0 * 32, c = h & 7;            // 16-byte chunk c of rows 64 + h/8 + 16 i
+        int is = 0; uint32_t iph = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+          Op op; int m0, n0, zs, kt0, nk;
+          if (!decode(t, op, m0, n0, zs, kt0, nk)) continue;
+          ACtx actx[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) actx[i] = op.prepA(m0 + BM / 2 + (h >> 3) + 16 * i);
+          for (int it = 0; it < nk; ++it) {
+            const int k0 = (kt0 + it) * BK;
+            const uint32_t a_st = sbase + is * L::STAGE_BYTES;
+            const KCtx kc = op.prepK(k0 + c * 4);
+            mbar_wait(bar_empty + 8 * is, iph ^ 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = BM / 2 + (h >> 3) + 16 * i;
+              const float* p = op.ptrA(actx[i], kc, m0 + r, k0 + c * 4);
+              cp_async16(a_st + (uint32_t)(r * 128 + ((c ^ (r & 7)) * 16)), p ? p : zero_src, p ? 16u : 0u);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_landed + 8 * is) : "memory");
+            if (++is == STAGES) { is = 0; iph ^= 1; }
+          }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
     } else if (!L::TMA_B && warp <= TMA_BLD / 32) {
       // B stage: BN x 32 fp32 = BN * 8 chunks of 16 bytes over 64 threads, into the UMMA layout (same chunk map as the cp.async feed)
@@ -958,6 +1000,11 @@ struct TmaApi {
   }
 };
 inline TmaApi& tma_api() { static TmaApi a; return a; }
+// Option (off: measured slower, 0.383 vs 0.370 ms/step): half of the A tile (rows 64..127) from four otherwise idle warps through cp.async
+// (functor addresses, the same SWIZZLE_128B layout) instead of the TMA unit, whose ~4.2 cycles per box row bound the feed once two
+// producer threads keep it busy.  K-major A operands of BN = 64 launches; DQN_TC_AHELP=1 switches it on, the selftest covers it.
+inline int& a_helper_enabled() { static int v = 0; return v; }
+inline int a_tma_rows(int bn) { return (a_helper_enabled() && bn == 64 && TC_TMA64_NBUF == 2 && TC_TMA_B) ? 64 : BM; }
 // conv input gradients through the TMA feed.  With six accumulators per tile they lost to the cp.async feed (their act' epilogue - stored-
 // output loads at scattered pixel offsets - sat in front of the next tile: conv2 class-merged 48.1 vs 34.7 us, conv3 37.6 vs 35.4); with two
 // accumulator sets (DB64) the epilogue is off the main loop and the step is ~1 % faster with them (0.408 vs 0.412 ms).  DQN_TC_TMA_DGRAD=0
@@ -973,7 +1020,7 @@ inline bool tma_tiled_2d(CUtensorMap* m, const float* p, long long rows, long lo
   return tma_api().tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-inline bool tma_a_kmajor(CUtensorMap* m, const float* p, long long rows, long long kcols, long long ld) { return tma_tiled_2d(m, p, rows, kcols, ld, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B); }
+inline bool tma_a_kmajor(CUtensorMap* m, const float* p, long long rows, long long kcols, long long ld, int box_rows = BM) { return tma_tiled_2d(m, p, rows, kcols, ld, BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B); }
 inline bool tma_a_mnmajor(CUtensorMap* m, const float* p, long long krows, long long mcols, long long ld) { return tma_tiled_2d(m, p, krows, mcols, ld, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE); }
 inline bool tma_b_kmajor(CUtensorMap* m, const float* p, long long nrows, long long kcols, long long ld, int bn) { return tma_tiled_2d(m, p, nrows, kcols, ld, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B); }
 // [krows][ld] with ncols valid columns, n contiguous: {32 n, k, atoms of 32 n}
@@ -985,35 +1032,35 @@ inline bool tma_b_mnmajor(CUtensorMap* m, const float* p, long long krows, long 
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // NHWC fp32 activations [nimg][IH][IW][Cin] as an im2col-mode map: 128 output pixels x 32 channels of one filter tap per load
-inline bool tma_a_im2col(CUtensorMap* m, const float* p, int nimg, const dqn::ConvGeom& g) {
+inline bool tma_a_im2col(CUtensorMap* m, const float* p, int nimg, const dqn::ConvGeom& g, int box_rows = BM) {
   if (!tma_api().load() || (reinterpret_cast<uintptr_t>(p) & 15) || g.Cin % 32 != 0 || g.KH > 128 || g.KW > 128 || g.S > 8) return false;
   cuuint64_t gd[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)nimg};
   cuuint64_t gs[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.IW * g.Cin * 4, (cuuint64_t)g.IH * g.IW * g.Cin * 4};
   int lo[2] = {0, 0}, up[2] = {-(g.KW - 1), -(g.KH - 1)};       // no padding: base pixels keep the whole filter window inside the image
   cuuint32_t es[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
-  return tma_api().im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  return tma_api().im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), gd, gs, lo, up, 32, box_rows, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // operand sets of one launch -> maps; false = this launch stays on the cp.async feed
 inline bool tma_build(const dqn::DenseFwdOp* ops, int nops, int bn, TmaMaps& tm) {
-  tm.kind = TMA_DENSE_FWD;
+  tm.kind = TMA_DENSE_FWD; tm.a_rows = a_tma_rows(bn);
   for (int i = 0; i < nops; ++i)
-    if (!ops[i].Xs || !tma_a_kmajor(&tm.a[i], ops[i].Xs, ops[i].M, ops[i].K, ops[i].ldx) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], ops[i].Ws, ops[i].K, ops[i].N, ops[i].N, bn))) return false;
+    if (!ops[i].Xs || !tma_a_kmajor(&tm.a[i], ops[i].Xs, ops[i].M, ops[i].K, ops[i].ldx, tm.a_rows) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], ops[i].Ws, ops[i].K, ops[i].N, ops[i].N, bn))) return false;
   return true;
 }
 inline bool tma_build(const dqn::DenseDgradOp* ops, int nops, int bn, TmaMaps& tm) {
   if (nops != 1) return false;
   const dqn::DenseDgradOp& o = ops[0];
-  tm.kind = TMA_DENSE_DGRAD; tm.seg_k = o.K1;
+  tm.kind = TMA_DENSE_DGRAD; tm.seg_k = o.K1; tm.a_rows = a_tma_rows(bn);
   const int k0 = o.seg0();
   if (k0 % BK != 0) return false;
-  if (!tma_a_kmajor(&tm.a[0], o.Ds, o.M, k0, o.ldd) || (TC_TMA_B && !tma_b_kmajor(&tm.b[0], o.Ws, o.N, k0, k0, bn))) return false;
-  if (o.K1 > 0 && (!tma_a_kmajor(&tm.a[1], o.Ds2, o.M, o.K - o.K1, o.ldd2) || (TC_TMA_B && !tma_b_kmajor(&tm.b[1], o.Ws2, o.N, o.K - o.K1, o.K - o.K1, bn)))) return false;
+  if (!tma_a_kmajor(&tm.a[0], o.Ds, o.M, k0, o.ldd, tm.a_rows) || (TC_TMA_B && !tma_b_kmajor(&tm.b[0], o.Ws, o.N, k0, k0, bn))) return false;
+  if (o.K1 > 0 && (!tma_a_kmajor(&tm.a[1], o.Ds2, o.M, o.K - o.K1, o.ldd2, tm.a_rows) || (TC_TMA_B && !tma_b_kmajor(&tm.b[1], o.Ws2, o.N, o.K - o.K1, o.K - o.K1, bn)))) return false;
   return true;
 }
 inline bool tma_build(const dqn::DenseWgradOp* ops, int nops, int bn, TmaMaps& tm) {
-  tm.kind = TMA_DENSE_WGRAD;
+  tm.kind = TMA_DENSE_WGRAD; tm.a_rows = BM;
   for (int i = 0; i < nops; ++i) {
     if (!ops[i].no_bias || !ops[i].Xs) return false;            // the ones row of [x 1] is not a box: bias gradient by colsum_kernel
     if (!tma_a_mnmajor(&tm.a[i], ops[i].Xs, ops[i].K, ops[i].M, ops[i].ldx) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], ops[i].Ds, ops[i].K, ops[i].N, ops[i].ldd, bn))) return false;
@@ -1021,12 +1068,12 @@ inline bool tma_build(const dqn::DenseWgradOp* ops, int nops, int bn, TmaMaps& t
   return true;
 }
 inline bool tma_build(const dqn::ConvFwdOp* ops, int nops, int bn, TmaMaps& tm) {
-  tm.kind = TMA_CONV_FWD;
+  tm.kind = TMA_CONV_FWD; tm.a_rows = a_tma_rows(bn);
   for (int i = 0; i < nops; ++i) {
     const dqn::ConvFwdOp& o = ops[i];
     if (o.a8 || !o.Xs || o.g.Cin % 32 != 0) return false;
     if (i > 0 && (o.g.Cin != ops[0].g.Cin || o.g.KW != ops[0].g.KW || o.g.S != ops[0].g.S || o.g.OH != ops[0].g.OH || o.g.OW != ops[0].g.OW)) return false;
-    if (!tma_a_im2col(&tm.a[i], o.Xs, o.nimg, o.g) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], o.Ws, o.K, o.N, o.N, bn))) return false;
+    if (!tma_a_im2col(&tm.a[i], o.Xs, o.nimg, o.g, tm.a_rows) || (TC_TMA_B && !tma_b_mnmajor(&tm.b[i], o.Ws, o.K, o.N, o.N, bn))) return false;
   }
   tm.cin = ops[0].g.Cin; tm.kw = ops[0].g.KW; tm.stride = ops[0].g.S; tm.oh = ops[0].g.OH; tm.ow = ops[0].g.OW;
   return true;
@@ -1036,12 +1083,12 @@ inline bool tma_build(const dqn::ConvDgradMergedOp* ops, int nops, int bn, TmaMa
   const dqn::ConvDgradMergedOp& o = ops[0];
   const dqn::ConvGeom& g = o.g;
   if (!o.Ds || !o.Ws || g.Cout % 32 != 0 || o.N % 32 != 0 || o.TH > 16 || o.TW > 16 || (reinterpret_cast<uintptr_t>(o.Ds) & 15) || !tma_api().load()) return false;
-  tm.kind = TMA_CONV_DGRAD_MERGED; tm.cin = g.Cout; tm.kw = o.TW; tm.ntaps = o.TH; tm.oh = o.AH; tm.ow = o.BW; tm.stride = 1;
+  tm.kind = TMA_CONV_DGRAD_MERGED; tm.cin = g.Cout; tm.kw = o.TW; tm.ntaps = o.TH; tm.oh = o.AH; tm.ow = o.BW; tm.stride = 1; tm.a_rows = a_tma_rows(bn);
   cuuint64_t gd[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)o.nimg};
   cuuint64_t gs[3] = {(cuuint64_t)g.Cout * 4, (cuuint64_t)g.OW * g.Cout * 4, (cuuint64_t)g.OH * g.OW * g.Cout * 4};
   int lo[2] = {-(o.TW - 1), -(o.TH - 1)}, up[2] = {o.BW - o.TW - (g.OW - 1), o.AH - o.TH - (g.OH - 1)};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  if (tma_api().im2col(&tm.a[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (tma_api().im2col(&tm.a[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, tm.a_rows, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
   return tma_b_mnmajor(&tm.b[0], o.Ws, o.K, o.N, o.N, bn);
 }
@@ -1059,7 +1106,7 @@ inline bool tma_build(const dqn::ConvWgradOp* ops, int nops, int bn, TmaMaps& tm
   if (nops != 1) return false;
   const dqn::ConvWgradOp& o = ops[0];
   if (o.a8 || !o.no_bias || !o.Xs || o.g.Cin % 32 != 0 || o.N % 32 != 0) return false;
-  tm.kind = TMA_CONV_WGRAD; tm.a_slabs = 1;
+  tm.kind = TMA_CONV_WGRAD; tm.a_slabs = 1; tm.a_rows = BM;
   tm.cin = o.g.Cin; tm.kw = o.g.KW; tm.stride = o.g.S; tm.oh = o.g.OH; tm.ow = o.g.OW; tm.ntaps = o.g.KH * o.g.KW;
   return tma_a_im2col_wgrad(&tm.a[0], o.Xs, o.nimg, o.g) && tma_b_mnmajor(&tm.b[0], o.Ds, o.K, o.N, o.N, bn);
 }
@@ -1069,7 +1116,7 @@ inline bool tma_build(const dqn::ConvDgradOp* ops, int nops, int bn, TmaMaps& tm
   const dqn::ConvDgradOp& o = ops[0];
   const dqn::ConvGeom& g = o.g;
   if (!o.Ds || !o.Ws || g.Cout % 32 != 0 || g.S * g.S > 4 || (reinterpret_cast<uintptr_t>(o.Ds) & 15) || (reinterpret_cast<uintptr_t>(o.Ws) & 15) || !tma_api().load()) return false;
-  tm.kind = TMA_CONV_DGRAD; tm.cin = g.Cout; tm.kw = g.KW; tm.stride = g.S;
+  tm.kind = TMA_CONV_DGRAD; tm.cin = g.Cout; tm.kw = g.KW; tm.stride = g.S; tm.a_rows = a_tma_rows(bn);
   for (int z = 0; z < g.S * g.S; ++z) {
     dqn::ConvDgradOp c = o; c.set_class(z);
     if (c.TH < 1 || c.TW < 1 || c.AH < 1 || c.BW < 1 || c.TH > 16 || c.TW > 16) return false;
@@ -1078,7 +1125,7 @@ inline bool tma_build(const dqn::ConvDgradOp* ops, int nops, int bn, TmaMaps& tm
     // base pixels b' = b - (TW-1), b in [0, BW): from -(TW-1) to BW - TW = (OW - 1) + upper
     int lo[2] = {-(c.TW - 1), -(c.TH - 1)}, up[2] = {c.BW - c.TW - (g.OW - 1), c.AH - c.TH - (g.OH - 1)};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (tma_api().im2col(&tm.a[z], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, BM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (tma_api().im2col(&tm.a[z], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.Ds), gd, gs, lo, up, 32, tm.a_rows, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
   }
   // weights [(kh,kw)][Cin][Cout]: B(k = co, n = ci) of one tap is a K-major [Cin][Cout] slab
@@ -1235,6 +1282,7 @@ void tc_init(dqn_engine* e) {
   { const char* v = getenv("DQN_TC_TMA_WGRAD"); e->tc_tma_wgrad = v ? atoi(v) : 0; }
   { const char* v = getenv("DQN_DGRAD_MERGE"); e->dgrad_merge = v ? atoi(v) : 1; }
   { const char* v = getenv("DQN_TC_TMA_DGRAD"); tc::tma_conv_dgrad_enabled() = v ? atoi(v) : 1; }
+  { const char* v = getenv("DQN_TC_AHELP"); tc::a_helper_enabled() = v ? atoi(v) : 0; }
   for (size_t l = 1; l < e->convs.size() && l < DQN_MAX_LAYERS; ++l)
     if (dqn::ConvDgradMergedOp::geometry_ok(e->convs[l].g)) e->wm[l] = dalloc<float>((long long)e->convs[l].w.K * e->convs[l].g.Cout);
   long long off = 0;

@@ -287,7 +287,8 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
 }
 
 int main(int argc, char** argv) {
-  tc::tma_conv_dgrad_enabled() = 1;      // keep the TMA-fed conv input gradients covered (the engine leaves them on the cp.async feed)
+  tc::tma_conv_dgrad_enabled() = 1;      // keep the TMA-fed conv input gradients covered
+  { const char* v = getenv("DQN_TC_AHELP"); if (v) tc::a_helper_enabled() = atoi(v); }
   { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
     const int it = argc > 2 ? atoi(argv[2]) : 20;
