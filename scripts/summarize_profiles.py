@@ -65,7 +65,7 @@ def _expected(scope):
     if scope == "dgrad_merge_weights": return "dgrad_merge_weights_kernel"
     if scope == "splitk_reduce": return "splitk_reduce_kernel"
     if scope.startswith("heads_fwd"): return "heads_fwd_kernel"
-    if scope == "head_loss": return "head_loss_kernel"
+    if scope == "head_loss": return "head_loss"
     if scope == "heads_dgrad": return "heads_dgrad_kernel"
     if scope.endswith("_bgrad"): return "colsum_kernel"
     if scope == "adam": return "adam_kernel"
