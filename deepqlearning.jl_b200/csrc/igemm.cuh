@@ -166,6 +166,24 @@ struct KCtx { long long off; int t0, t1, t2; long long offb; };
 
 // ------------------------------------------------------------------------------------------------
 // Dense forward:  C[m][n] = act( sum_k X[m][k] W[k][n] + W[K][n] )
+// 256-bit global store (sm_100: STG.E.ENL2.256): a lane that owns 8 consecutive fp32 of an output row writes one whole 32-byte sector.
+// The tensor-core epilogue has one row per lane, so with 128-bit stores every store instruction touched 32 rows with half a sector each.
+DQN_HD void st_global_v8(float* p, const float4& a, const float4& b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+  reinterpret_cast<float4*>(p)[0] = a; reinterpret_cast<float4*>(p)[1] = b;
+#endif
+}
+DQN_HD void ld_global_v8(const float* p, float4& a, float4& b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+  a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1];
+#endif
+}
+DQN_HD bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
 struct DenseFwdOp {
   static constexpr bool HAS_A8 = false;      // can feed the tensor-core kernel from a byte tensor
   static constexpr bool A_MCONTIG = false, B_KCONTIG = false, Z_IS_CLASS = false;
@@ -210,6 +228,13 @@ struct DenseFwdOp {
   DQN_HD float4 epi_aux4(int, int n) const { return ldg4(W + (long long)K * N + n); }
   DQN_HD void store4x(int m, int n, float4 v, const float4& b) const {
     *reinterpret_cast<float4*>(C + (long long)m * ldc + n) = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
+  }
+  // eight consecutive columns (n % 8 == 0) in one 256-bit store
+  DQN_HD bool can_store8() const { return (N % 8 == 0) && (ldc % 8 == 0) && al32(C); }
+  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const { a = epi_aux4(m, n); b = epi_aux4(m, n + 4); }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& b, const float4& c) const {
+    st_global_v8(C + (long long)m * ldc + n, make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act)),
+                 make4(act_apply(u.x + c.x, act), act_apply(u.y + c.y, act), act_apply(u.z + c.z, act), act_apply(u.w + c.w, act)));
   }
 };
 
@@ -286,6 +311,17 @@ struct DenseDgradOp {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *o = v;
   }
+  DQN_HD bool can_store8() const { return !accumulate && (ldx % 8 == 0) && (N % 8 == 0) && al32(dX) && (!apply_act || ((ldy % 8 == 0) && al32(Y))); }
+  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
+    if (apply_act) ld_global_v8(Y + (long long)m * ldy + n, a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
+  }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
+    if (apply_act) {
+      v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
+      u.x *= act_deriv(z.x, act); u.y *= act_deriv(z.y, act); u.z *= act_deriv(z.z, act); u.w *= act_deriv(z.w, act);
+    }
+    st_global_v8(dX + (long long)m * ldx + n, v, u);
+  }
 };
 
 // Dense wgrad:  dW[m][n] = sum_k [X 1][k][m] D[k][n],  m in [0, Kin], k over the batch rows
@@ -337,6 +373,12 @@ struct DenseWgradOp {
   }
   DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
   DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
+  DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(dW); }
+  DQN_HD void epi_aux8(int, int, float4& a, float4& b) const { a = make4(0.f, 0.f, 0.f, 0.f); b = a; }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4&, const float4&) const {
+    const float sc = oscale(m);
+    st_global_v8(dW + (long long)m * N + n, make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc), make4(u.x * sc, u.y * sc, u.z * sc, u.w * sc));
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -422,6 +464,12 @@ struct ConvFwdOp {
   DQN_HD void store4x(int m, int n, float4 v, const float4& b) const {
     *reinterpret_cast<float4*>(Y + (long long)m * N + n) = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
   }
+  DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(Y); }
+  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const { a = epi_aux4(m, n); b = epi_aux4(m, n + 4); }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& b, const float4& c) const {
+    st_global_v8(Y + (long long)m * N + n, make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act)),
+                 make4(act_apply(u.x + c.x, act), act_apply(u.y + c.y, act), act_apply(u.z + c.z, act), act_apply(u.w + c.w, act)));
+  }
 };
 
 // Conv wgrad: dW[m][co] = sum_pix [im2col(X) 1][pix][m] D[pix][co];  m = (kh,kw,ci) or the bias row
@@ -496,6 +544,12 @@ struct ConvWgradOp {
   }
   DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
   DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
+  DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(dW); }
+  DQN_HD void epi_aux8(int, int, float4& a, float4& b) const { a = make4(0.f, 0.f, 0.f, 0.f); b = a; }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4&, const float4&) const {
+    const float sc = oscale(m);
+    st_global_v8(dW + (long long)m * N + n, make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc), make4(u.x * sc, u.y * sc, u.z * sc, u.w * sc));
+  }
 };
 
 // Conv dgrad by stride-parity class (ph,pw): rows are the input pixels with ih%S==ph, iw%S==pw, and only
@@ -602,6 +656,17 @@ struct ConvDgradOp {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
   }
+  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX) && (!apply_act || al32(Yprev)); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
+  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
+    if (apply_act) ld_global_v8(Yprev + out_off(m, n), a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
+  }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
+    if (apply_act) {
+      v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
+      u.x *= act_deriv(z.x, act); u.y *= act_deriv(z.y, act); u.z *= act_deriv(z.z, act); u.w *= act_deriv(z.w, act);
+    }
+    st_global_v8(dX + out_off(m, n), v, u);
+  }
 };
 
 
@@ -679,6 +744,17 @@ struct ConvDgradMergedOp {
   DQN_HD void store4x(int m, int n, float4 v, const float4& y) const {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
+  }
+  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX) && (!apply_act || al32(Yprev)); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
+  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
+    if (apply_act) ld_global_v8(Yprev + out_off(m, n), a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
+  }
+  DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
+    if (apply_act) {
+      v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
+      u.x *= act_deriv(z.x, act); u.y *= act_deriv(z.y, act); u.z *= act_deriv(z.z, act); u.w *= act_deriv(z.w, act);
+    }
+    st_global_v8(dX + out_off(m, n), v, u);
   }
 };
 #ifdef __CUDACC__

@@ -155,6 +155,9 @@ template <int BN, int R, int NBUF, bool A_MN, bool B_MN, bool A8 = false, bool T
 #ifndef TC_MAX_STAGES
 #define TC_MAX_STAGES 12
 #endif
+#ifndef TC_ST8
+#define TC_ST8 1                   // epilogue: 256-bit stores (one sector per lane) where the output row allows it
+#endif
 #ifndef TC_PSPLIT
 #define TC_PSPLIT 1                // TMA feed: two producer threads on alternate stages
 #endif
@@ -826,6 +829,7 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
       // round trips per chunk - 6800 cycles per tile in the stage trace, a third of the kernel.  (Registers: the launch bound of 1024
       // threads caps ptxas at 64 per thread, so only the chunk in flight is held.)
       const bool vec = m < op.M && !part && op.can_store4();
+      const bool st8 = TC_ST8 && op.can_store8() && (n0 & 7) == 0;
       if (q4 == 0) TRACE(etr, 12);
       mbar_wait(bar_accf + 8 * buf, aph);
       if (q4 == 0) TRACE(etr, 13);
@@ -848,8 +852,11 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
             tmem_ld16_nowait(tb + a * BN + c0, q[a - 1]);
           }
           if (vec && n0 + c0 + 15 < op.N) {
+            if (st8) { op.epi_aux8(m, n0 + c0, aux[0], aux[1]); op.epi_aux8(m, n0 + c0 + 8, aux[2], aux[3]); }
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
+              for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
+            }
           }
           if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 0);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -864,20 +871,38 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = 0u;
           if (vec && n0 + c0 + 15 < op.N) {
+            if (st8) { op.epi_aux8(m, n0 + c0, aux[0], aux[1]); op.epi_aux8(m, n0 + c0 + 8, aux[2], aux[3]); }
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
+              for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
+            }
           }
         }
         if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 2);
         if (m < op.M) {
           if (vec && n0 + c0 + 15 < op.N) {
+            if (st8) {                                           // one whole 32-byte sector per lane and store (see st_global_v8)
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              op.store4x(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), aux[j >> 2]);
+              for (int j = 0; j < 16; j += 8)
+                op.store8x(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
+                           make4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])), aux[j >> 2], aux[(j >> 2) + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                op.store4x(m, n0 + c0 + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), aux[j >> 2]);
+            }
           } else if (part && (op.N & 3) == 0 && n0 + c0 + 15 < op.N) {
-            float4* wp = reinterpret_cast<float4*>(ws + (long long)zs * ws_stride + mrel * op.N + n0 + c0);
+            float* wq = ws + (long long)zs * ws_stride + mrel * op.N + n0 + c0;
+            if (dqn::al32(wq)) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) wp[j >> 2] = make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              for (int j = 0; j < 16; j += 8)
+                dqn::st_global_v8(wq + j, make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
+                                  make4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])));
+            } else {
+              float4* wp = reinterpret_cast<float4*>(wq);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) wp[j >> 2] = make4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {

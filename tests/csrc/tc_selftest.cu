@@ -286,12 +286,51 @@ template <int BN> static void bench_dense(int M, int N, int K, int iters) {
   cudaFree(dW); cudaFree(dC); cudaFree(ar.d);
 }
 
+// timing of a dense weight gradient [x]^T delta (both operands MN-major) at the fc1 shape: features x units x batch rows - tuning aid
+template <int BN> static void bench_dense_wgrad(int feat, int units, int rows, int iters) {
+  Arena ar; ar.init(64 << 20);
+  std::vector<float> X((size_t)rows * feat, 0.5f), D((size_t)rows * units, 0.25f);
+  long long oX = ar.put(X), oD = ar.put(D), oOnes = ar.put(std::vector<float>{1.f, 0.f, 0.f, 0.f}, true);
+  ar.upload();
+  float* dG; CKC(cudaMalloc(&dG, (size_t)(feat + 1) * units * 4));
+  DenseWgradOp g{}; g.X = nullptr; g.ldx = feat; g.D = nullptr; g.ldd = units; g.M = feat + 1; g.N = units; g.K = rows; g.vecA = g.vecB = 1;
+  if (g_feed == 1) { g.no_bias = 1; g.M = feat; }
+  g.dW = dG; g.Xs = ar.d + oX; g.Ds = ar.d + oD; g.ones = ar.d + oOnes; g.lo_delta = ar.plane;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  run_tc<BN>(g, 1, 1, nullptr, 0, ar.d);
+  cudaEventRecord(a);
+  for (int i = 0; i < iters; ++i) launch_tc_raw<BN>(g, 1, 1, nullptr, 0, ar.d);
+  cudaEventRecord(b); CKC(cudaEventSynchronize(b));
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  const double us = 1e3 * ms / iters, tf = 2.0 * g.M * g.N * g.K / (us * 1e-6) / 1e12;
+#ifdef TC_TRACE
+  {
+    std::vector<long long> tr(16384);
+    CKC(cudaMemcpyFromSymbol(tr.data(), tc::tc_trace, sizeof(long long) * 16384));
+    const long long t0 = tr[0];
+    for (int it = 0; it < 20; ++it) {
+      printf("  %2d:", it);
+      for (int j = 0; j < 15; ++j) { if (j == 3 || j == 8 || j == 12) printf(" |"); printf(" %6lld", tr[it * 16 + j] ? tr[it * 16 + j] - t0 : -1); }
+      printf("\n");
+    }
+    std::vector<long long> z(16384, 0); CKC(cudaMemcpyToSymbol(tc::tc_trace, z.data(), sizeof(long long) * 16384));
+  }
+#endif
+  printf("bench dense wgrad %s feat=%d units=%d rows=%d BN=%d: %.1f us  %.1f TFLOP/s algorithmic  tiles %d\n", g_last_tma ? "[tma]" : "[cpa]", feat, units, rows, BN, us, tf,
+         ((g.M + 127) / 128) * ((units + BN - 1) / BN));
+  cudaFree(dG); cudaFree(ar.d);
+}
+
 int main(int argc, char** argv) {
   tc::tma_conv_dgrad_enabled() = 1;      // keep the TMA-fed conv input gradients covered
   { const char* v = getenv("DQN_TC_AHELP"); if (v) tc::a_helper_enabled() = atoi(v); }
   { cudaDeviceProp pr; CKC(cudaGetDeviceProperties(&pr, 0)); g_nsm = pr.multiProcessorCount; }
   if (argc > 1) {
     const int it = argc > 2 ? atoi(argv[2]) : 20;
+    if (argc > 3 && argv[3][0] == 'w') {
+      for (g_feed = 0; g_feed < 2; ++g_feed) bench_dense_wgrad<64>(3136, 512, 256, it);
+      return 0;
+    }
     if (argc > 3 && argv[3][0] == 'd') {
       for (g_feed = 0; g_feed < 2; ++g_feed) { bench_conv_dgrad(256, 20, 20, 32, 64, 4, 2, it); bench_conv_dgrad(256, 9, 9, 64, 64, 3, 1, it); }
       return 0;
