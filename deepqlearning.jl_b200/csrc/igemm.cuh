@@ -175,13 +175,6 @@ DQN_HD void st_global_v8(float* p, const float4& a, const float4& b) {
   reinterpret_cast<float4*>(p)[0] = a; reinterpret_cast<float4*>(p)[1] = b;
 #endif
 }
-DQN_HD void ld_global_v8(const float* p, float4& a, float4& b) {
-#ifdef __CUDA_ARCH__
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-#else
-  a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1];
-#endif
-}
 DQN_HD bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 
 struct DenseFwdOp {
@@ -231,7 +224,6 @@ struct DenseFwdOp {
   }
   // eight consecutive columns (n % 8 == 0) in one 256-bit store
   DQN_HD bool can_store8() const { return (N % 8 == 0) && (ldc % 8 == 0) && al32(C); }
-  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const { a = epi_aux4(m, n); b = epi_aux4(m, n + 4); }
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& b, const float4& c) const {
     st_global_v8(C + (long long)m * ldc + n, make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act)),
                  make4(act_apply(u.x + c.x, act), act_apply(u.y + c.y, act), act_apply(u.z + c.z, act), act_apply(u.w + c.w, act)));
@@ -311,10 +303,7 @@ struct DenseDgradOp {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *o = v;
   }
-  DQN_HD bool can_store8() const { return !accumulate && (ldx % 8 == 0) && (N % 8 == 0) && al32(dX) && (!apply_act || ((ldy % 8 == 0) && al32(Y))); }
-  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
-    if (apply_act) ld_global_v8(Y + (long long)m * ldy + n, a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
-  }
+  DQN_HD bool can_store8() const { return !accumulate && (ldx % 8 == 0) && (N % 8 == 0) && al32(dX); }
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
     if (apply_act) {
       v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
@@ -374,7 +363,6 @@ struct DenseWgradOp {
   DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
   DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
   DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(dW); }
-  DQN_HD void epi_aux8(int, int, float4& a, float4& b) const { a = make4(0.f, 0.f, 0.f, 0.f); b = a; }
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4&, const float4&) const {
     const float sc = oscale(m);
     st_global_v8(dW + (long long)m * N + n, make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc), make4(u.x * sc, u.y * sc, u.z * sc, u.w * sc));
@@ -465,7 +453,6 @@ struct ConvFwdOp {
     *reinterpret_cast<float4*>(Y + (long long)m * N + n) = make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act));
   }
   DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(Y); }
-  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const { a = epi_aux4(m, n); b = epi_aux4(m, n + 4); }
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& b, const float4& c) const {
     st_global_v8(Y + (long long)m * N + n, make4(act_apply(v.x + b.x, act), act_apply(v.y + b.y, act), act_apply(v.z + b.z, act), act_apply(v.w + b.w, act)),
                  make4(act_apply(u.x + c.x, act), act_apply(u.y + c.y, act), act_apply(u.z + c.z, act), act_apply(u.w + c.w, act)));
@@ -545,7 +532,6 @@ struct ConvWgradOp {
   DQN_HD float4 epi_aux4(int, int) const { return make4(0.f, 0.f, 0.f, 0.f); }
   DQN_HD void store4x(int m, int n, float4 v, const float4&) const { store4(m, n, v); }
   DQN_HD bool can_store8() const { return (N % 8 == 0) && al32(dW); }
-  DQN_HD void epi_aux8(int, int, float4& a, float4& b) const { a = make4(0.f, 0.f, 0.f, 0.f); b = a; }
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4&, const float4&) const {
     const float sc = oscale(m);
     st_global_v8(dW + (long long)m * N + n, make4(v.x * sc, v.y * sc, v.z * sc, v.w * sc), make4(u.x * sc, u.y * sc, u.z * sc, u.w * sc));
@@ -656,10 +642,7 @@ struct ConvDgradOp {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
   }
-  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX) && (!apply_act || al32(Yprev)); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
-  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
-    if (apply_act) ld_global_v8(Yprev + out_off(m, n), a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
-  }
+  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
     if (apply_act) {
       v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);
@@ -745,10 +728,7 @@ struct ConvDgradMergedOp {
     if (apply_act) { v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act); }
     *reinterpret_cast<float4*>(dX + out_off(m, n)) = v;
   }
-  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX) && (!apply_act || al32(Yprev)); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
-  DQN_HD void epi_aux8(int m, int n, float4& a, float4& b) const {
-    if (apply_act) ld_global_v8(Yprev + out_off(m, n), a, b); else { a = make4(1.f, 1.f, 1.f, 1.f); b = a; }
-  }
+  DQN_HD bool can_store8() const { return (g.Cin % 8 == 0) && al32(dX); }      // columns n..n+7 (n % 8 == 0) are channels of one pixel
   DQN_HD void store8x(int m, int n, float4 v, float4 u, const float4& y, const float4& z) const {
     if (apply_act) {
       v.x *= act_deriv(y.x, act); v.y *= act_deriv(y.y, act); v.z *= act_deriv(y.z, act); v.w *= act_deriv(y.w, act);

@@ -852,11 +852,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
             tmem_ld16_nowait(tb + a * BN + c0, q[a - 1]);
           }
           if (vec && n0 + c0 + 15 < op.N) {
-            if (st8) { op.epi_aux8(m, n0 + c0, aux[0], aux[1]); op.epi_aux8(m, n0 + c0 + 8, aux[2], aux[3]); }
-            else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
-            }
+            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
           }
           if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 0);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -871,11 +868,8 @@ tc_gemm_kernel(const __grid_constant__ Op opa, const __grid_constant__ Op opb, c
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = 0u;
           if (vec && n0 + c0 + 15 < op.N) {
-            if (st8) { op.epi_aux8(m, n0 + c0, aux[0], aux[1]); op.epi_aux8(m, n0 + c0 + 8, aux[2], aux[3]); }
-            else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
-            }
+            for (int j = 0; j < 4; ++j) aux[j] = op.epi_aux4(m, n0 + c0 + 4 * j);
           }
         }
         if (q4 == 0 && etr == 0) ETRACE(c0 / 16, 2);
