@@ -154,6 +154,7 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   } else if (warp >= WARP_EPI0) {
     // ===== epilogue: (hi + hi') + (lo + lo') + bias -> activation -> 128-byte rows =====
     const int q4 = warp & 3;
+    const bool st8 = dqn::al32(p.Y);
     int buf = 0; uint32_t ph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int m = t * BM + q4 * 32 + lane;
@@ -171,6 +172,7 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < p.M) {
           float* out = p.Y + (long long)m * COUT + c0;
+          float4 o4[4];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 b = bq[j >> 2];
@@ -181,8 +183,12 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
               const float lo = __fadd_rn(__uint_as_float(hl0[j + u]), __uint_as_float(hl1[j + u]));
               y[u] = __fadd_rn(hi, lo);
             }
-            *reinterpret_cast<float4*>(out + j) = make4(dqn::act_apply(y[0] + b.x, p.act), dqn::act_apply(y[1] + b.y, p.act),
-                                                       dqn::act_apply(y[2] + b.z, p.act), dqn::act_apply(y[3] + b.w, p.act));
+            o4[j >> 2] = make4(dqn::act_apply(y[0] + b.x, p.act), dqn::act_apply(y[1] + b.y, p.act), dqn::act_apply(y[2] + b.z, p.act), dqn::act_apply(y[3] + b.w, p.act));
+          }
+          if (st8) { dqn::st_global_v8(out, o4[0], o4[1]); dqn::st_global_v8(out + 8, o4[2], o4[3]); }     // whole sectors (see igemm.cuh)
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(out)[j] = o4[j];
           }
         }
       }
