@@ -1530,7 +1530,7 @@ int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float
           CK(cudaEventRecord(h->main_mark, h->stream)); CK(cudaStreamWaitEvent(is, h->main_mark, 0)); h->main_dirty = false;
         }
         // the step in flight (if any) must have gathered its rows and refreshed its priorities: it says so in device memory (tree epoch)
-        epoch_wait_kernel<<<1, 32, 0, is>>>(h->st, (unsigned int)h->n_launched);
+        epoch_wait_kernel<<<1, 32, 0, is>>>(h->st, h->n_launched);
         CK(cudaGetLastError());
       }
       CK(cudaStreamWaitEvent(is, h->copy_done, 0));

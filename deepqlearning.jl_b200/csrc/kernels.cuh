@@ -17,9 +17,11 @@ struct DevState {
   float loss;                     // loss_val SOLVER:223-224
   int error;                      // sticky error flags raised by kernels (bit 0: sampler did not converge,
                                   //   bit 1: non-positive priority PER:78, bit 2: td0+eps <= 0 PER:66, bit 3: bad action)
-  unsigned int step;              // gradient steps finished so far: step s publishes its scalars to host slot s & 1
-  unsigned int tree_epoch;        // s once step s has gathered its rows and refreshed its priorities: from then on it touches neither the
-  unsigned int pad;               //   replay rows nor the tree, and new transitions may be ingested beside the rest of it (epoch_wait_kernel)
+  int pad;
+  unsigned long long step;        // gradient steps finished so far: step s publishes its scalars to host slot s & 1  (64-bit: a 32-bit
+                                  //   counter wraps after 18 days at 2700 steps/s, and the epochs below must never decrease)
+  unsigned long long tree_epoch;  // s once step s has gathered its rows and refreshed its priorities: from then on it touches neither the
+                                  //   replay rows nor the tree, and new transitions may be ingested beside the rest of it (epoch_wait_kernel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -282,28 +284,28 @@ __global__ void tree_update_kernel(float* __restrict__ tree, int P, const long l
   }
   if (publish_epoch && j == 0) {          // (all levels are written: the barrier above closed the last one)
     __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->tree_epoch), "r"(st->step + 1u) : "memory");
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&st->tree_epoch), "l"(st->step + 1ULL) : "memory");
   }
   if (end_of_step && j == 0) {
     st->b1p *= beta1; st->b2p *= beta2;
     if (advance_sampler) st->sample_call += 1;
-    const unsigned int s = ++st->step;
+    const unsigned long long s = ++st->step;
     if (publish) {      // scalars of the finished step -> mapped pinned host words (loss, grad_norm, error flags, step), two slots:
       publish += 4 * (s & 1);           // the host may read step s while step s+1 runs (dqn_step_result)
       publish[0] = st->loss; publish[1] = __uint_as_float(st->gradmax_bits); reinterpret_cast<int*>(publish)[2] = st->error;
-      reinterpret_cast<unsigned int*>(publish)[3] = s;
+      reinterpret_cast<unsigned int*>(publish)[3] = (unsigned int)s;
     }
   }
 }
 
 // First kernel of an ingest on the ingest lane: returns once step `expected` (the one in flight when dqn_replay_add was called) has
 // published its tree epoch.  One warp, sleeping between polls: it shares an SM with a persistent GEMM CTA without taking anything from it.
-__global__ void epoch_wait_kernel(DevState* st, unsigned int expected) {
+__global__ void epoch_wait_kernel(DevState* st, unsigned long long expected) {
   if (threadIdx.x != 0) return;
   const long long t0 = clock64();
   while (true) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->tree_epoch) : "memory");
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&st->tree_epoch) : "memory");
     if (v >= expected) break;
     if (clock64() - t0 > 240000000000LL) { atomicOr(&st->error, 32); break; }   // ~2 min: the step in flight may itself be waiting for a peer rank
     __nanosleep(200);
