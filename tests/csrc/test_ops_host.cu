@@ -141,8 +141,48 @@ static void test_fastdiv_and_u8() {
   printf("ok   fastdiv/u8\n");
 }
 
+// The 8-column epilogue store of an op writes exactly what its two 4-column stores write (host path of st_global_v8: two float4 stores).
+static void test_store8() {
+  const int M = 5, N = 16, K = 8;
+  {
+    std::vector<float> W((K + 1) * N), c4(M * N, -7.f), c8(M * N, -7.f);
+    for (size_t i = 0; i < W.size(); ++i) W[i] = 0.01f * (float)i - 0.3f;
+    alignas(32) static float buf4[5 * 16], buf8[5 * 16];
+    DenseFwdOp o{}; o.W = W.data(); o.ldc = N; o.act = ACT_RELU; o.M = M; o.N = N; o.K = K;
+    for (int pass = 0; pass < 2; ++pass) {
+      o.C = pass ? buf8 : buf4;
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; n += 8) {
+          const float4 v = make4(m - 0.25f * n, 0.5f * n - m, 1.f + n, -2.f * m), u = make4(0.125f * (m + n), 3.f - m, n * 0.75f, -1.f - m);
+          const float4 x = o.epi_aux4(m, n), y = o.epi_aux4(m, n + 4);
+          if (pass) o.store8x(m, n, v, u, x, y); else { o.store4x(m, n, v, x); o.store4x(m, n + 4, u, y); }
+        }
+    }
+    double d = 0; for (int i = 0; i < M * N; ++i) d = std::fmax(d, std::fabs((double)buf4[i] - buf8[i]));
+    if (!o.can_store8() || d != 0) { printf("FAIL store8 dense fwd %g\n", d); ++fails; } else printf("ok   store8 dense fwd\n");
+  }
+  {
+    ConvGeom g{}; g.IH = 6; g.IW = 6; g.Cin = 8; g.KH = 4; g.KW = 4; g.S = 2; g.OH = 2; g.OW = 2; g.Cout = 8; g.init();
+    alignas(32) static float x4[6 * 6 * 8], x8[6 * 6 * 8], yp[6 * 6 * 8];
+    for (int i = 0; i < 6 * 6 * 8; ++i) { x4[i] = x8[i] = -7.f; yp[i] = (i % 3 == 0) ? 0.f : 0.5f; }
+    ConvDgradMergedOp o{}; o.dX = x4; o.Yprev = yp; o.act = ACT_RELU; o.apply_act = 1; o.nimg = 1; o.g = g; o.init();
+    for (int pass = 0; pass < 2; ++pass) {
+      o.dX = pass ? x8 : x4;
+      for (int m = 0; m < o.M; ++m)
+        for (int n = 0; n < o.N; n += 8) {
+          const float4 v = make4(m + 1.f, n - 2.f, 0.5f * m, 0.25f * n), u = make4(-1.f * m, 2.f + n, 1.5f, m * n * 0.125f);
+          const float4 x = o.epi_aux4(m, n), y = o.epi_aux4(m, n + 4);
+          if (pass) o.store8x(m, n, v, u, x, y); else { o.store4x(m, n, v, x); o.store4x(m, n + 4, u, y); }
+        }
+    }
+    double d = 0; for (int i = 0; i < 6 * 6 * 8; ++i) d = std::fmax(d, std::fabs((double)x4[i] - x8[i]));
+    if (!o.can_store8() || d != 0) { printf("FAIL store8 merged conv dgrad %g\n", d); ++fails; } else printf("ok   store8 merged conv dgrad\n");
+  }
+}
+
 int main() {
   test_fastdiv_and_u8();
+  test_store8();
   test_dgrad_two_towers(9, 20, 8, 12);
   test_dgrad_two_towers(5, 7, 4, 8);
   test_dense(7, 12, 8, ACT_RELU, false);
