@@ -123,7 +123,10 @@ int dqn_sync_target(dqn_engine_t* h);                            /* Flux.loadpar
 int dqn_get_adam_state(dqn_engine_t* h, float* m_flat, float* v_flat, double beta_pow[2], int64_t n);
 
 /* ---- replay writes: add_exp! (PER:65-74; callers SOLVER:88-95, PER:121-122) ------------------------ */
-/* n transitions appended at the ring cursor; priority (td0+eps)^alpha; DQN_ERR_STATE if td0+eps <= 0. */
+/* n transitions appended at the ring cursor; priority (td0+eps)^alpha; DQN_ERR_STATE if td0+eps <= 0.
+ * The call returns when the caller's buffers have been copied (its own copy stream); the ring / sum-tree writes run asynchronously, in
+ * program order with every other call on the handle - if a step is in flight (dqn_train_step_async) they are ordered behind that step's
+ * priority update, not behind the whole step, so add + async step + dqn_step_result(back = 1) keeps the GPU busy between steps. */
 int dqn_replay_add(dqn_engine_t* h, const void* s, const int32_t* a, const float* r, const void* sp,
                    const uint8_t* done, const float* td0, int64_t n);
 int dqn_replay_add_device(dqn_engine_t* h, const void* s, const int32_t* a, const float* r, const void* sp,
