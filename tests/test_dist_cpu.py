@@ -70,3 +70,20 @@ def test_control_plane_world2_gloo():
         assert p.exitcode == 0
     got = sorted(out.get(timeout=5) for _ in range(2))
     assert got == [(0, True), (1, True)]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference --gpus 2` launched as the driver launches it (torchrun, 2 ranks, no GPU needed): rank 0 alone times the
+    CPU restatement and prints ONE JSON line with the contract's keys; the other rank exits 0 without work."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "3", "--buffer", "4096"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "dqn_gradient_steps_per_sec" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "configs[2]" in d["config"]["workload"]
